@@ -1,0 +1,558 @@
+// C ABI (include/xs_b200.h) and host-side orchestration of the exhaustive matcher.
+//
+// Data in HBM per index:  db32 [n][d_pad] fp32 (exact operand), db16 [n_pad][d_pad] bf16 (coarse
+// operand, n_pad = multiple of 256 so TMA boxes never straddle the end), a grow-only workspace
+// (query copies, score rows, candidate pools, results).  One search = prep_queries -> coarse
+// kernel (batch-1 scan | tcgen05 GEMM with fused top-K) -> finalise (exact rescoring + sort),
+// all on one stream; uncertified queries are re-run on the exact fp32 path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xs_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+using namespace xs;
+
+// ---- errors ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); \
+    return fail(e_ == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+#define XS_TRY(expr) do { int r_ = (expr); if (r_ != XS_OK) return r_; } while (0)
+
+// ---- workspace buffers -------------------------------------------------------------------------------
+struct Buf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t need) {
+        if (need <= cap) return XS_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = need + need / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, need); want = need; }
+        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return fail(XS_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); }
+        cap = want;
+        return XS_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct xs_index {
+    int device = 0; int num_sms = 0;
+    int64_t n = 0, n_pad = 0, id_offset = 0;
+    int d = 0, d_pad = 0;
+    __nv_bfloat16* db16 = nullptr; float* db32 = nullptr; DevStats* dstats = nullptr;
+    CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
+    // tunables
+    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0;
+    // workspace
+    Buf q_raw, q32, q16, eps, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    std::mutex mu;
+    xs_stats stats{};
+    int64_t bytes = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encoder() {
+    if (g_encode) return XS_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(XS_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return XS_OK;
+}
+
+// 2-D bf16 tensor [rows][d_pad], box {64 columns, box_rows}, 128-byte swizzle (what umma_desc_sw128 expects).
+static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d_pad, int box_rows) {
+    XS_TRY(get_encoder());
+    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(XS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return XS_OK;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- ABI: misc -----------------------------------------------------------------------------------------
+extern "C" const char* xs_last_error(void) { return g_err.c_str(); }
+extern "C" int xs_abi_version(void) { return 1; }
+extern "C" int xs_device_count(int* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { cudaGetLastError(); if (count) *count = 0; return fail(XS_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    if (count) *count = c;
+    return XS_OK;
+}
+
+// ---- index lifecycle -------------------------------------------------------------------------------------
+static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_offset) {
+    if (n <= 0 || d <= 0) return fail(XS_ERR_ARG, "empty database (n=%lld, d=%d)", (long long)n, d);
+    if (n >= (int64_t)0xFFFFFF00u) return fail(XS_ERR_UNSUPPORTED, "more than 2^32-256 rows per index; shard the database");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(XS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    ix->device = device; ix->num_sms = prop.multiProcessorCount;
+    ix->n = n; ix->d = d; ix->id_offset = id_offset;
+    ix->d_pad = (int)round_up(d, COL_ALIGN);
+    ix->n_pad = round_up(n, ROW_ALIGN);
+    const size_t b32 = (size_t)n * ix->d_pad * sizeof(float), b16 = (size_t)ix->n_pad * ix->d_pad * 2;
+    CU_TRY(cudaMalloc(&ix->db32, b32));
+    CU_TRY(cudaMalloc(&ix->db16, b16));
+    CU_TRY(cudaMalloc(&ix->dstats, sizeof(DevStats)));
+    ix->bytes = (int64_t)(b32 + b16);
+    CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& e : ix->ev) CU_TRY(cudaEventCreate(&e));
+    CU_TRY(cudaMemsetAsync(ix->dstats, 0, sizeof(DevStats), ix->stream));
+    // zero the padding rows of the bf16 copy (they are read by TMA boxes and by the scan's row groups)
+    if (ix->n_pad > n) CU_TRY(cudaMemsetAsync(ix->db16 + (size_t)n * ix->d_pad, 0, (size_t)(ix->n_pad - n) * ix->d_pad * 2, ix->stream));
+    XS_TRY(make_tmap(&ix->tmap_db_b, ix->db16, ix->n_pad, ix->d_pad, GEMM_BN));
+    XS_TRY(make_tmap(&ix->tmap_db_a, ix->db16, ix->n_pad, ix->d_pad, GEMM_BM));
+    return XS_OK;
+}
+
+static void index_free(xs_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+                   &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
+    if (ix->db16) cudaFree(ix->db16);
+    if (ix->db32) cudaFree(ix->db32);
+    if (ix->dstats) cudaFree(ix->dstats);
+    for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    cudaGetLastError();
+    delete ix;
+}
+
+// Copies `rows` rows starting at r0 of a strided host matrix into a dense device tile.
+//   column-major source (stride_row == 1): tile is [d][rows]   (pitch = rows)
+//   row-major source    (stride_col == 1): tile is [rows][d]   (pitch = d)
+static int stage_host_rows(const void* src, int dtype, bool colmajor, int64_t stride, int64_t r0, int64_t rows,
+                           int d, void* tile, cudaStream_t st) {
+    const size_t es = dtype == XS_F64 ? 8 : 4;
+    const char* s = static_cast<const char*>(src);
+    if (colmajor)   // stride = elements between consecutive columns
+        CU_TRY(cudaMemcpy2DAsync(tile, (size_t)rows * es, s + (size_t)r0 * es, (size_t)stride * es, (size_t)rows * es, (size_t)d,
+                                 cudaMemcpyHostToDevice, st));
+    else            // stride = elements between consecutive rows
+        CU_TRY(cudaMemcpy2DAsync(tile, (size_t)d * es, s + (size_t)r0 * stride * es, (size_t)stride * es, (size_t)d * es, (size_t)rows,
+                                 cudaMemcpyHostToDevice, st));
+    return XS_OK;
+}
+
+static int check_layout(int dtype, int64_t rows, int d, int64_t stride_row, int64_t stride_col, bool* colmajor) {
+    if (dtype != XS_F32 && dtype != XS_F64) return fail(XS_ERR_ARG, "dtype must be XS_F32 or XS_F64");
+    if (stride_col == 1 && stride_row >= d) { *colmajor = false; return XS_OK; }
+    if (stride_row == 1 && stride_col >= rows) { *colmajor = true; return XS_OK; }
+    if (rows == 1 && stride_col == 1) { *colmajor = false; return XS_OK; }
+    return fail(XS_ERR_ARG, "unsupported strides (row %lld, col %lld): pass a row-major matrix or the F-order view vecs.T",
+                (long long)stride_row, (long long)stride_col);
+}
+
+extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int64_t stride_row, int64_t stride_col,
+                               int device, int renormalise, int64_t id_offset, xs_index** out) {
+    if (!db || !out) return fail(XS_ERR_ARG, "null pointer");
+    bool colmajor = false;
+    XS_TRY(check_layout(dtype, n, d, stride_row, stride_col, &colmajor));
+    xs_index* ix = new xs_index();
+    int rc = index_alloc(ix, n, d, device, id_offset);
+    if (rc != XS_OK) { index_free(ix); return rc; }
+    const size_t es = dtype == XS_F64 ? 8 : 4;
+    const int64_t chunk = 8192;
+    rc = ix->stage.ensure((size_t)chunk * d * es);
+    for (int64_t r0 = 0; rc == XS_OK && r0 < n; r0 += chunk) {
+        const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
+        rc = stage_host_rows(db, dtype, colmajor, colmajor ? stride_col : stride_row, r0, rows, d, ix->stage.p, ix->stream);
+        if (rc != XS_OK) break;
+        launch_layout_rows(ix->stage.p, dtype, colmajor, colmajor ? rows : d, rows, d, ix->d_pad, ix->db32 + (size_t)r0 * ix->d_pad, ix->stream);
+        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->dstats, ix->stream);
+        cudaError_t e = cudaStreamSynchronize(ix->stream);      // the staging tile is reused by the next chunk
+        if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e));
+    }
+    ix->stage.release();
+    if (rc != XS_OK) { index_free(ix); return rc; }
+    *out = ix;
+    return XS_OK;
+}
+
+extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int device, int renormalise, int64_t id_offset, xs_index** out) {
+    if (!db_dev || !out) return fail(XS_ERR_ARG, "null pointer");
+    xs_index* ix = new xs_index();
+    int rc = index_alloc(ix, n, d, device, id_offset);
+    if (rc != XS_OK) { index_free(ix); return rc; }
+    const int64_t chunk = 1 << 20;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
+        launch_layout_rows(db_dev + (size_t)r0 * d, XS_F32, false, d, rows, d, ix->d_pad, ix->db32 + (size_t)r0 * ix->d_pad, ix->stream);
+        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->dstats, ix->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); index_free(ix); return rc; }
+    *out = ix;
+    return XS_OK;
+}
+
+extern "C" int xs_index_destroy(xs_index* ix) { index_free(ix); return XS_OK; }
+
+extern "C" int xs_index_info(const xs_index* ix, int64_t* n, int* d, int* device, int64_t* device_bytes) {
+    if (!ix) return fail(XS_ERR_ARG, "null index");
+    if (n) *n = ix->n;
+    if (d) *d = ix->d;
+    if (device) *device = ix->device;
+    if (device_bytes) *device_bytes = ix->bytes;
+    return XS_OK;
+}
+
+extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
+    if (!ix || !name) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!strcmp(name, "eps_sigmas")) ix->eps_sigmas = (float)value;
+    else if (!strcmp(name, "scan_max_q")) ix->scan_max_q = (int)value;
+    else if (!strcmp(name, "force_path")) ix->force_path = (int)value;
+    else if (!strcmp(name, "gemm_splits")) ix->gemm_splits = (int)value;
+    else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
+    return XS_OK;
+}
+
+extern "C" int xs_index_stats(const xs_index* cix, xs_stats* out) {
+    if (!cix || !out) return fail(XS_ERR_ARG, "null pointer");
+    xs_index* ix = const_cast<xs_index*>(cix);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (ix->ev_valid) {
+        cudaSetDevice(ix->device);
+        if (cudaEventSynchronize(ix->ev[3]) == cudaSuccess) {
+            cudaEventElapsedTime(&ix->stats.ms_coarse, ix->ev[1], ix->ev[2]);
+            cudaEventElapsedTime(&ix->stats.ms_total, ix->ev[0], ix->ev[3]);
+        }
+        cudaGetLastError();
+    }
+    *out = ix->stats;
+    return XS_OK;
+}
+
+// ---- search core -----------------------------------------------------------------------------------------
+enum { PATH_SCAN = 1, PATH_GEMM = 2, PATH_EXACT = 3 };
+
+struct CoreArgs {
+    float* q32;                 // [nq][d_pad] device, fp32 (normalised in place when prep_renorm)
+    int64_t nq;
+    int k;
+    bool prep;                  // run prep_queries (false: q32 is final, eps must be valid for nq queries)
+    bool prep_renorm;
+    const CUtensorMap* tmap_a;  // non-null: bf16 query operand comes from this map (self-kNN) at row a_row0
+    int64_t a_row0;
+    int64_t self_base;          // -1 or first database row of the queries
+    int64_t* out_idx; float* out_score; int* status;   // device; pitch = k
+    int path;                   // PATH_*
+};
+
+__global__ void boost_self_kernel(float* scores, int64_t pitch, int nq, int64_t self_base) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) scores[(int64_t)q * pitch + self_base + q] = INFINITY;
+}
+__global__ void zero_rows_bf16_kernel(__nv_bfloat16* p, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = __float2bfloat16(0.f);
+}
+
+// Exact path for queries q32[0..nq): fp32 rows, fp64 accumulation, per-slice exact top-k, merge.
+static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t self_base,
+                     int64_t* out_idx, float* out_score, int* status, int* launches) {
+    const int P = (int)((ix->n + SLICE_ROWS - 1) / SLICE_ROWS);
+    const int cap = k;
+    const int64_t chunk_max = 16;
+    XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
+    const int64_t slots = round_up(chunk_max, 128) * P;
+    XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
+    XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
+    XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
+        const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
+        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->num_sms, ix->stream);
+        *launches += (c + 3) / 4;
+        if (self_base >= 0) { boost_self_kernel<<<(c + 127) / 128, 128, 0, ix->stream>>>(ix->scores.as<float>(), ix->n, c, self_base + q0); ++*launches; }
+        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, true, ix->pool_items.as<uint64_t>(),
+                               ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
+        FinaliseArgs fa{};
+        fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
+        fa.P = P; fa.cap = cap; fa.db32 = ix->db32; fa.q32 = q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad; fa.eps = nullptr;
+        fa.k = k; fa.exact = true; fa.id_offset = ix->id_offset; fa.self_base = self_base >= 0 ? self_base + q0 : -1;
+        fa.out_idx = out_idx + q0 * k; fa.out_score = out_score ? out_score + q0 * k : nullptr;
+        fa.status = status ? status + q0 : nullptr; fa.n_cand = nullptr; fa.out_pitch = k;
+        launch_finalise(fa, c, ix->stream);
+        *launches += 2;
+    }
+    CU_TRY(cudaGetLastError());
+    return XS_OK;
+}
+
+static int search_core(xs_index* ix, const CoreArgs& a) {
+    const int64_t nq = a.nq; const int k = a.k;
+    int launches = 0;
+    ix->stats = xs_stats{};
+    ix->stats.n_queries = nq; ix->stats.path = a.path;
+    XS_TRY(ix->eps.ensure((size_t)nq * sizeof(float)));
+    XS_TRY(ix->ncand.ensure(sizeof(int)));
+    CU_TRY(cudaMemsetAsync(ix->ncand.p, 0, sizeof(int), ix->stream));
+    CU_TRY(cudaEventRecord(ix->ev[0], ix->stream));
+    ix->ev_valid = true;
+
+    if (a.path == PATH_EXACT) {
+        if (a.prep) { launch_prep_queries(a.q32, nullptr, nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->stream); ++launches; }
+        CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
+        XS_TRY(run_exact(ix, a.q32, nq, k, a.self_base, a.out_idx, a.out_score, a.status, &launches));
+        CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
+    } else if (a.path == PATH_SCAN) {
+        if (a.prep) { launch_prep_queries(a.q32, nullptr, nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->stream); ++launches; }
+        const int P = (int)((ix->n + SLICE_ROWS - 1) / SLICE_ROWS);
+        const int cap = 2 * k + 256;
+        const int64_t chunk_max = 8;
+        XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
+        const int64_t slots = round_up(chunk_max, 128) * P;
+        XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
+        XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
+        XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
+        for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
+            const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
+            launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->num_sms, ix->stream);
+            launches += (c + 1) / 2;
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
+            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, false, ix->pool_items.as<uint64_t>(),
+                                   ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
+            FinaliseArgs fa{};
+            fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
+            fa.P = P; fa.cap = cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad; fa.eps = ix->eps.as<float>() + q0;
+            fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset; fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
+            fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
+            fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
+            launch_finalise(fa, c, ix->stream);
+            launches += 2;
+        }
+    } else {
+        // tcgen05 GEMM with fused top-K, queries in batches that bound the pool workspace
+        const int64_t batch_max = 8192;
+        const int64_t nq_pad = round_up(nq < batch_max ? nq : batch_max, GEMM_BM);
+        CUtensorMap tmap_q;
+        if (!a.tmap_a) {
+            XS_TRY(ix->q16.ensure((size_t)round_up(nq, GEMM_BM) * ix->d_pad * 2));
+            const int64_t pad_rows = round_up(nq, GEMM_BM) - nq;
+            if (pad_rows) {
+                const int64_t cnt = pad_rows * ix->d_pad;
+                zero_rows_bf16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->stream>>>(ix->q16.as<__nv_bfloat16>() + nq * ix->d_pad, cnt);
+                ++launches;
+            }
+        }
+        if (a.prep) {
+            launch_prep_queries(a.q32, a.tmap_a ? nullptr : ix->q16.as<__nv_bfloat16>(), nq, ix->d_pad, a.prep_renorm, ix->dstats,
+                                ix->eps_sigmas, ix->eps.as<float>(), ix->stream);
+            ++launches;
+        }
+        (void)nq_pad;
+        for (int64_t q0 = 0; q0 < nq; q0 += batch_max) {
+            const int64_t c = (nq - q0 < batch_max) ? nq - q0 : batch_max;
+            GemmPlan plan = plan_gemm(c, ix->n_pad, k, ix->num_sms, ix->gemm_splits);
+            const int64_t slots = (int64_t)plan.m_tiles * plan.splits * GEMM_BM;
+            XS_TRY(ix->pool_items.ensure((size_t)slots * plan.cap * 8));
+            XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
+            XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
+            const CUtensorMap* ta = a.tmap_a;
+            int64_t row0 = a.a_row0 + q0;
+            if (!ta) {
+                XS_TRY(make_tmap(&tmap_q, ix->q16.as<__nv_bfloat16>() + q0 * ix->d_pad, round_up(c, GEMM_BM), ix->d_pad, GEMM_BM));
+                ta = &tmap_q; row0 = 0;
+            }
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
+            cudaError_t e = launch_gemm_topk(*ta, ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+                                             ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
+                                             (int)row0, ix->stream);
+            if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
+            FinaliseArgs fa{};
+            fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
+            fa.P = plan.splits; fa.cap = plan.cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad;
+            fa.eps = ix->eps.as<float>() + q0; fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset;
+            fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
+            fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
+            fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
+            launch_finalise(fa, c, ix->stream);
+            launches += 2;
+        }
+    }
+    CU_TRY(cudaEventRecord(ix->ev[3], ix->stream));
+    CU_TRY(cudaGetLastError());
+    ix->stats.gpu_launches = launches;
+    return XS_OK;
+}
+
+static int choose_path(const xs_index* ix, int64_t nq, int k) {
+    if (ix->force_path >= PATH_SCAN && ix->force_path <= PATH_EXACT) return ix->force_path;
+    if (k > 2048 || (int64_t)k * 4 > ix->n) return PATH_EXACT;     // huge k: the coarse filter has nothing to discard
+    if (nq <= ix->scan_max_q) return PATH_SCAN;
+    return PATH_GEMM;
+}
+
+// After the coarse pass: read the certificate bits, re-run uncertified queries exactly.
+static int rerun_uncertified(xs_index* ix, float* q32, int64_t nq, int k, int64_t self_base, int64_t* out_idx, float* out_score, int* status_dev) {
+    std::vector<int> st((size_t)nq);
+    CU_TRY(cudaMemcpyAsync(st.data(), status_dev, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    int ncand = 0;
+    CU_TRY(cudaMemcpyAsync(&ncand, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(cudaStreamSynchronize(ix->stream));
+    ix->stats.n_candidates = ncand;
+    int launches = 0;
+    int64_t reruns = 0;
+    for (int64_t q = 0; q < nq;) {
+        if (!(st[(size_t)q] & ST_UNCERTIFIED)) { ++q; continue; }
+        int64_t e = q + 1;
+        while (e < nq && e - q < 16 && (st[(size_t)e] & ST_UNCERTIFIED)) ++e;
+        XS_TRY(run_exact(ix, q32 + q * ix->d_pad, e - q, k, self_base >= 0 ? self_base + q : -1, out_idx + q * k,
+                         out_score ? out_score + q * k : nullptr, nullptr, &launches));
+        reruns += e - q;
+        q = e;
+    }
+    ix->stats.n_exact_rerun = reruns;
+    ix->stats.gpu_launches += launches;
+    return XS_OK;
+}
+
+static int check_search_args(const xs_index* ix, int64_t nq, int k) {
+    if (!ix) return fail(XS_ERR_ARG, "null index");
+    if (nq <= 0) return fail(XS_ERR_ARG, "no queries (nq=%lld)", (long long)nq);
+    if (k <= 0 || k > ix->n) return fail(XS_ERR_ARG, "k=%d out of range for a database of %lld rows", k, (long long)ix->n);
+    if (k > 4096) return fail(XS_ERR_UNSUPPORTED, "k=%d > 4096: use xs_rank_all for full rankings", k);
+    return XS_OK;
+}
+
+extern "C" int xs_search_dev(xs_index* ix, const float* q_dev, int64_t nq, int renormalise_q, int k,
+                             int64_t* out_idx_dev, float* out_score_dev, int32_t* out_status_dev, void* stream) {
+    XS_TRY(check_search_args(ix, nq, k));
+    if (!q_dev || !out_idx_dev) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    // order our stream after the caller's pending work, and the caller's stream after ours
+    cudaEvent_t ev;
+    CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(ev, user));
+    CU_TRY(cudaStreamWaitEvent(ix->stream, ev, 0));
+    XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
+    XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
+    launch_layout_rows(q_dev, XS_F32, false, ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream);
+    CoreArgs a{};
+    a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
+    a.self_base = -1; a.out_idx = out_idx_dev; a.out_score = out_score_dev;
+    a.status = out_status_dev ? out_status_dev : ix->status.as<int>();
+    a.path = choose_path(ix, nq, k);
+    int rc = search_core(ix, a);
+    if (rc == XS_OK) { ix->stats.gpu_launches += 1; }
+    if (rc == XS_OK && !out_status_dev && a.path != PATH_EXACT)
+        rc = rerun_uncertified(ix, a.q32, nq, k, -1, out_idx_dev, out_score_dev, a.status);
+    cudaEventRecord(ev, ix->stream);
+    cudaStreamWaitEvent(user, ev, 0);
+    cudaEventDestroy(ev);
+    return rc;
+}
+
+extern "C" int xs_search(xs_index* ix, const void* q, int dtype, int64_t nq, int64_t stride_row, int64_t stride_col,
+                         int renormalise_q, int k, int64_t* out_idx, float* out_score) {
+    XS_TRY(check_search_args(ix, nq, k));
+    if (!q || !out_idx) return fail(XS_ERR_ARG, "null pointer");
+    bool colmajor = false;
+    XS_TRY(check_layout(dtype, nq, ix->d, stride_row, stride_col, &colmajor));
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    const size_t es = dtype == XS_F64 ? 8 : 4;
+    XS_TRY(ix->q_raw.ensure((size_t)nq * ix->d * es));
+    XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
+    XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
+    XS_TRY(ix->out_idx.ensure((size_t)nq * k * sizeof(int64_t)));
+    XS_TRY(ix->out_score.ensure((size_t)nq * k * sizeof(float)));
+    XS_TRY(stage_host_rows(q, dtype, colmajor, colmajor ? stride_col : stride_row, 0, nq, ix->d, ix->q_raw.p, ix->stream));
+    launch_layout_rows(ix->q_raw.p, dtype, colmajor, colmajor ? nq : ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream);
+    CoreArgs a{};
+    a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
+    a.self_base = -1; a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
+    a.path = choose_path(ix, nq, k);
+    XS_TRY(search_core(ix, a));
+    ix->stats.gpu_launches += 1;
+    if (a.path != PATH_EXACT) XS_TRY(rerun_uncertified(ix, a.q32, nq, k, -1, a.out_idx, a.out_score, a.status));
+    CU_TRY(cudaMemcpyAsync(out_idx, a.out_idx, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+    if (out_score) CU_TRY(cudaMemcpyAsync(out_score, a.out_score, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(cudaStreamSynchronize(ix->stream));
+    return XS_OK;
+}
+
+extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, int64_t* out_idx, float* out_score) {
+    if (!ix) return fail(XS_ERR_ARG, "null index");
+    if (q_begin < 0 || q_end > ix->n || q_begin >= q_end) return fail(XS_ERR_ARG, "bad row range [%lld, %lld)", (long long)q_begin, (long long)q_end);
+    XS_TRY(check_search_args(ix, q_end - q_begin, k));
+    if (!out_idx) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    const int64_t batch = 8192;
+    XS_TRY(ix->status.ensure((size_t)batch * sizeof(int)));
+    XS_TRY(ix->out_idx.ensure((size_t)batch * k * sizeof(int64_t)));
+    XS_TRY(ix->out_score.ensure((size_t)batch * k * sizeof(float)));
+    xs_stats total{};
+    for (int64_t r0 = q_begin; r0 < q_end; r0 += batch) {
+        const int64_t c = (q_end - r0 < batch) ? q_end - r0 : batch;
+        CoreArgs a{};
+        a.q32 = ix->db32 + (size_t)r0 * ix->d_pad; a.nq = c; a.k = k; a.prep = true; a.prep_renorm = false;   // rows are used as stored
+        a.path = choose_path(ix, c, k);
+        a.tmap_a = (a.path == PATH_GEMM) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
+        a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
+        XS_TRY(search_core(ix, a));
+        if (a.path != PATH_EXACT) XS_TRY(rerun_uncertified(ix, a.q32, c, k, r0, a.out_idx, a.out_score, a.status));
+        CU_TRY(cudaMemcpyAsync(out_idx + (r0 - q_begin) * k, a.out_idx, (size_t)c * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+        if (out_score) CU_TRY(cudaMemcpyAsync(out_score + (r0 - q_begin) * k, a.out_score, (size_t)c * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(cudaStreamSynchronize(ix->stream));
+        total.n_queries += ix->stats.n_queries; total.n_exact_rerun += ix->stats.n_exact_rerun;
+        total.n_candidates += ix->stats.n_candidates; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;
+    }
+    ix->stats = total;
+    ix->ev_valid = false;
+    return XS_OK;
+}
+
+extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, int64_t stride_row, int64_t stride_col,
+                           int renormalise_q, int64_t* out_ranks, float* out_scores_sorted) {
+    (void)ix; (void)q; (void)dtype; (void)nq; (void)stride_row; (void)stride_col; (void)renormalise_q; (void)out_ranks; (void)out_scores_sorted;
+    return fail(XS_ERR_UNSUPPORTED, "xs_rank_all: full-ranking sort kernel not built yet");
+}
+
+extern "C" int xs_merge_candidates(int device, const int64_t* in_idx, const float* in_score, int n_parts, int64_t nq, int k,
+                                   int64_t* out_idx, float* out_score, void* stream) {
+    if (!in_idx || !in_score || !out_idx) return fail(XS_ERR_ARG, "null pointer");
+    if (n_parts <= 0 || nq <= 0 || k <= 0) return fail(XS_ERR_ARG, "bad sizes");
+    if ((int64_t)n_parts * k > 16384) return fail(XS_ERR_UNSUPPORTED, "n_parts*k = %lld > 16384", (long long)n_parts * k);
+    CU_TRY(cudaSetDevice(device));
+    launch_merge_parts(in_idx, in_score, n_parts, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream));
+    CU_TRY(cudaGetLastError());
+    return XS_OK;
+}

@@ -1,0 +1,155 @@
+// Index build and query preparation kernels.
+//
+// The reference hands the matcher `vecs.T` -- an F-order (N,D) view of a (D,N) C-contiguous
+// array (src/networks/imageretrievalnet.py:370, src/online.py:133) in fp32 or, by accident of
+// np.concatenate on an fp64 seed, fp64 (src/online.py:96-100).  The device wants row-major rows:
+//   db32 [N][d_pad] fp32  -- exact rescoring operand
+//   db16 [n_pad][d_pad] bf16 -- coarse scoring operand (TMA / UMMA tiles, batch-1 scan)
+// so the build is: stage a block of rows -> layout_rows (transpose + convert) -> finish_rows
+// (optional L2 normalisation as nnsearch.py:693-697, bf16 rounding, norm statistics).
+#include "common.cuh"
+#include "internal.h"
+
+namespace xs {
+
+// ---- layout_rows ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void layout_colmajor_kernel(const T* __restrict__ src, int64_t pitch, int64_t rows, int d,
+                                       int d_pad, float* __restrict__ dst) {
+    // src[c * pitch + r]  ->  dst[r * d_pad + c]; 32x32 tile through shared memory
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int c = c0 + j;
+        int64_t r = r0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < d && r < rows) ? (float)src[(int64_t)c * pitch + r] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int64_t r = r0 + j;
+        int c = c0 + threadIdx.x;
+        if (r < rows && c < d_pad) dst[r * d_pad + c] = tile[threadIdx.x][j];
+    }
+}
+
+template <typename T>
+__global__ void layout_rowmajor_kernel(const T* __restrict__ src, int64_t pitch, int64_t rows, int d,
+                                       int d_pad, float* __restrict__ dst) {
+    const int64_t r = blockIdx.x;
+    if (r >= rows) return;
+    for (int c = threadIdx.x; c < d_pad; c += blockDim.x)
+        dst[r * d_pad + c] = (c < d) ? (float)src[r * pitch + c] : 0.f;
+}
+
+void launch_layout_rows(const void* src_tile, int dtype, bool colmajor, int64_t pitch,
+                        int64_t rows, int d, int d_pad, float* dst32, cudaStream_t st) {
+    if (rows <= 0) return;
+    if (colmajor) {
+        dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((d_pad + 31) / 32)), block(32, 8);
+        if (dtype == 0) layout_colmajor_kernel<float><<<grid, block, 0, st>>>((const float*)src_tile, pitch, rows, d, d_pad, dst32);
+        else            layout_colmajor_kernel<double><<<grid, block, 0, st>>>((const double*)src_tile, pitch, rows, d, d_pad, dst32);
+    } else {
+        if (dtype == 0) layout_rowmajor_kernel<float><<<(unsigned)rows, 256, 0, st>>>((const float*)src_tile, pitch, rows, d, d_pad, dst32);
+        else            layout_rowmajor_kernel<double><<<(unsigned)rows, 256, 0, st>>>((const double*)src_tile, pitch, rows, d, d_pad, dst32);
+    }
+}
+
+// ---- finish_rows / prep_queries ------------------------------------------------------------------
+// One warp per row.  Sum of squares and of fourth powers in fp64 (fixed lane-strided order).
+__device__ __forceinline__ void row_moments(const float* row, int d_pad, double& s2, double& s4) {
+    double a2 = 0.0, a4 = 0.0;
+    for (int c = lane_id() * 4; c < d_pad; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(row + c);
+        double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
+        double q0 = x0 * x0, q1 = x1 * x1, q2 = x2 * x2, q3 = x3 * x3;
+        a2 += (q0 + q1) + (q2 + q3);
+        a4 += (q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3);
+    }
+    s2 = warp_sum(a2);
+    s4 = warp_sum(a4);
+}
+
+__device__ __forceinline__ void scale_and_round(float* row32, __nv_bfloat16* row16, int d_pad, float scale, bool do_scale) {
+    for (int c = lane_id() * 4; c < d_pad; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(row32 + c);
+        if (do_scale) {
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            *reinterpret_cast<float4*>(row32 + c) = v;
+        }
+        if (row16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(row16 + c) = pk;
+        }
+    }
+}
+
+__global__ void finish_rows_kernel(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad,
+                                   int renorm, DevStats* stats) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float* row = rows32 + r * d_pad;
+    double s2, s4;
+    row_moments(row, d_pad, s2, s4);
+    float scale = 1.f;
+    if (renorm) {
+        // a zero row stays zero (the reference would produce NaNs, nnsearch.py:697)
+        scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
+        double sc = scale;
+        s4 *= sc * sc * sc * sc;
+        s2 *= sc * sc;
+    }
+    scale_and_round(row, rows16 ? rows16 + r * d_pad : nullptr, d_pad, scale, renorm != 0);
+    if (lane_id() == 0) {
+        float n4 = (float)sqrt(sqrt(s4)) * 1.000001f, n2 = (float)sqrt(s2) * 1.000001f;
+        atomicMax(&stats->v4max_bits, __float_as_uint(n4));
+        atomicMax(&stats->vnmax_bits, __float_as_uint(n2));
+    }
+}
+
+void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm,
+                        DevStats* stats, cudaStream_t st) {
+    if (rows <= 0) return;
+    const int wpb = 8;
+    finish_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(rows32, rows16, rows, d_pad, renorm ? 1 : 0, stats);
+}
+
+// eps[q] bounds |bf16 coarse score - exact score| for query q against ANY database row:
+// both operands are rounded to bf16 (unit roundoff u = 2^-9), so the error of one product is
+// ~ v_i q_i (d1 + d2) with independent roundings of variance <= u^2/3; over the row the standard
+// deviation is <= u sqrt(2/3) sqrt(sum (v_i q_i)^2) <= u sqrt(2/3) ||v||_4 ||q||_4 (Cauchy-Schwarz).
+// eps = sigmas * that bound + a small absolute term for the fp32 accumulation inside the tensor core.
+__global__ void prep_queries_kernel(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, int renorm,
+                                    const DevStats* stats, float eps_sigmas, float* eps) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nq) return;
+    float* row = q32 + r * d_pad;
+    double s2, s4;
+    row_moments(row, d_pad, s2, s4);
+    float scale = 1.f;
+    if (renorm) {
+        scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
+        double sc = scale;
+        s4 *= sc * sc * sc * sc;
+        s2 *= sc * sc;
+    }
+    scale_and_round(row, q16 ? q16 + r * d_pad : nullptr, d_pad, scale, renorm != 0);
+    if (lane_id() == 0) {
+        const float v4 = __uint_as_float(stats->v4max_bits), vn = __uint_as_float(stats->vnmax_bits);
+        const float q4 = (float)sqrt(sqrt(s4)), qn = (float)sqrt(s2);
+        const float u = 1.0f / 512.0f;
+        eps[r] = eps_sigmas * u * 0.8165f * q4 * v4 + 2e-5f * qn * vn;
+    }
+}
+
+void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
+                         const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st) {
+    if (nq <= 0) return;
+    const int wpb = 4;
+    prep_queries_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, st>>>(q32, q16, nq, d_pad, renorm ? 1 : 0, stats, eps_sigmas, eps);
+}
+
+}  // namespace xs

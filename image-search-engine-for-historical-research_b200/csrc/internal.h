@@ -1,0 +1,91 @@
+// Host-side declarations shared by the translation units of libxs_b200.so (not part of the ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace xs {
+
+// Geometry of the coarse (bf16) GEMM kernel -- see gemm_topk.cu.
+constexpr int GEMM_BM = 128;      // queries per tile  (UMMA M, TMEM lanes)
+constexpr int GEMM_BN = 256;      // database rows per tile (UMMA N, TMEM columns)
+constexpr int GEMM_BK = 64;       // K elements per pipeline stage (= one 128-byte swizzle atom of bf16)
+constexpr int ROW_ALIGN = 256;    // database rows are padded to a multiple of this
+constexpr int COL_ALIGN = 64;     // descriptor length is padded to a multiple of this
+
+constexpr int SLICE_ROWS = 4096;  // rows per partial list in the score-matrix -> pools kernel
+
+// status bits written by the finalise kernel (one int32 per query)
+constexpr int ST_UNCERTIFIED = 1;
+
+struct DevStats {                 // device-side database statistics (uint-ordered positive floats)
+    unsigned int v4max_bits;      // max over rows of ||v||_4
+    unsigned int vnmax_bits;      // max over rows of ||v||_2
+};
+
+// ---- build.cu -----------------------------------------------------------------------------------
+// src_tile is a device buffer holding `rows` database rows either row-major ([rows][pitch]) or
+// column-major ([d][pitch], the reference's (D,N) layout); writes fp32 rows [rows][d_pad].
+void launch_layout_rows(const void* src_tile, int dtype, bool colmajor, int64_t pitch,
+                        int64_t rows, int d, int d_pad, float* dst32, cudaStream_t st);
+// Optional L2 normalisation, bf16 copy, ||.||_4 / ||.||_2 maxima.  dst16 rows have pitch d_pad.
+void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm,
+                        DevStats* stats, cudaStream_t st);
+// Query preparation: normalise (optional), fp32 + bf16 copies, per-query error band eps.
+void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
+                         const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
+
+// ---- scan.cu ------------------------------------------------------------------------------------
+// Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  nq <= 4.
+void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
+                        float* scores, int64_t score_pitch, int num_sms, cudaStream_t st);
+// Exact scoring: scores[q][row] = fp32( sum_fp64 db32[row][i] * q32[q][i] ).  Any nq (looped in 4s).
+void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n, int d_pad,
+                         float* scores, int64_t score_pitch, int num_sms, cudaStream_t st);
+// Score matrix -> candidate pools (one partial list per SLICE_ROWS rows).
+//   exact = false: keep items within the eps band below the slice's k-th best
+//   exact = true : keep exactly the slice's k best (full 64-bit item order)
+void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
+                            const float* eps, bool exact, uint64_t* pool_items, int* pool_count,
+                            uint32_t* pool_thr, int P, int cap, cudaStream_t st);
+
+// ---- gemm_topk.cu -------------------------------------------------------------------------------
+struct GemmPlan {
+    int m_tiles;      // ceil(nq / 128)
+    int n_tiles;      // n_pad / 256
+    int splits;       // partial lists per query (P)
+    int k_keep;       // items kept by a mid-job trim
+    int cap;          // capacity of one partial list (>= 2 * k_keep)
+    int grid;         // CTAs launched
+};
+GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits);
+size_t   gemm_smem_bytes();
+// tmap_q: [nq_pad128][d_pad] bf16, box {64,128};  tmap_db: [n_pad][d_pad] bf16, box {64,256}
+cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
+                             int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
+                             uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0, cudaStream_t st);
+
+// ---- finalise.cu --------------------------------------------------------------------------------
+struct FinaliseArgs {
+    const uint64_t* pool_items; const int* pool_count; const uint32_t* pool_thr;
+    int P, cap;
+    const float* db32; const float* q32; int d_pad;
+    const float* eps;           // per-query band (ignored when exact)
+    int k; bool exact;          // exact: pool scores are already fp32-exact -> no rescoring
+    int64_t id_offset;
+    int64_t self_base;          // >= 0: query q is database row self_base + q and must rank first
+    int64_t* out_idx; float* out_score; int* status; int* n_cand;
+    int64_t out_pitch;          // elements between consecutive queries in out_idx / out_score
+};
+int  finalise_cand_max(int k);
+void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);
+// Multi-GPU merge of [parts][nq][k] lists.
+void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts, int64_t nq, int k,
+                        int64_t* out_idx, float* out_score, cudaStream_t st);
+// Full ranking helpers (K == N).
+void launch_rank_all(const float* scores, int64_t score_pitch, int nq, int64_t n, int64_t id_offset,
+                     uint64_t* work_a, uint64_t* work_b, int64_t* out_ranks, float* out_sorted,
+                     cudaStream_t st);
+
+}  // namespace xs

@@ -1,0 +1,154 @@
+/*
+ * xs_b200.h -- C ABI of the B200-native exhaustive (exact top-K) matcher.
+ *
+ * This is the drop-in boundary for ONE path of YYao-42/Image-Search-Engine-for-Historical-Research:
+ * L2-normalised global descriptors scored as scores = vecs.T @ qvecs and ranked to the top K.
+ * The reference has no FFI of its own (it is 100 % Python); the entry points below are what a
+ * ctypes binding for its three call shapes needs, and each one names the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   B1  matching_L2(K, train[N,D], test[Q,D]) -> (idx int64[Q,K], time_per_query)
+ *                                                   src/utils/nnsearch.py:687-706
+ *   B2  scores = np.dot(vecs.T, qvecs); ranks = np.argsort(-scores, axis=0)
+ *                                                   src/main_retrieve.py:175-176
+ *   B3  KNN(database, 'cosine').search(queries, k) -> (sims f32[nq,k], ids int64[nq,k])
+ *                                                   src/utils/knn.py:8-40
+ *       and its N x N use for the diffusion graph   src/utils/diffusion.py:67
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * non-zero code otherwise, with a thread-local message behind xs_last_error(); no exception
+ * crosses the boundary.  Host entry points block until results are in the caller's buffers;
+ * *_dev entry points enqueue on the given CUDA stream and return.  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with XS_ERR_CUDA.
+ */
+#ifndef XS_B200_H
+#define XS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define XS_API __attribute__((visibility("default")))
+#else
+#define XS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xs_index xs_index;
+
+enum { XS_OK = 0, XS_ERR_ARG = 1, XS_ERR_CUDA = 2, XS_ERR_NOMEM = 3, XS_ERR_UNSUPPORTED = 4 };
+enum { XS_F32 = 0, XS_F64 = 1 };
+
+/* Query statistics of the last search on an index (see xs_index_stats). */
+typedef struct xs_stats {
+    int64_t n_queries;       /* queries in the last call                                          */
+    int64_t n_exact_rerun;   /* queries whose bf16 candidate set could not be certified and were   */
+                             /* re-run on the exact fp32 path (never a silent miss)               */
+    int64_t n_candidates;    /* total candidates rescored in fp32 (sum over queries)              */
+    int32_t path;            /* 1 = batch-1 HBM scan, 2 = tcgen05 GEMM + fused top-K, 3 = exact   */
+    int32_t gpu_launches;    /* kernels launched by the last call                                 */
+    float   ms_coarse;       /* device time of the coarse kernel (scan or GEMM), CUDA events      */
+    float   ms_total;        /* device time of the whole call                                     */
+} xs_stats;
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+XS_API const char* xs_last_error(void);
+/* ABI version of this library (bumped on any signature change). */
+XS_API int xs_abi_version(void);
+/* Number of visible CUDA devices (0 and XS_ERR_CUDA if the driver is absent). */
+XS_API int xs_device_count(int* count);
+
+/*
+ * Build a device-resident index from a HOST matrix of n rows x d columns.
+ *   replaces: the implicit "index" of matching_L2 (the raw train matrix, nnsearch.py:687-698)
+ *             and BaseKNN.__init__/add (fp32 copy + IndexFlatIP.add, knn.py:8-23,34-40).
+ * db           element (r, c) lives at db[r*stride_row + c*stride_col] (strides in ELEMENTS).
+ *              Accepted: row-major (stride_col == 1) and the reference's F-order view vecs.T of a
+ *              (D,N) C array (stride_row == 1, stride_col >= n).  The caller keeps ownership;
+ *              the matrix is not modified.
+ * dtype        XS_F32 or XS_F64 (online.py:96-100 accidentally builds float64).
+ * renormalise  1: divide every row by its L2 norm first (matching_L2 semantics, :693-697);
+ *              0: use rows as given (KNN / np.dot semantics).
+ * id_offset    added to every returned id (row-sharding across GPUs: shard g passes its first row).
+ * Device layout: bf16 row-major copy (coarse scoring) + fp32 row-major copy (exact rescoring).
+ */
+XS_API int xs_index_create(const void* db, int dtype, int64_t n, int d,
+                    int64_t stride_row, int64_t stride_col,
+                    int device, int renormalise, int64_t id_offset, xs_index** out);
+
+/* Same, from a DEVICE fp32 row-major [n, d] matrix on `device` (rows contiguous). */
+XS_API int xs_index_create_dev(const float* db_dev, int64_t n, int d,
+                        int device, int renormalise, int64_t id_offset, xs_index** out);
+
+XS_API int xs_index_destroy(xs_index* index);
+
+/* n rows, d columns, device ordinal and device bytes held; any out pointer may be NULL. */
+XS_API int xs_index_info(const xs_index* index, int64_t* n, int* d, int* device, int64_t* device_bytes);
+XS_API int xs_index_stats(const xs_index* index, xs_stats* out);
+
+/*
+ * Exact top-k by inner product, HOST buffers (the end-to-end call).
+ *   replaces: the per-query loop of matching_L2 (nnsearch.py:699-703) with renormalise_q = 1,
+ *             np.dot + argsort[:k] (main_retrieve.py:175-176) and IndexFlatIP.search
+ *             (knn.py:25-31) with renormalise_q = 0.
+ * q            nq x d host matrix, element (r,c) at q[r*stride_row + c*stride_col]; same two
+ *              layouts as xs_index_create.
+ * out_idx      [nq, k] int64, best first; ids are row numbers + id_offset.
+ * out_score    [nq, k] fp32 exact scores (may be NULL).
+ * Ordering: descending fp32 score; exact ties by ascending id.  k must be <= n.
+ */
+XS_API int xs_search(xs_index* index, const void* q, int dtype, int64_t nq,
+              int64_t stride_row, int64_t stride_col, int renormalise_q, int k,
+              int64_t* out_idx, float* out_score);
+
+/*
+ * Same with DEVICE buffers on the index's device, enqueued on `stream` (a cudaStream_t).
+ * q_dev is fp32 row-major [nq, d].  out_status_dev (may be NULL) receives one int32 per query:
+ * 0 = certified by the bf16 coarse pass, 1 = needs the exact path.  With out_status_dev == NULL
+ * the call synchronises the stream once to re-run uncertified queries itself.
+ */
+XS_API int xs_search_dev(xs_index* index, const float* q_dev, int64_t nq, int renormalise_q, int k,
+                  int64_t* out_idx_dev, float* out_score_dev, int32_t* out_status_dev,
+                  void* stream);
+
+/*
+ * Self-kNN over database rows [q_begin, q_end): top-k neighbours of each row among ALL rows.
+ *   replaces: self.knn.search(self.features, n_trunc)              src/utils/diffusion.py:67
+ * Row i's own id is always returned first (get_affinity relies on ids[i][0] == i, :108).
+ * Outputs are HOST buffers [q_end-q_begin, k].
+ */
+XS_API int xs_self_knn(xs_index* index, int64_t q_begin, int64_t q_end, int k,
+                int64_t* out_idx, float* out_score);
+
+/*
+ * Full ranking (k == n) for nq host queries: out_ranks is [n, nq] int64, one COLUMN per query,
+ * best first -- the exact shape of `ranks` at main_retrieve.py:176 / evaluate.py:52-55.
+ */
+XS_API int xs_rank_all(xs_index* index, const void* q, int dtype, int64_t nq,
+                int64_t stride_row, int64_t stride_col, int renormalise_q,
+                int64_t* out_ranks, float* out_scores_sorted);
+
+/*
+ * Merge per-shard results after an all-gather (row-sharded multi-GPU search).
+ * in_idx / in_score: DEVICE [n_parts, nq, k] (part-major, as all_gather lays them out);
+ * out: DEVICE [nq, k].  Descending score, ties by ascending id.  Enqueued on `stream`.
+ */
+XS_API int xs_merge_candidates(int device, const int64_t* in_idx, const float* in_score,
+                        int n_parts, int64_t nq, int k,
+                        int64_t* out_idx, float* out_score, void* stream);
+
+/*
+ * Tunables (set before searching; all have safe defaults):
+ *   "eps_sigmas"   float  width of the bf16 error band in standard deviations      (8.0)
+ *   "scan_max_q"   int    largest batch served by the batch-1 HBM scan kernel      (1)
+ *   "force_path"   int    0 = auto, 1 = scan, 2 = tcgen05 GEMM, 3 = exact fp32      (0)
+ *   "gemm_splits"  int    database splits per query tile, 0 = auto                 (0)
+ */
+XS_API int xs_set_param(xs_index* index, const char* name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XS_B200_H */

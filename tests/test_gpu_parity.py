@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Bar: identical top-K id lists except where the adjudicating float64 scores are within a few fp32
+ulp (rtol 1e-6), scores within 1e-5 relative of the oracle's fp32 scores, identical mAP.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PATHS = {"scan": 1, "gemm": 2, "exact": 3}
+
+
+def _check_lists(oracle, ids, ref_ids, s64, what):
+    for j in range(ids.shape[0]):
+        ok, msg = oracle.compare_topk(ids[j], ref_ids[j], lambda i, j=j: s64[i, j])
+        assert ok, f"{what}, query {j}: {msg}"
+
+
+@pytest.fixture(scope="module")
+def cfg1(synth, oracle):
+    vecs, qvecs = synth.gaussian(4993, 70, d=2048)
+    ref_ids, ref_sims = oracle.topk_ip(vecs, qvecs, 100)
+    return vecs, qvecs, ref_ids, ref_sims, oracle.scores_f64(vecs, qvecs)
+
+
+@pytest.mark.parametrize("path", ["gemm", "scan", "exact"])
+def test_cfg1_every_path(pkg, oracle, cfg1, path):
+    vecs, qvecs, ref_ids, ref_sims, s64 = cfg1
+    with pkg.ExactIndex(vecs.T) as ix:
+        ix.set_param("force_path", PATHS[path])
+        nq = 70 if path != "scan" else 6
+        ids, sims = ix.search(qvecs.T[:nq], 100)
+        st = ix.stats()
+    assert st["path"] == PATHS[path] and st["gpu_launches"] > 0
+    _check_lists(oracle, ids, ref_ids[:nq], s64, path)
+    np.testing.assert_allclose(sims, ref_sims[:nq], rtol=1e-5, atol=1e-7)
+    assert ids.dtype == np.int64 and sims.dtype == np.float32
+
+
+def test_default_dispatch(pkg, cfg1):
+    vecs, qvecs, *_ = cfg1
+    with pkg.ExactIndex(vecs.T) as ix:
+        ix.search(qvecs.T[:1], 100)
+        assert ix.stats()["path"] == 1          # batch 1 -> HBM scan
+        ix.search(qvecs.T, 100)
+        assert ix.stats()["path"] == 2          # batch 70 -> tcgen05 GEMM + fused top-K
+        assert ix.stats()["n_exact_rerun"] == 0
+
+
+@pytest.mark.parametrize("fam", ["G", "P"])
+def test_golden_top100(pkg, synth, oracle, golden, fam):
+    v, q = synth.gaussian(1000, 5, d=2048, family=fam)
+    s64 = oracle.scores_f64(v, q)
+    for path in ("gemm", "scan"):
+        with pkg.ExactIndex(v.T) as ix:
+            ix.set_param("force_path", PATHS[path])
+            ids, sims = ix.search(q.T, 100)
+        _check_lists(oracle, ids, golden[f"C_{fam}_top100"].T.astype(np.int64), s64, f"golden {fam} {path}")
+        np.testing.assert_allclose(sims, golden[f"C_{fam}_top100_scores"].T, rtol=1e-5, atol=1e-7)
+        for j in range(5):       # matching_L2's distance order names the same sets
+            assert set(ids[j]) == set(golden[f"C_{fam}_matching_L2_idx"][j])
+
+
+def test_matching_L2_api(pkg, synth, golden):
+    vecs, qvecs = synth.gaussian(512, 8, d=64)
+    idx, tpq = pkg.matching_L2(10, vecs.T, qvecs.T)
+    assert idx.shape == (8, 10) and idx.dtype == np.int64 and tpq > 0
+    np.testing.assert_array_equal(idx, golden["A_matching_L2_idx"])
+    # float64, un-normalised rows: the function normalises (nnsearch.py:693-698)
+    vecs64 = vecs.astype(np.float64) * np.linspace(0.5, 2.0, vecs.shape[1])[None, :]
+    q64 = qvecs.astype(np.float64) * 3.0
+    idx, _ = pkg.matching_L2(10, vecs64.T, q64.T)
+    np.testing.assert_array_equal(idx, golden["B_matching_L2_idx"])
+    # cached index is reused for the same array, rebuilt after an in-place edit
+    a = pkg.cached_index(vecs64.T, True)
+    assert pkg.cached_index(vecs64.T, True) is a
+    pkg.clear_index_cache()
+
+
+def test_rank_ip_topk_and_map(pkg, synth, oracle, golden):
+    v, q, gnd = synth.clustered(3000, 12, d=256, n_clusters=40, noise=1.6, spread=0.5)
+    ranks = pkg.rank_ip(v, q, K=100)
+    assert ranks.shape == (100, 12) and ranks.dtype == np.int64
+    s64 = oracle.scores_f64(v, q)
+    _check_lists(oracle, ranks.T, golden["D_top100"].T.astype(np.int64), s64, "rank_ip")
+    m100, aps100, _, _ = oracle.compute_map(ranks, gnd, [1, 5, 10])
+    assert m100 == golden["D_map_top100"]
+    np.testing.assert_array_equal(aps100, golden["D_aps_top100"])
+    pkg.clear_index_cache()
+
+
+def test_knn_wrapper(pkg, synth, oracle):
+    v, q = synth.gaussian(2000, 9, d=128)
+    knn = pkg.KNN(v.T, "cosine")
+    assert (knn.N, knn.D) == (2000, 128) and knn.database.flags["C_CONTIGUOUS"]
+    sims, ids = knn.search(q.T, 7)
+    rs, ri = oracle.knn_search(v.T, q.T, 7, "cosine")
+    np.testing.assert_array_equal(ids, ri)
+    np.testing.assert_allclose(sims, rs, rtol=1e-5, atol=1e-7)
+    knn2 = pkg.KNN(v.T * 1.5, "euclidean")
+    dist, ids2 = knn2.search(q.T, 7)
+    rd, ri2 = oracle.knn_search(v.T * 1.5, q.T, 7, "euclidean")
+    np.testing.assert_array_equal(ids2, ri2)
+    np.testing.assert_allclose(dist, rd, rtol=1e-4, atol=1e-5)
+    with pytest.raises(KeyError):
+        pkg.KNN(v.T, "manhattan")
+
+
+def test_self_knn_self_first(pkg, synth, oracle):
+    v, _ = synth.gaussian(1500, 1, d=256)
+    knn = pkg.KNN(v.T, "cosine")
+    sims, ids = knn.self_search(20)
+    assert (ids[:, 0] == np.arange(1500)).all()
+    rs, ri = oracle.knn_search(v.T, v.T, 20, "cosine")
+    s64 = oracle.scores_f64(v, v)
+    _check_lists(oracle, ids, ri, s64, "self-kNN")
+    np.testing.assert_allclose(sims, rs, rtol=1e-5, atol=1e-6)
+
+
+def test_ties_and_duplicates(pkg, synth, oracle, golden):
+    v, q = synth.ties(256, 4, d=64, n_distinct=16)
+    for path in ("gemm", "scan", "exact"):
+        with pkg.ExactIndex(v.T) as ix:
+            ix.set_param("force_path", PATHS[path])
+            ids, sims = ix.search(q.T, 40)
+        rid, rsim = oracle.topk_ip(v, q, 40)
+        # duplicated rows give exactly equal exact scores -> the documented rule (ascending id) decides
+        np.testing.assert_array_equal(ids, rid, err_msg=path)
+        np.testing.assert_allclose(sims, golden["E_sorted_scores"][:40].T, rtol=1e-5, atol=1e-7)
+
+
+def test_edges(pkg, synth, oracle):
+    v, q = synth.gaussian(300, 3, d=100)              # d not a multiple of 64, N not of 256
+    s64 = oracle.scores_f64(v, q)
+    with pkg.ExactIndex(v.T) as ix:
+        for path in ("gemm", "scan", "exact"):
+            ix.set_param("force_path", PATHS[path])
+            for k in (1, 7, 300):
+                if k * 4 > 300 and path != "exact":
+                    continue
+                ids, _ = ix.search(q.T, k)
+                rid, _ = oracle.topk_ip(v, q, k)
+                _check_lists(oracle, ids, rid, s64, f"edge {path} k={k}")
+        ix.set_param("force_path", 0)
+        ids, _ = ix.search(q.T, 300)                  # k == N -> exact path by dispatch
+        assert sorted(ids[0].tolist()) == list(range(300))
+        with pytest.raises(ValueError):
+            ix.search(q.T, 301)
+        with pytest.raises(ValueError):
+            ix.search(q.T[:, :50], 5)
+    # row-major input and id_offset (a shard's view)
+    with pkg.ExactIndex(np.ascontiguousarray(v.T), id_offset=1000) as ix:
+        ids, _ = ix.search(np.ascontiguousarray(q.T), 5)
+        rid, _ = oracle.topk_ip(v, q, 5)
+        np.testing.assert_array_equal(ids, rid + 1000)
