@@ -1,0 +1,123 @@
+"""Row-sharded exact search across the GPUs of one box (one process per GPU, torch.distributed).
+
+The database is split into contiguous row ranges, rank g owning rows ``[offsets[g], offsets[g+1])``
+(SURVEY.md section 8e).  Every rank scores ALL queries against its shard and produces an exact
+local top-k with GLOBAL ids (``id_offset``); the only exchange step is one all-gather of the
+``[nq, k]`` (score, id) lists -- 84 KB per rank at nq=70, k=100 -- followed by a ``G*k -> k`` merge
+kernel (xs_merge_candidates).  Rescoring needs no communication: a shard holds the fp32 rows of
+its own candidates.
+
+The local searcher and the merge are injectable so that the sharding / id-offset / gather logic
+is covered by world_size-2 gloo tests on CPU, where the test passes the oracle in; the default
+is the CUDA path, and there is no automatic fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+
+def shard_bounds(n_rows: int, world: int):
+    """Contiguous, near-equal row ranges: ``bounds[g] .. bounds[g+1]``."""
+    base, rem = divmod(int(n_rows), int(world))
+    b = [0]
+    for g in range(world):
+        b.append(b[-1] + base + (1 if g < rem else 0))
+    return b
+
+
+def merge_parts_host(ids_parts: np.ndarray, sims_parts: np.ndarray, k: int):
+    """Reference semantics of the merge kernel (descending score, ties by ascending id), used by
+    the CPU tests to check the CUDA merge: ``[G, nq, k] -> [nq, k]``."""
+    g, nq, kk = ids_parts.shape
+    ids = np.empty((nq, k), dtype=np.int64)
+    sims = np.empty((nq, k), dtype=np.float32)
+    for j in range(nq):
+        i = ids_parts[:, j, :].reshape(-1)
+        s = sims_parts[:, j, :].reshape(-1)
+        keep = i >= 0
+        i, s = i[keep], s[keep]
+        order = np.lexsort((i, -s.astype(np.float64)))[:k]
+        ids[j, :len(order)] = i[order]
+        sims[j, :len(order)] = s[order]
+        ids[j, len(order):] = -1
+        sims[j, len(order):] = -np.inf
+    return ids, sims
+
+
+class ShardedSearcher:
+    """Glue between a per-rank local searcher and the process group.
+
+    ``local_search(queries, k) -> (ids [nq,k] int64 GLOBAL ids, sims [nq,k] f32)`` as torch tensors
+    on ``device``; ``merge(ids_all [G,nq,k], sims_all [G,nq,k], k) -> (ids, sims)``.
+    """
+
+    def __init__(self, local_search, merge, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local_search = local_search
+        self.merge = merge
+
+    def search(self, queries, k: int):
+        import torch
+        ids, sims = self.local_search(queries, k)
+        if self.world == 1:
+            return ids, sims
+        ids_all = torch.empty((self.world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+        sims_all = torch.empty((self.world,) + tuple(sims.shape), dtype=sims.dtype, device=sims.device)
+        self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(sims_all, sims.contiguous(), group=self.group)
+        return self.merge(ids_all, sims_all, k)
+
+
+class CudaShard:
+    """The CUDA local searcher + merge for one rank: wraps an ExactIndex built with ``id_offset``."""
+
+    def __init__(self, index, device: int):
+        import torch
+        self.torch = torch
+        self.index = index
+        self.device = device
+        self.lib = nat.load()
+        self._out = {}
+
+    def _buffers(self, nq, k):
+        torch = self.torch
+        key = (nq, k)
+        if key not in self._out:
+            dev = torch.device("cuda", self.device)
+            self._out[key] = (torch.empty((nq, k), dtype=torch.int64, device=dev),
+                              torch.empty((nq, k), dtype=torch.float32, device=dev),
+                              torch.zeros((nq,), dtype=torch.int32, device=dev))
+        return self._out[key]
+
+    def local_search(self, queries, k):
+        """``queries``: fp32 row-major torch tensor on this rank's device."""
+        torch = self.torch
+        nq = int(queries.shape[0])
+        ids, sims, status = self._buffers(nq, k)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.index.search_device(queries.data_ptr(), nq, k, ids.data_ptr(), sims.data_ptr(),
+                                 status_ptr=status.data_ptr(), stream=stream)
+        return ids, sims
+
+    def uncertified(self, nq, k) -> int:
+        """Number of queries of the last local_search(nq, k) the bf16 pass could not certify."""
+        return int(self._buffers(nq, k)[2].sum().item())
+
+    def merge(self, ids_all, sims_all, k):
+        torch = self.torch
+        g, nq, kk = ids_all.shape
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=ids_all.device)
+        out_s = torch.empty((nq, k), dtype=torch.float32, device=ids_all.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(self.lib.xs_merge_candidates(self.device, C.c_void_p(ids_all.data_ptr()), C.c_void_p(sims_all.data_ptr()),
+                                               int(g), int(nq), int(k), C.c_void_p(out_i.data_ptr()),
+                                               C.c_void_p(out_s.data_ptr()), C.c_void_p(stream) if stream else None),
+                  "xs_merge_candidates")
+        return out_i, out_s
