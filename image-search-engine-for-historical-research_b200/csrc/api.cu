@@ -54,9 +54,9 @@ struct xs_index {
     __nv_bfloat16* db16 = nullptr; float* db32 = nullptr; DevStats* dstats = nullptr;
     CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
     // tunables
-    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0;
+    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; float debug_thr = 0.f;
     // workspace
-    Buf q_raw, q32, q16, eps, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf q_raw, q32, q16, eps, thr0, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -138,7 +138,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     if (ix->db16) cudaFree(ix->db16);
     if (ix->db32) cudaFree(ix->db32);
@@ -235,6 +235,8 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "scan_max_q")) ix->scan_max_q = (int)value;
     else if (!strcmp(name, "force_path")) ix->force_path = (int)value;
     else if (!strcmp(name, "gemm_splits")) ix->gemm_splits = (int)value;
+    else if (!strcmp(name, "sample_pass")) ix->sample_pass = (int)value;
+    else if (!strcmp(name, "debug_thr")) ix->debug_thr = (float)value;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
 }
@@ -387,10 +389,33 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 XS_TRY(make_tmap(&tmap_q, ix->q16.as<__nv_bfloat16>() + q0 * ix->d_pad, round_up(c, GEMM_BM), ix->d_pad, GEMM_BM));
                 ta = &tmap_q; row0 = 0;
             }
+            // threshold bootstrap on a strided sample of database tiles (skipped when the sample would be the whole database)
+            const float* thr0 = nullptr;
+            XS_TRY(ix->thr0.ensure((size_t)c * sizeof(float)));
+            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms) {
+                GemmPlan sp = plan_gemm_sample(plan, ix->num_sms);
+                const int64_t sslots = (int64_t)sp.m_tiles * sp.splits * GEMM_BM;
+                XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));
+                XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
+                XS_TRY(ix->pool_thr.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
+                cudaError_t es = launch_gemm_topk(*ta, ix->tmap_db_b, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+                                                  ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
+                                                  (int)row0, nullptr, ix->stream);
+                if (es != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk (sample) launch failed: %s", cudaGetErrorString(es));
+                launch_sample_threshold(ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), sp.splits, sp.cap, k,
+                                        ix->eps.as<float>() + q0, ix->thr0.as<float>(), c, ix->stream);
+                thr0 = ix->thr0.as<float>();
+                launches += 2;
+            } else if (ix->debug_thr != 0.f) {
+                std::vector<float> h((size_t)c, ix->debug_thr);
+                CU_TRY(cudaMemcpyAsync(ix->thr0.p, h.data(), (size_t)c * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+                CU_TRY(cudaStreamSynchronize(ix->stream));
+                thr0 = ix->thr0.as<float>();
+            }
             if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
             cudaError_t e = launch_gemm_topk(*ta, ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
-                                             (int)row0, ix->stream);
+                                             (int)row0, thr0, ix->stream);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));
             if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
             FinaliseArgs fa{};

@@ -180,6 +180,48 @@ void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st) {
     finalise_kernel<<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max);
 }
 
+// ---- threshold bootstrap ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sample_threshold_kernel(const uint64_t* __restrict__ pool_items, const int* __restrict__ pool_count, int P, int cap,
+                        int k, const float* __restrict__ eps, float* __restrict__ thr0) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t misc[2];
+    __shared__ uint32_t sh_total;
+    const int64_t q = blockIdx.x;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) sh_total = 0;
+    __syncthreads();
+    uint32_t t = 0;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) t += (uint32_t)pool_count[pool_slot(q, p, P)];
+    if (t) atomicAdd(&sh_total, t);
+    __syncthreads();
+    const uint32_t total = sh_total;
+    if (total < (uint32_t)k) { if (threadIdx.x == 0) thr0[q] = -INFINITY; return; }
+    auto each = [&](auto fn) {
+        for (int p = warp; p < P; p += nwarps) {
+            const int64_t slot = pool_slot(q, p, P);
+            const int cnt = pool_count[slot];
+            const uint64_t* lst = pool_items + slot * cap;
+            for (int b = 0; b < cnt; b += 32) {
+                int i = b + lane;
+                bool valid = i < cnt;
+                fn(valid ? lst[i] : 0ull, valid);
+            }
+        }
+    };
+    const uint64_t T = block_kth_largest(each, (uint32_t)k, 4, hist, misc);
+    if (threadIdx.x == 0) {
+        const float cut = key_score((uint32_t)(T >> 32)) - 2.f * eps[q];
+        thr0[q] = nextafterf(cut, -INFINITY);        // the main pass keeps scores strictly above thr0
+    }
+}
+
+void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
+                             const float* eps, float* thr0, int64_t nq, cudaStream_t st) {
+    if (nq <= 0) return;
+    sample_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(pool_items, pool_count, P, cap, k, eps, thr0);
+}
+
 // ---- multi-GPU merge -------------------------------------------------------------------------------
 // in: [parts][nq][k] (score desc, id asc inside every part; parts own increasing id ranges, so the
 // flat position p*k + r orders equal scores by ascending id).  One CTA per query.

@@ -105,8 +105,8 @@ constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 // ---- the kernel ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                 int m_tiles, int n_tiles, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
-                 int k, int k_keep, int cap, const float* __restrict__ eps,
+                 int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
+                 int k, int k_keep, int cap, const float* __restrict__ eps, const float* __restrict__ thr0,
                  uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -149,7 +149,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         const uint32_t full = smem_u32(&bars->full[stage]);
                         mbar_expect_tx(full, STAGE_BYTES);
                         tma_load_2d(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
-                        tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * GEMM_BN, HINT_EVICT_FIRST);
+                        tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * tile_stride * GEMM_BN, HINT_EVICT_FIRST);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -199,7 +199,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const int64_t slot = ((int64_t)mt * splits + sp) * GEMM_BM + m;
             uint64_t* list = pool_items + slot * cap;
             int cnt = 0;
-            float thr = active ? -INFINITY : INFINITY;
+            float thr = active ? (thr0 ? thr0[q] : -INFINITY) : INFINITY;
             uint32_t thr_rec = 0;
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -211,7 +211,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     uint32_t v[32];
                     tc_ld32(taddr + c * 32, v);
                     tc_ld_wait();
-                    const int64_t row_base = (int64_t)t * GEMM_BN + c * 32;
+                    const int64_t row_base = (int64_t)t * tile_stride * GEMM_BN + c * 32;
                     const int64_t lim = n_valid - row_base;                 // rows >= n_valid are zero padding
                     if (lim >= 32) {
 #pragma unroll
@@ -235,7 +235,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         const int c_src = __shfl_sync(0xffffffffu, cnt, src);
                         uint32_t T;
                         const int c_new = warp_prune(l, c_src, k_keep, true, 0.f, my_hist, T);
-                        if (lane == src) { cnt = c_new; thr = key_score(T); thr_rec = max(thr_rec, T); }
+                        if (lane == src) { cnt = c_new; thr = fmaxf(thr, key_score(T)); thr_rec = max(thr_rec, T); }
                     }
                 }
                 tc_fence_before();
@@ -297,16 +297,35 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
     p.cap = 2 * p.k_keep;
     const int64_t jobs = (int64_t)p.m_tiles * p.splits;
     p.grid = (int)(jobs < num_sms ? jobs : num_sms);
+    p.tile_stride = 1;
+    return p;
+}
+
+// Threshold bootstrap: S database tiles spread evenly over the database (stride), one tile per job.
+// The k-th best score of that sample is a valid lower bound of the k-th best of the whole database.
+GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms) {
+    GemmPlan p = main_plan;
+    const int all_tiles = main_plan.n_tiles;
+    int s = num_sms / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
+    if (s < 16) s = 16;
+    if (s > num_sms) s = num_sms;
+    if (s > all_tiles) s = all_tiles;
+    p.n_tiles = s;
+    p.tile_stride = all_tiles / s;
+    p.splits = s;                                   // one tile per job: no list can fill up (256 < cap)
+    const int64_t jobs = (int64_t)p.m_tiles * p.splits;
+    p.grid = (int)(jobs < num_sms ? jobs : num_sms);
     return p;
 }
 
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
-                             uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0, cudaStream_t st) {
+                             uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
+                             const float* thr0, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
-    gemm_topk_kernel<<<plan.grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.splits,
-                                                                  d_pad / GEMM_BK, a_row0, nq, n_valid, k, plan.k_keep, plan.cap, eps,
+    gemm_topk_kernel<<<plan.grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits,
+                                                                  d_pad / GEMM_BK, a_row0, nq, n_valid, k, plan.k_keep, plan.cap, eps, thr0,
                                                                   pool_items, pool_count, pool_thr);
     return cudaGetLastError();
 }

@@ -58,13 +58,16 @@ struct GemmPlan {
     int k_keep;       // items kept by a mid-job trim
     int cap;          // capacity of one partial list (>= 2 * k_keep)
     int grid;         // CTAs launched
+    int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
 };
 GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits);
+GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms);
 size_t   gemm_smem_bytes();
 // tmap_q: [nq_pad128][d_pad] bf16, box {64,128};  tmap_db: [n_pad][d_pad] bf16, box {64,256}
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
-                             uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0, cudaStream_t st);
+                             uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
+                             const float* thr0, cudaStream_t st);
 
 // ---- finalise.cu --------------------------------------------------------------------------------
 struct FinaliseArgs {
@@ -80,6 +83,9 @@ struct FinaliseArgs {
 };
 int  finalise_cand_max(int k);
 void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);
+// thr0[q] = (k-th best pooled coarse score) - 2 eps[q], one ulp lower; -inf when fewer than k items.
+void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
+                             const float* eps, float* thr0, int64_t nq, cudaStream_t st);
 // Multi-GPU merge of [parts][nq][k] lists.
 void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts, int64_t nq, int k,
                         int64_t* out_idx, float* out_score, cudaStream_t st);

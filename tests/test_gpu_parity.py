@@ -96,12 +96,14 @@ def test_knn_wrapper(pkg, synth, oracle):
     assert (knn.N, knn.D) == (2000, 128) and knn.database.flags["C_CONTIGUOUS"]
     sims, ids = knn.search(q.T, 7)
     rs, ri = oracle.knn_search(v.T, q.T, 7, "cosine")
-    np.testing.assert_array_equal(ids, ri)
+    s64 = oracle.scores_f64(v, q)
+    _check_lists(oracle, ids, ri, s64, "KNN cosine")
     np.testing.assert_allclose(sims, rs, rtol=1e-5, atol=1e-7)
     knn2 = pkg.KNN(v.T * 1.5, "euclidean")
     dist, ids2 = knn2.search(q.T, 7)
     rd, ri2 = oracle.knn_search(v.T * 1.5, q.T, 7, "euclidean")
-    np.testing.assert_array_equal(ids2, ri2)
+    d64 = -(((v.T * 1.5).astype(np.float64)[:, None, :] - q.T.astype(np.float64)[None, :, :]) ** 2).sum(-1)
+    _check_lists(oracle, ids2, ri2, d64, "KNN euclidean")
     np.testing.assert_allclose(dist, rd, rtol=1e-4, atol=1e-5)
     with pytest.raises(KeyError):
         pkg.KNN(v.T, "manhattan")
