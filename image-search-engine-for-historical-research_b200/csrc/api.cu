@@ -298,7 +298,13 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
         launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->num_sms, ix->stream);
         *launches += (c + 3) / 4;
         if (self_base >= 0) { boost_self_kernel<<<(c + 127) / 128, 128, 0, ix->stream>>>(ix->scores.as<float>(), ix->n, c, self_base + q0); ++*launches; }
-        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, true, ix->pool_items.as<uint64_t>(),
+        const float* thr0 = nullptr;
+        if (ix->n >= 8 * SLICE_ROWS) {
+            XS_TRY(ix->thr0.ensure((size_t)chunk_max * sizeof(float)));
+            launch_scores_sample_threshold(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, true, ix->thr0.as<float>(), ix->stream);
+            thr0 = ix->thr0.as<float>(); ++*launches;
+        }
+        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, thr0, true, ix->pool_items.as<uint64_t>(),
                                ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
         FinaliseArgs fa{};
         fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
@@ -345,7 +351,13 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->num_sms, ix->stream);
             launches += (c + 1) / 2;
             if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
-            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, false, ix->pool_items.as<uint64_t>(),
+            const float* thr0 = nullptr;
+            if (ix->n >= 8 * SLICE_ROWS) {
+                XS_TRY(ix->thr0.ensure((size_t)chunk_max * sizeof(float)));
+                launch_scores_sample_threshold(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, false, ix->thr0.as<float>(), ix->stream);
+                thr0 = ix->thr0.as<float>(); ++launches;
+            }
+            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, thr0, false, ix->pool_items.as<uint64_t>(),
                                    ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
@@ -392,8 +404,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             // threshold bootstrap on a strided sample of database tiles (skipped when the sample would be the whole database)
             const float* thr0 = nullptr;
             XS_TRY(ix->thr0.ensure((size_t)c * sizeof(float)));
-            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms) {
-                GemmPlan sp = plan_gemm_sample(plan, ix->num_sms);
+            GemmPlan sp = plan_gemm_sample(plan, ix->num_sms);
+            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 4 * k) {
                 const int64_t sslots = (int64_t)sp.m_tiles * sp.splits * GEMM_BM;
                 XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));
                 XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));

@@ -11,7 +11,9 @@
 
 namespace xs {
 
-constexpr int FIN_THREADS = 512;
+constexpr int FIN_THREADS = 1024;
+constexpr int FIN_MAX_LISTS = 4096;          // partial lists per query that the shared-memory gather supports
+constexpr int FIN_SMEM_BUDGET = 200 * 1024;  // dynamic shared memory the finalise kernel may ask for
 
 // Descending bitonic sort of m (power of two) 64-bit items in shared memory.
 __device__ void block_sort_desc(uint64_t* a, int m) {
@@ -30,42 +32,96 @@ __device__ void block_sort_desc(uint64_t* a, int m) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
-finalise_kernel(FinaliseArgs a, int cand_max) {
-    extern __shared__ uint64_t cand[];                  // [cand_max], cand_max is a power of two
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t misc[2];
-    __shared__ uint32_t sh_total, sh_ncand, sh_flag, sh_selfkey;
-    const int64_t q = blockIdx.x;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-
-    if (threadIdx.x == 0) { sh_total = 0; sh_ncand = 0; sh_flag = 0; sh_selfkey = 0; }
+// Exclusive prefix sum of offs[0..P) in place (offs[P] = total), whole CTA.  scratch: 33 words.
+__device__ void block_exclusive_scan(int* offs, int P, int* scratch) {
+    const int nth = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (P + nth - 1) / nth;
+    const int lo = min(tid * chunk, P), hi = min(lo + chunk, P);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += offs[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) scratch[warp] = inc;
     __syncthreads();
-    {   // total number of pooled candidates + largest "dropped above this" mark
-        uint32_t t = 0, thr = 0;
-        for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
-            int64_t slot = pool_slot(q, p, a.P);
-            t += (uint32_t)a.pool_count[slot];
-            thr = max(thr, a.pool_thr[slot]);
-        }
-        if (t) atomicAdd(&sh_total, t);
-        if (thr) atomicMax(&sh_flag, thr);
+    if (warp == 0) {
+        int w = (lane < (nth >> 5)) ? scratch[lane] : 0, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        scratch[lane] = winc - w;
+        if (lane == 31) scratch[32] = winc;
     }
     __syncthreads();
-    const uint32_t total = sh_total;
-    const uint32_t max_thr = sh_flag;
+    int run = scratch[warp] + inc - sum;
+    for (int i = lo; i < hi; ++i) { int c = offs[i]; offs[i] = run; run += c; }
+    if (tid == 0) offs[P] = scratch[32];
     __syncthreads();
-    if (threadIdx.x == 0) sh_flag = 0;
+}
+
+// Copies every pooled item of query q into shared memory (flat), all loads independent.
+// offs[] must hold the exclusive scan of the list counts.  Returns nothing; items[0..total) filled.
+__device__ void gather_pool(const uint64_t* __restrict__ pool_items, int64_t q, int P, int cap,
+                            const int* offs, int total, uint64_t* items) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int lo = 0, hi = P - 1;                       // largest p with offs[p] <= i
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid - 1; }
+        items[i] = pool_items[pool_slot(q, lo, P) * cap + (i - offs[lo])];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
+    extern __shared__ uint64_t fin_smem[];              // [cand_max] candidates | [item_cap] gathered items | [P+1] offsets
+    uint64_t* cand = fin_smem;
+    uint64_t* items = fin_smem + cand_max;
+    int* offs = reinterpret_cast<int*>(items + item_cap);
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t misc[2];
+    __shared__ int scan_scratch[33];
+    __shared__ uint32_t sh_ncand, sh_flag, sh_selfkey;
+    const int64_t q = blockIdx.x;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool staged = a.P <= FIN_MAX_LISTS;           // offsets fit -> try the shared-memory gather
+
+    if (threadIdx.x == 0) { sh_ncand = 0; sh_flag = 0; sh_selfkey = 0; }
+    __syncthreads();
+    uint32_t total = 0;
+    {   // list sizes, and the largest "something above this key was dropped upstream" mark
+        uint32_t thr = 0, t = 0;
+        for (int p = threadIdx.x; p < a.P; p += blockDim.x) {
+            const int64_t slot = pool_slot(q, p, a.P);
+            const int c = a.pool_count[slot];
+            if (staged) offs[p] = c; else t += (uint32_t)c;
+            thr = max(thr, a.pool_thr[slot]);
+        }
+        if (thr) atomicMax(&sh_flag, thr);
+        if (!staged && t) atomicAdd(&sh_ncand, t);
+        __syncthreads();
+        if (staged) { block_exclusive_scan(offs, a.P, scan_scratch); total = (uint32_t)offs[a.P]; }
+        else { total = sh_ncand; __syncthreads(); if (threadIdx.x == 0) sh_ncand = 0; __syncthreads(); }
+    }
+    const uint32_t max_thr = sh_flag;
+    const bool in_smem = staged && total <= (uint32_t)item_cap;
+    if (in_smem) gather_pool(a.pool_items, q, a.P, a.cap, offs, (int)total, items);
 
     auto each = [&](auto fn) {
-        for (int p = warp; p < a.P; p += nwarps) {
-            const int64_t slot = pool_slot(q, p, a.P);
-            const int cnt = a.pool_count[slot];
-            const uint64_t* lst = a.pool_items + slot * a.cap;
-            for (int b = 0; b < cnt; b += 32) {
-                int i = b + lane;
-                bool valid = i < cnt;
-                fn(valid ? lst[i] : 0ull, valid);
+        if (in_smem) {
+            const int n_up = ((int)total + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
+            for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
+                bool valid = i < (int)total;
+                fn(valid ? items[i] : 0ull, valid);
+            }
+        } else {
+            for (int p = warp; p < a.P; p += nwarps) {
+                const int64_t slot = pool_slot(q, p, a.P);
+                const int cnt = a.pool_count[slot];
+                const uint64_t* lst = a.pool_items + slot * a.cap;
+                for (int b = 0; b < cnt; b += 32) {
+                    int i = b + lane;
+                    bool valid = i < cnt;
+                    fn(valid ? lst[i] : 0ull, valid);
+                }
             }
         }
     };
@@ -174,39 +230,48 @@ int finalise_cand_max(int k) {
 void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
     const int cand_max = finalise_cand_max(a.k);
-    const size_t smem = (size_t)cand_max * sizeof(uint64_t);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(finalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    finalise_kernel<<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max);
+    const size_t offs_bytes = (a.P <= FIN_MAX_LISTS) ? ((size_t)(a.P + 2) * sizeof(int) + 8) : 8;
+    const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes;
+    // room for the gathered pool items: what the pools can hold, capped by the shared-memory budget
+    size_t want_items = (size_t)a.P * (size_t)a.cap;
+    size_t max_items = (FIN_SMEM_BUDGET > fixed) ? (FIN_SMEM_BUDGET - fixed) / sizeof(uint64_t) : 0;
+    if (max_items > 12288) max_items = 12288;      // 96 KB: two CTAs per SM; larger pools take the global-memory path
+    int item_cap = (int)(want_items < max_items ? want_items : max_items);
+    if (a.P > FIN_MAX_LISTS) item_cap = 0;
+    const size_t smem = fixed + (size_t)item_cap * sizeof(uint64_t);
+    cudaFuncSetAttribute(finalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
+    finalise_kernel<<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max, item_cap);
 }
 
 // ---- threshold bootstrap ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 sample_threshold_kernel(const uint64_t* __restrict__ pool_items, const int* __restrict__ pool_count, int P, int cap,
                         int k, const float* __restrict__ eps, float* __restrict__ thr0) {
+    extern __shared__ uint64_t smp_items[];            // [8 * P]: the sample pass leaves at most 8 items per list
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[2];
     __shared__ uint32_t sh_total;
     const int64_t q = blockIdx.x;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (threadIdx.x == 0) sh_total = 0;
     __syncthreads();
-    uint32_t t = 0;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) t += (uint32_t)pool_count[pool_slot(q, p, P)];
-    if (t) atomicAdd(&sh_total, t);
+    const int n = 8 * P;
+    uint32_t mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int p = i >> 3, j = i & 7;
+        const int64_t slot = pool_slot(q, p, P);
+        const bool valid = j < pool_count[slot];
+        smp_items[i] = valid ? pool_items[slot * cap + j] : 0ull;
+        mine += valid ? 1u : 0u;
+    }
+    if (mine) atomicAdd(&sh_total, mine);
     __syncthreads();
     const uint32_t total = sh_total;
     if (total < (uint32_t)k) { if (threadIdx.x == 0) thr0[q] = -INFINITY; return; }
+    const int n_up = (n + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
     auto each = [&](auto fn) {
-        for (int p = warp; p < P; p += nwarps) {
-            const int64_t slot = pool_slot(q, p, P);
-            const int cnt = pool_count[slot];
-            const uint64_t* lst = pool_items + slot * cap;
-            for (int b = 0; b < cnt; b += 32) {
-                int i = b + lane;
-                bool valid = i < cnt;
-                fn(valid ? lst[i] : 0ull, valid);
-            }
+        for (int i = threadIdx.x; i < n_up; i += blockDim.x) {
+            const uint64_t it = (i < n) ? smp_items[i] : 0ull;
+            fn(it, it != 0ull);
         }
     };
     const uint64_t T = block_kth_largest(each, (uint32_t)k, 4, hist, misc);
@@ -219,13 +284,13 @@ sample_threshold_kernel(const uint64_t* __restrict__ pool_items, const int* __re
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
-    sample_threshold_kernel<<<(unsigned)nq, 256, 0, st>>>(pool_items, pool_count, P, cap, k, eps, thr0);
+    sample_threshold_kernel<<<(unsigned)nq, 1024, (size_t)8 * P * sizeof(uint64_t), st>>>(pool_items, pool_count, P, cap, k, eps, thr0);
 }
 
 // ---- multi-GPU merge -------------------------------------------------------------------------------
 // in: [parts][nq][k] (score desc, id asc inside every part; parts own increasing id ranges, so the
 // flat position p*k + r orders equal scores by ascending id).  One CTA per query.
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(512)
 merge_parts_kernel(const int64_t* __restrict__ in_idx, const float* __restrict__ in_score, int parts,
                    int64_t nq, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_score, int m) {
     extern __shared__ uint64_t cand[];                  // [m] power of two >= parts*k
@@ -265,7 +330,7 @@ void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts,
     const size_t smem = (size_t)m * sizeof(uint64_t);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    merge_parts_kernel<<<(unsigned)nq, FIN_THREADS, smem, st>>>(in_idx, in_score, parts, nq, k, out_idx, out_score, m);
+    merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(in_idx, in_score, parts, nq, k, out_idx, out_score, m);
 }
 
 }  // namespace xs

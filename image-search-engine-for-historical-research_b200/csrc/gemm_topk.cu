@@ -106,7 +106,7 @@ constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
-                 int k, int k_keep, int cap, const float* __restrict__ eps, const float* __restrict__ thr0,
+                 int k, int k_keep, int cap, int sample_mode, const float* __restrict__ eps, const float* __restrict__ thr0,
                  uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -201,6 +201,44 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             int cnt = 0;
             float thr = active ? (thr0 ? thr0[q] : -INFINITY) : INFINITY;
             uint32_t thr_rec = 0;
+            if (sample_mode) {
+                // Threshold bootstrap: only the 8 best scores of this lane's tile(s) are needed (the
+                // union of per-tile top-8 lists holds >= k items, and its k-th best is a valid lower
+                // bound of the database's k-th best).  Sorted in registers, no lists, no trims.
+                float top[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
+                for (int t = t0; t < t1; ++t, ++it) {
+                    const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
+#pragma unroll 1
+                    for (int c = 0; c < GEMM_BN / 32; ++c) {
+                        uint32_t v[32];
+                        tc_ld32(taddr + c * 32, v);
+                        tc_ld_wait();
+                        const int64_t lim = n_valid - ((int64_t)t * tile_stride * GEMM_BN + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float s = __uint_as_float(v[i]);
+                            if (s > top[7] && i < lim) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { const float hi = fmaxf(top[j], s); s = fminf(top[j], s); top[j] = hi; }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&bars->tempty[acc]));
+                }
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (top[j] > -INFINITY) list[cnt++] = make_item(top[j], 0u);
+                }
+                pool_count[slot] = cnt;
+                pool_thr[slot] = 0u;
+                continue;
+            }
             for (int t = t0; t < t1; ++t, ++it) {
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
@@ -298,6 +336,7 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
     const int64_t jobs = (int64_t)p.m_tiles * p.splits;
     p.grid = (int)(jobs < num_sms ? jobs : num_sms);
     p.tile_stride = 1;
+    p.sample_mode = 0;
     return p;
 }
 
@@ -312,7 +351,8 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms) {
     if (s > all_tiles) s = all_tiles;
     p.n_tiles = s;
     p.tile_stride = all_tiles / s;
-    p.splits = s;                                   // one tile per job: no list can fill up (256 < cap)
+    p.splits = s;                                   // one tile per job
+    p.sample_mode = 1;                              // register top-8 per (query, tile)
     const int64_t jobs = (int64_t)p.m_tiles * p.splits;
     p.grid = (int)(jobs < num_sms ? jobs : num_sms);
     return p;
@@ -325,7 +365,7 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
     gemm_topk_kernel<<<plan.grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits,
-                                                                  d_pad / GEMM_BK, a_row0, nq, n_valid, k, plan.k_keep, plan.cap, eps, thr0,
+                                                                  d_pad / GEMM_BK, a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, eps, thr0,
                                                                   pool_items, pool_count, pool_thr);
     return cudaGetLastError();
 }

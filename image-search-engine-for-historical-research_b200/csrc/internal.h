@@ -47,8 +47,12 @@ void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n,
 //   exact = false: keep items within the eps band below the slice's k-th best
 //   exact = true : keep exactly the slice's k best (full 64-bit item order)
 void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                            const float* eps, bool exact, uint64_t* pool_items, int* pool_count,
+                            const float* eps, const float* thr0, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st);
+// thr0[q] = lower bound of query q's k-th best score, from 16384 scores sampled at a fixed stride
+// (minus the 2*eps band unless exact); -inf when the sample is too small for k.
+void launch_scores_sample_threshold(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
+                                    const float* eps, bool exact, float* thr0, cudaStream_t st);
 
 // ---- gemm_topk.cu -------------------------------------------------------------------------------
 struct GemmPlan {
@@ -58,6 +62,7 @@ struct GemmPlan {
     int k_keep;       // items kept by a mid-job trim
     int cap;          // capacity of one partial list (>= 2 * k_keep)
     int grid;         // CTAs launched
+    int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)
     int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
 };
 GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits);

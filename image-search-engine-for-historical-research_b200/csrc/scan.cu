@@ -172,8 +172,9 @@ void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n,
 // grid = (P, nq); CTA (p, q) reduces rows [p*SLICE_ROWS, ...) of query q to one partial list.
 __global__ void __launch_bounds__(256)
 scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t n, int k,
-                       const float* __restrict__ eps, int exact, uint64_t* __restrict__ pool_items,
-                       int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr, int P, int cap) {
+                       const float* __restrict__ eps, const float* __restrict__ thr0, int exact,
+                       uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr,
+                       int P, int cap) {
     __shared__ uint32_t keys[SLICE_ROWS];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[2];
@@ -201,6 +202,10 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
         if (exact) cut = T;
         else cut = (uint64_t)score_key(key_score((uint32_t)(T >> 32)) - 2.f * eps[q]) << 32;
     }
+    if (thr0) {                                         // database-wide lower bound from the sampled scores
+        const uint64_t c0 = (uint64_t)score_key(thr0[q]) << 32;
+        cut = cut > c0 ? cut : c0;
+    }
     const int64_t slot = pool_slot(q, p, P);
     uint64_t* out = pool_items + slot * cap;
     each([&](uint64_t it, bool valid) {
@@ -220,11 +225,48 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
 }
 
 void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                            const float* eps, bool exact, uint64_t* pool_items, int* pool_count,
+                            const float* eps, const float* thr0, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st) {
     dim3 grid((unsigned)P, (unsigned)nq);
-    scores_to_pools_kernel<<<grid, 256, 0, st>>>(scores, score_pitch, n, k, eps, exact ? 1 : 0,
+    scores_to_pools_kernel<<<grid, 256, 0, st>>>(scores, score_pitch, n, k, eps, thr0, exact ? 1 : 0,
                                                  pool_items, pool_count, pool_thr, P, cap);
+}
+
+// ---- scores_sample_threshold -----------------------------------------------------------------------
+// One CTA per query: the k-th best of SCORE_SAMPLE scores taken at a fixed stride over the row range
+// is a lower bound of the k-th best of all rows; slices then emit only what can still matter.
+constexpr int SCORE_SAMPLE = 16384;
+__global__ void __launch_bounds__(1024)
+scores_sample_threshold_kernel(const float* __restrict__ scores, int64_t pitch, int64_t n, int k,
+                               const float* __restrict__ eps, int exact, float* __restrict__ thr0) {
+    extern __shared__ uint32_t skeys[];                 // [SCORE_SAMPLE]
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t misc[2];
+    const int64_t q = blockIdx.x;
+    const int64_t stride = n / SCORE_SAMPLE > 0 ? n / SCORE_SAMPLE : 1;
+    const int cnt = (int)min((int64_t)SCORE_SAMPLE, n / stride);
+    const float* s = scores + q * pitch;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) skeys[i] = score_key(s[(int64_t)i * stride]);
+    __syncthreads();
+    if (cnt < 4 * k) { if (threadIdx.x == 0) thr0[q] = -INFINITY; return; }
+    const int cnt_up = (cnt + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
+    auto each = [&](auto fn) {
+        for (int i = threadIdx.x; i < cnt_up; i += blockDim.x) {
+            bool valid = i < cnt;
+            fn(valid ? ((uint64_t)skeys[i] << 32) : 0ull, valid);
+        }
+    };
+    const uint64_t T = block_kth_largest(each, (uint32_t)k, 4, hist, misc);
+    if (threadIdx.x == 0) {
+        const float kth = key_score((uint32_t)(T >> 32));
+        thr0[q] = exact ? kth : nextafterf(kth - 2.f * eps[q], -INFINITY);
+    }
+}
+
+void launch_scores_sample_threshold(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
+                                    const float* eps, bool exact, float* thr0, cudaStream_t st) {
+    cudaFuncSetAttribute(scores_sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCORE_SAMPLE * 4);
+    scores_sample_threshold_kernel<<<(unsigned)nq, 1024, SCORE_SAMPLE * 4, st>>>(scores, score_pitch, n, k, eps, exact ? 1 : 0, thr0);
 }
 
 }  // namespace xs
