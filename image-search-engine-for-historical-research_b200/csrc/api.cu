@@ -47,6 +47,20 @@ struct Buf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct PinnedBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t need) {
+        if (need <= cap) return XS_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, need + need / 4);
+        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return fail(XS_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", need, cudaGetErrorString(e)); }
+        cap = need + need / 4;
+        return XS_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct xs_index {
     int device = 0; int num_sms = 0;
     int64_t n = 0, n_pad = 0, id_offset = 0;
@@ -57,6 +71,7 @@ struct xs_index {
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; float debug_thr = 0.f;
     // workspace
     Buf q_raw, q32, q16, eps, thr0, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -140,6 +155,7 @@ static void index_free(xs_index* ix) {
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
+    ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
     if (ix->db32) cudaFree(ix->db32);
     if (ix->dstats) cudaFree(ix->dstats);
@@ -261,6 +277,7 @@ extern "C" int xs_index_stats(const xs_index* cix, xs_stats* out) {
 enum { PATH_SCAN = 1, PATH_GEMM = 2, PATH_EXACT = 3 };
 
 struct CoreArgs {
+    const float* raw;           // optional: caller's fp32 row-major [nq][d] device matrix, not yet copied into q32
     float* q32;                 // [nq][d_pad] device, fp32 (normalised in place when prep_renorm)
     int64_t nq;
     int k;
@@ -319,6 +336,23 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
     return XS_OK;
 }
 
+// Query preparation: one fused kernel when the raw layout allows it, else layout -> (zero pad) -> prep.
+static int prepare_queries(xs_index* ix, const CoreArgs& a, __nv_bfloat16* q16, int* launches) {
+    if (!a.prep) return XS_OK;
+    const int64_t nq_pad = round_up(a.nq, GEMM_BM);
+    if (a.raw && launch_prep_queries_fused(a.raw, a.q32, q16, a.nq, nq_pad, ix->d, ix->d_pad, a.prep_renorm, ix->dstats,
+                                           ix->eps_sigmas, ix->eps.as<float>(), ix->stream)) { ++*launches; return XS_OK; }
+    if (a.raw) { launch_layout_rows(a.raw, XS_F32, false, ix->d, a.nq, ix->d, ix->d_pad, a.q32, ix->stream); ++*launches; }
+    if (q16 && nq_pad > a.nq) {
+        const int64_t cnt = (nq_pad - a.nq) * ix->d_pad;
+        zero_rows_bf16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->stream>>>(q16 + a.nq * ix->d_pad, cnt);
+        ++*launches;
+    }
+    launch_prep_queries(a.q32, q16, a.nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->stream);
+    ++*launches;
+    return XS_OK;
+}
+
 static int search_core(xs_index* ix, const CoreArgs& a) {
     const int64_t nq = a.nq; const int k = a.k;
     int launches = 0;
@@ -331,12 +365,12 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
     ix->ev_valid = true;
 
     if (a.path == PATH_EXACT) {
-        if (a.prep) { launch_prep_queries(a.q32, nullptr, nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->stream); ++launches; }
+        XS_TRY(prepare_queries(ix, a, nullptr, &launches));
         CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
         XS_TRY(run_exact(ix, a.q32, nq, k, a.self_base, a.out_idx, a.out_score, a.status, &launches));
         CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
     } else if (a.path == PATH_SCAN) {
-        if (a.prep) { launch_prep_queries(a.q32, nullptr, nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->stream); ++launches; }
+        XS_TRY(prepare_queries(ix, a, nullptr, &launches));
         const int P = (int)((ix->n + SLICE_ROWS - 1) / SLICE_ROWS);
         const int cap = 2 * k + 256;
         const int64_t chunk_max = 8;
@@ -373,20 +407,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         const int64_t batch_max = 8192;
         const int64_t nq_pad = round_up(nq < batch_max ? nq : batch_max, GEMM_BM);
         CUtensorMap tmap_q;
-        if (!a.tmap_a) {
-            XS_TRY(ix->q16.ensure((size_t)round_up(nq, GEMM_BM) * ix->d_pad * 2));
-            const int64_t pad_rows = round_up(nq, GEMM_BM) - nq;
-            if (pad_rows) {
-                const int64_t cnt = pad_rows * ix->d_pad;
-                zero_rows_bf16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->stream>>>(ix->q16.as<__nv_bfloat16>() + nq * ix->d_pad, cnt);
-                ++launches;
-            }
-        }
-        if (a.prep) {
-            launch_prep_queries(a.q32, a.tmap_a ? nullptr : ix->q16.as<__nv_bfloat16>(), nq, ix->d_pad, a.prep_renorm, ix->dstats,
-                                ix->eps_sigmas, ix->eps.as<float>(), ix->stream);
-            ++launches;
-        }
+        if (!a.tmap_a) XS_TRY(ix->q16.ensure((size_t)round_up(nq, GEMM_BM) * ix->d_pad * 2));
+        XS_TRY(prepare_queries(ix, a, a.tmap_a ? nullptr : ix->q16.as<__nv_bfloat16>(), &launches));
         (void)nq_pad;
         for (int64_t q0 = 0; q0 < nq; q0 += batch_max) {
             const int64_t c = (nq - q0 < batch_max) ? nq - q0 : batch_max;
@@ -478,6 +500,47 @@ static int rerun_uncertified(xs_index* ix, float* q32, int64_t nq, int k, int64_
     return XS_OK;
 }
 
+// Host-API epilogue: results + certificate bits land in pinned memory with ONE synchronisation;
+// uncertified queries (rare) are re-run on the exact path and re-copied; then a plain memcpy to the
+// caller's (possibly pageable) buffers.
+static int finish_to_host(xs_index* ix, float* q32, int64_t nq, int k, int64_t self_base, int64_t* dev_idx, float* dev_score,
+                          int* dev_status, bool coarse, int64_t* out_idx, float* out_score) {
+    const size_t nb_i = (size_t)nq * k * sizeof(int64_t), nb_s = (size_t)nq * k * sizeof(float);
+    XS_TRY(ix->h_idx.ensure(nb_i));
+    XS_TRY(ix->h_score.ensure(nb_s));
+    XS_TRY(ix->h_status.ensure((size_t)(nq + 1) * sizeof(int)));
+    CU_TRY(cudaMemcpyAsync(ix->h_idx.p, dev_idx, nb_i, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_score) CU_TRY(cudaMemcpyAsync(ix->h_score.p, dev_score, nb_s, cudaMemcpyDeviceToHost, ix->stream));
+    if (coarse) {
+        CU_TRY(cudaMemcpyAsync(ix->h_status.as<int>() + 1, dev_status, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(ix->stream));
+    if (coarse) {
+        const int* st = ix->h_status.as<int>() + 1;
+        ix->stats.n_candidates = ix->h_status.as<int>()[0];
+        int launches = 0;
+        int64_t reruns = 0;
+        for (int64_t q = 0; q < nq;) {
+            if (!(st[q] & ST_UNCERTIFIED)) { ++q; continue; }
+            int64_t e = q + 1;
+            while (e < nq && e - q < 16 && (st[e] & ST_UNCERTIFIED)) ++e;
+            XS_TRY(run_exact(ix, q32 + q * ix->d_pad, e - q, k, self_base >= 0 ? self_base + q : -1, dev_idx + q * k,
+                             dev_score + q * k, nullptr, &launches));
+            CU_TRY(cudaMemcpyAsync(ix->h_idx.as<int64_t>() + q * k, dev_idx + q * k, (size_t)(e - q) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+            if (out_score) CU_TRY(cudaMemcpyAsync(ix->h_score.as<float>() + q * k, dev_score + q * k, (size_t)(e - q) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+            reruns += e - q;
+            q = e;
+        }
+        if (reruns) CU_TRY(cudaStreamSynchronize(ix->stream));
+        ix->stats.n_exact_rerun = reruns;
+        ix->stats.gpu_launches += launches;
+    }
+    memcpy(out_idx, ix->h_idx.p, nb_i);
+    if (out_score) memcpy(out_score, ix->h_score.p, nb_s);
+    return XS_OK;
+}
+
 static int check_search_args(const xs_index* ix, int64_t nq, int k) {
     if (!ix) return fail(XS_ERR_ARG, "null index");
     if (nq <= 0) return fail(XS_ERR_ARG, "no queries (nq=%lld)", (long long)nq);
@@ -500,14 +563,13 @@ extern "C" int xs_search_dev(xs_index* ix, const float* q_dev, int64_t nq, int r
     CU_TRY(cudaStreamWaitEvent(ix->stream, ev, 0));
     XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
     XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
-    launch_layout_rows(q_dev, XS_F32, false, ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream);
     CoreArgs a{};
+    a.raw = q_dev;
     a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
     a.self_base = -1; a.out_idx = out_idx_dev; a.out_score = out_score_dev;
     a.status = out_status_dev ? out_status_dev : ix->status.as<int>();
     a.path = choose_path(ix, nq, k);
     int rc = search_core(ix, a);
-    if (rc == XS_OK) { ix->stats.gpu_launches += 1; }
     if (rc == XS_OK && !out_status_dev && a.path != PATH_EXACT)
         rc = rerun_uncertified(ix, a.q32, nq, k, -1, out_idx_dev, out_score_dev, a.status);
     cudaEventRecord(ev, ix->stream);
@@ -531,18 +593,16 @@ extern "C" int xs_search(xs_index* ix, const void* q, int dtype, int64_t nq, int
     XS_TRY(ix->out_idx.ensure((size_t)nq * k * sizeof(int64_t)));
     XS_TRY(ix->out_score.ensure((size_t)nq * k * sizeof(float)));
     XS_TRY(stage_host_rows(q, dtype, colmajor, colmajor ? stride_col : stride_row, 0, nq, ix->d, ix->q_raw.p, ix->stream));
-    launch_layout_rows(ix->q_raw.p, dtype, colmajor, colmajor ? nq : ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream);
     CoreArgs a{};
+    int extra_launches = 0;
+    if (dtype == XS_F32 && !colmajor) a.raw = ix->q_raw.as<float>();          // dense fp32 rows: prepared in one fused kernel
+    else { launch_layout_rows(ix->q_raw.p, dtype, colmajor, colmajor ? nq : ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream); extra_launches = 1; }
     a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
     a.self_base = -1; a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
     a.path = choose_path(ix, nq, k);
     XS_TRY(search_core(ix, a));
-    ix->stats.gpu_launches += 1;
-    if (a.path != PATH_EXACT) XS_TRY(rerun_uncertified(ix, a.q32, nq, k, -1, a.out_idx, a.out_score, a.status));
-    CU_TRY(cudaMemcpyAsync(out_idx, a.out_idx, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
-    if (out_score) CU_TRY(cudaMemcpyAsync(out_score, a.out_score, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-    CU_TRY(cudaStreamSynchronize(ix->stream));
-    return XS_OK;
+    ix->stats.gpu_launches += extra_launches;
+    return finish_to_host(ix, a.q32, nq, k, -1, a.out_idx, a.out_score, a.status, a.path != PATH_EXACT, out_idx, out_score);
 }
 
 extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, int64_t* out_idx, float* out_score) {
@@ -565,10 +625,8 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
         a.tmap_a = (a.path == PATH_GEMM) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
         a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
         XS_TRY(search_core(ix, a));
-        if (a.path != PATH_EXACT) XS_TRY(rerun_uncertified(ix, a.q32, c, k, r0, a.out_idx, a.out_score, a.status));
-        CU_TRY(cudaMemcpyAsync(out_idx + (r0 - q_begin) * k, a.out_idx, (size_t)c * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
-        if (out_score) CU_TRY(cudaMemcpyAsync(out_score + (r0 - q_begin) * k, a.out_score, (size_t)c * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(cudaStreamSynchronize(ix->stream));
+        XS_TRY(finish_to_host(ix, a.q32, c, k, r0, a.out_idx, a.out_score, a.status, a.path != PATH_EXACT,
+                              out_idx + (r0 - q_begin) * k, out_score ? out_score + (r0 - q_begin) * k : nullptr));
         total.n_queries += ix->stats.n_queries; total.n_exact_rerun += ix->stats.n_exact_rerun;
         total.n_candidates += ix->stats.n_candidates; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;
     }

@@ -145,6 +145,74 @@ __global__ void prep_queries_kernel(float* q32, __nv_bfloat16* q16, int64_t nq, 
     }
 }
 
+// Fast path for d == d_pad <= 2048: the raw row goes straight into registers (16 float4 per lane,
+// all loads issued up front), moments, scaling, fp32 + bf16 stores and eps in one kernel; the rows
+// [nq, nq_pad) of the bf16 copy (GEMM tile padding) are zero-filled by the same launch.
+__global__ void prep_queries_fused_kernel(const float* __restrict__ raw, float* __restrict__ q32, __nv_bfloat16* __restrict__ q16,
+                                          int64_t nq, int64_t nq_pad, int d_pad, int renorm, const DevStats* stats,
+                                          float eps_sigmas, float* __restrict__ eps) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = lane_id();
+    if (r >= nq_pad) return;
+    if (r >= nq) {
+        if (q16) for (int c = lane * 8; c < d_pad; c += 256) *reinterpret_cast<uint4*>(q16 + r * d_pad + c) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    float4 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int c = j * 128 + lane * 4;
+        v[j] = (c < d_pad) ? *reinterpret_cast<const float4*>(raw + r * d_pad + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double a2 = 0.0, a4 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        double x0 = v[j].x, x1 = v[j].y, x2 = v[j].z, x3 = v[j].w;
+        double q0 = x0 * x0, q1 = x1 * x1, q2 = x2 * x2, q3 = x3 * x3;
+        a2 += (q0 + q1) + (q2 + q3);
+        a4 += (q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3);
+    }
+    double s2 = warp_sum(a2), s4 = warp_sum(a4);
+    float scale = 1.f;
+    if (renorm) {
+        scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
+        double sc = scale;
+        s4 *= sc * sc * sc * sc;
+        s2 *= sc * sc;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int c = j * 128 + lane * 4;
+        if (c < d_pad) {
+            float4 w = v[j];
+            if (renorm) { w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale; }
+            *reinterpret_cast<float4*>(q32 + r * d_pad + c) = w;
+            if (q16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(q16 + r * d_pad + c) = pk;
+            }
+        }
+    }
+    if (lane == 0) {
+        const float v4 = __uint_as_float(stats->v4max_bits), vn = __uint_as_float(stats->vnmax_bits);
+        const float q4 = (float)sqrt(sqrt(s4)), qn = (float)sqrt(s2);
+        eps[r] = eps_sigmas * (1.0f / 512.0f) * 0.8165f * q4 * v4 + 2e-5f * qn * vn;
+    }
+}
+
+bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16, int64_t nq, int64_t nq_pad, int d, int d_pad,
+                               bool renorm, const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st) {
+    if (d != d_pad || d_pad > 2048 || (reinterpret_cast<uintptr_t>(raw) & 15)) return false;
+    const int wpb = 4;
+    const int64_t rows = q16 ? nq_pad : nq;
+    prep_queries_fused_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(raw, q32, q16, nq, rows, d_pad, renorm ? 1 : 0,
+                                                                                       stats, eps_sigmas, eps);
+    return true;
+}
+
 void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
                          const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st) {
     if (nq <= 0) return;

@@ -15,6 +15,38 @@ constexpr int FIN_THREADS = 1024;
 constexpr int FIN_MAX_LISTS = 4096;          // partial lists per query that the shared-memory gather supports
 constexpr int FIN_SMEM_BUDGET = 200 * 1024;  // dynamic shared memory the finalise kernel may ask for
 
+// Exact inner products of TWO database rows with the query row held in shared memory: fp32
+// operands, fp64 accumulation, fixed order (lane-strided float4s, chunk by chunk), warp-reduced.
+// All loads of a chunk are issued before any arithmetic so that 16 x 512 B are in flight per warp.
+__device__ __forceinline__ void exact_dot2(const float* __restrict__ v0, const float* __restrict__ v1, bool has1,
+                                           const float* qs, int d_pad, double& r0, double& r1) {
+    const int lane = lane_id();
+    double a0 = 0.0, a1 = 0.0;
+    for (int base = 0; base < d_pad; base += 1024) {
+        float4 x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * 128 + lane * 4;
+            const bool in = i < d_pad;
+            x[j] = in ? ld_stream_f4(v0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            y[j] = (in && has1) ? ld_stream_f4(v1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + j * 128 + lane * 4;
+            if (i < d_pad) {
+                const float4 w = *reinterpret_cast<const float4*>(qs + i);
+                a0 = fma((double)x[j].x, (double)w.x, a0); a0 = fma((double)x[j].y, (double)w.y, a0);
+                a0 = fma((double)x[j].z, (double)w.z, a0); a0 = fma((double)x[j].w, (double)w.w, a0);
+                a1 = fma((double)y[j].x, (double)w.x, a1); a1 = fma((double)y[j].y, (double)w.y, a1);
+                a1 = fma((double)y[j].z, (double)w.z, a1); a1 = fma((double)y[j].w, (double)w.w, a1);
+            }
+        }
+    }
+    r0 = warp_sum(a0);
+    r1 = warp_sum(a1);
+}
+
 // Descending bitonic sort of m (power of two) 64-bit items in shared memory.
 __device__ void block_sort_desc(uint64_t* a, int m) {
     for (int size = 2; size <= m; size <<= 1) {
@@ -76,6 +108,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     uint64_t* cand = fin_smem;
     uint64_t* items = fin_smem + cand_max;
     int* offs = reinterpret_cast<int*>(items + item_cap);
+    float* qs = reinterpret_cast<float*>(offs + ((a.P <= FIN_MAX_LISTS) ? ((a.P + 4) & ~3) : 4));   // [d_pad] query row
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[2];
     __shared__ int scan_scratch[33];
@@ -85,6 +118,8 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     const bool staged = a.P <= FIN_MAX_LISTS;           // offsets fit -> try the shared-memory gather
 
     if (threadIdx.x == 0) { sh_ncand = 0; sh_flag = 0; sh_selfkey = 0; }
+    for (int i = threadIdx.x * 4; i < a.d_pad; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(qs + i) = *reinterpret_cast<const float4*>(a.q32 + q * a.d_pad + i);
     __syncthreads();
     uint32_t total = 0;
     {   // list sizes, and the largest "something above this key was dropped upstream" mark
@@ -155,22 +190,16 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     if (!a.exact) uncertified = (found > (uint32_t)cand_max) || (max_thr != 0 && max_thr >= cut_key);
     else          uncertified = (max_thr != 0);
 
-    if (!a.exact) {   // exact rescoring, one warp per candidate
-        const float* qrow = a.q32 + q * a.d_pad;
-        for (int c = warp; c < ncand; c += nwarps) {
-            const uint32_t row = item_row(cand[c]);
-            const float* vrow = a.db32 + (int64_t)row * a.d_pad;
-            double acc = 0.0;
-            for (int i = lane * 4; i < a.d_pad; i += 128) {
-                float4 v = ld_stream_f4(vrow + i);
-                float4 w = *reinterpret_cast<const float4*>(qrow + i);
-                acc = fma((double)v.x, (double)w.x, acc);
-                acc = fma((double)v.y, (double)w.y, acc);
-                acc = fma((double)v.z, (double)w.z, acc);
-                acc = fma((double)v.w, (double)w.w, acc);
+    if (!a.exact) {   // exact rescoring, one warp per PAIR of candidates
+        for (int c = warp * 2; c < ncand; c += nwarps * 2) {
+            const bool has1 = c + 1 < ncand;
+            const uint32_t row0 = item_row(cand[c]), row1 = has1 ? item_row(cand[c + 1]) : row0;
+            double s0, s1;
+            exact_dot2(a.db32 + (int64_t)row0 * a.d_pad, a.db32 + (int64_t)row1 * a.d_pad, has1, qs, a.d_pad, s0, s1);
+            if (lane == 0) {
+                cand[c] = make_item((float)s0, row0);
+                if (has1) cand[c + 1] = make_item((float)s1, row1);
             }
-            acc = warp_sum(acc);
-            if (lane == 0) cand[c] = make_item((float)acc, row);
         }
     }
     __syncthreads();
@@ -181,18 +210,9 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
                 cand[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
         if (warp == 0) {      // its exact score <v, v>, recomputed here (the pooled one may be a +inf boost)
             const float* vrow = a.db32 + (int64_t)self_row * a.d_pad;
-            const float* qrow = a.q32 + q * a.d_pad;
-            double acc = 0.0;
-            for (int i = lane * 4; i < a.d_pad; i += 128) {
-                float4 v = *reinterpret_cast<const float4*>(vrow + i);
-                float4 w = *reinterpret_cast<const float4*>(qrow + i);
-                acc = fma((double)v.x, (double)w.x, acc);
-                acc = fma((double)v.y, (double)w.y, acc);
-                acc = fma((double)v.z, (double)w.z, acc);
-                acc = fma((double)v.w, (double)w.w, acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) sh_selfkey = score_key((float)acc);
+            double s0, s1;
+            exact_dot2(vrow, vrow, false, qs, a.d_pad, s0, s1);
+            if (lane == 0) sh_selfkey = score_key((float)s0);
         }
     }
     int m = 1;
@@ -230,8 +250,8 @@ int finalise_cand_max(int k) {
 void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
     const int cand_max = finalise_cand_max(a.k);
-    const size_t offs_bytes = (a.P <= FIN_MAX_LISTS) ? ((size_t)(a.P + 2) * sizeof(int) + 8) : 8;
-    const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes;
+    const size_t offs_bytes = ((a.P <= FIN_MAX_LISTS) ? (size_t)((a.P + 4) & ~3) : 4) * sizeof(int);
+    const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float);
     // room for the gathered pool items: what the pools can hold, capped by the shared-memory budget
     size_t want_items = (size_t)a.P * (size_t)a.cap;
     size_t max_items = (FIN_SMEM_BUDGET > fixed) ? (FIN_SMEM_BUDGET - fixed) / sizeof(uint64_t) : 0;

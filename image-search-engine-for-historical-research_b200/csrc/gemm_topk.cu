@@ -345,9 +345,8 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms) {
     GemmPlan p = main_plan;
     const int all_tiles = main_plan.n_tiles;
-    int s = num_sms / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
+    int s = (num_sms / 2) / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
     if (s < 16) s = 16;
-    if (s > num_sms) s = num_sms;
     if (s > all_tiles) s = all_tiles;
     p.n_tiles = s;
     p.tile_stride = all_tiles / s;

@@ -36,6 +36,11 @@ void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int 
 void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
                          const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
 
+// One-kernel variant reading the caller's raw fp32 row-major queries (d == d_pad <= 2048, 16-byte aligned);
+// also zero-fills bf16 rows [nq, nq_pad).  Returns false (nothing launched) when the fast path does not apply.
+bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16, int64_t nq, int64_t nq_pad, int d, int d_pad,
+                               bool renorm, const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
+
 // ---- scan.cu ------------------------------------------------------------------------------------
 // Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  nq <= 4.
 void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,

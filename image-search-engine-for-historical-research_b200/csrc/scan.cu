@@ -246,7 +246,13 @@ scores_sample_threshold_kernel(const float* __restrict__ scores, int64_t pitch, 
     const int64_t stride = n / SCORE_SAMPLE > 0 ? n / SCORE_SAMPLE : 1;
     const int cnt = (int)min((int64_t)SCORE_SAMPLE, n / stride);
     const float* s = scores + q * pitch;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) skeys[i] = score_key(s[(int64_t)i * stride]);
+    for (int i0 = threadIdx.x; i0 < cnt; i0 += blockDim.x * 8) {      // 8 independent strided loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = i0 + j * blockDim.x; v[j] = (i < cnt) ? s[(int64_t)i * stride] : 0.f; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = i0 + j * blockDim.x; if (i < cnt) skeys[i] = score_key(v[j]); }
+    }
     __syncthreads();
     if (cnt < 4 * k) { if (threadIdx.x == 0) thr0[q] = -INFINITY; return; }
     const int cnt_up = (cnt + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;

@@ -56,3 +56,15 @@ run("gemm default nq=16", 16, force_path=2)
 run("scan nq=1", 1, force_path=1)
 run("scan nq=2", 2, force_path=1)
 run("exact nq=4", 4, reps=3, force_path=3)
+
+# host-buffer API (e2e): pinned queries in, ids + scores back to the host
+import time
+qh = queries.cpu().pin_memory().numpy()
+for nq in (70, 1):
+    for _ in range(3):
+        ix.search(qh[:nq], K)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ix.search(qh[:nq], K)
+    dt = (time.perf_counter() - t0) / 20
+    print(f"host API nq={nq}: {dt*1e3:.3f} ms/call  ({nq/dt:.0f} QPS)  stats {ix.stats()}", flush=True)
