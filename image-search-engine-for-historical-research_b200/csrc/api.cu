@@ -70,7 +70,7 @@ struct xs_index {
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; float debug_thr = 0.f;
     // workspace
-    Buf q_raw, q32, q16, eps, thr0, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf q_raw, q32, q16, eps, thr0, ghist, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -153,7 +153,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
@@ -306,22 +306,18 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
     const int cap = k;
     const int64_t chunk_max = 16;
     XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
+    XS_TRY(ix->ghist.ensure((size_t)chunk_max * HIST_BINS * sizeof(uint32_t)));
     const int64_t slots = round_up(chunk_max, 128) * P;
     XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
     XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
     XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
     for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
         const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
-        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->num_sms, ix->stream);
+        CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->stream));
+        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->stream);
         *launches += (c + 3) / 4;
         if (self_base >= 0) { boost_self_kernel<<<(c + 127) / 128, 128, 0, ix->stream>>>(ix->scores.as<float>(), ix->n, c, self_base + q0); ++*launches; }
-        const float* thr0 = nullptr;
-        if (ix->n >= 8 * SLICE_ROWS) {
-            XS_TRY(ix->thr0.ensure((size_t)chunk_max * sizeof(float)));
-            launch_scores_sample_threshold(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, true, ix->thr0.as<float>(), ix->stream);
-            thr0 = ix->thr0.as<float>(); ++*launches;
-        }
-        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, thr0, true, ix->pool_items.as<uint64_t>(),
+        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, ix->ghist.as<uint32_t>(), true, ix->pool_items.as<uint64_t>(),
                                ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
         FinaliseArgs fa{};
         fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
@@ -375,23 +371,19 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         const int cap = 2 * k + 256;
         const int64_t chunk_max = 8;
         XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
+        XS_TRY(ix->ghist.ensure((size_t)chunk_max * HIST_BINS * sizeof(uint32_t)));
         const int64_t slots = round_up(chunk_max, 128) * P;
         XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
         XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
         XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
         for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
             const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
+            CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->stream));
             if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
-            launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->num_sms, ix->stream);
+            launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->stream);
             launches += (c + 1) / 2;
             if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
-            const float* thr0 = nullptr;
-            if (ix->n >= 8 * SLICE_ROWS) {
-                XS_TRY(ix->thr0.ensure((size_t)chunk_max * sizeof(float)));
-                launch_scores_sample_threshold(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, false, ix->thr0.as<float>(), ix->stream);
-                thr0 = ix->thr0.as<float>(); ++launches;
-            }
-            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, thr0, false, ix->pool_items.as<uint64_t>(),
+            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), false, ix->pool_items.as<uint64_t>(),
                                    ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();

@@ -11,28 +11,28 @@
 
 namespace xs {
 
-constexpr int FIN_THREADS = 1024;
+constexpr int FIN_THREADS = 512;
 constexpr int FIN_MAX_LISTS = 4096;          // partial lists per query that the shared-memory gather supports
 constexpr int FIN_SMEM_BUDGET = 200 * 1024;  // dynamic shared memory the finalise kernel may ask for
 
 // Exact inner products of TWO database rows with the query row held in shared memory: fp32
 // operands, fp64 accumulation, fixed order (lane-strided float4s, chunk by chunk), warp-reduced.
-// All loads of a chunk are issued before any arithmetic so that 16 x 512 B are in flight per warp.
+// All loads of a chunk are issued before any arithmetic so that 8 x 512 B are in flight per warp.
 __device__ __forceinline__ void exact_dot2(const float* __restrict__ v0, const float* __restrict__ v1, bool has1,
                                            const float* qs, int d_pad, double& r0, double& r1) {
     const int lane = lane_id();
     double a0 = 0.0, a1 = 0.0;
-    for (int base = 0; base < d_pad; base += 1024) {
-        float4 x[8], y[8];
+    for (int base = 0; base < d_pad; base += 512) {
+        float4 x[4], y[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
             const int i = base + j * 128 + lane * 4;
             const bool in = i < d_pad;
             x[j] = in ? ld_stream_f4(v0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             y[j] = (in && has1) ? ld_stream_f4(v1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
             const int i = base + j * 128 + lane * 4;
             if (i < d_pad) {
                 const float4 w = *reinterpret_cast<const float4*>(qs + i);
@@ -102,7 +102,7 @@ __device__ void gather_pool(const uint64_t* __restrict__ pool_items, int64_t q, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(FIN_THREADS, 1)
 finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     extern __shared__ uint64_t fin_smem[];              // [cand_max] candidates | [item_cap] gathered items | [P+1] offsets
     uint64_t* cand = fin_smem;
@@ -257,6 +257,7 @@ void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st) {
     size_t max_items = (FIN_SMEM_BUDGET > fixed) ? (FIN_SMEM_BUDGET - fixed) / sizeof(uint64_t) : 0;
     if (max_items > 12288) max_items = 12288;      // 96 KB: two CTAs per SM; larger pools take the global-memory path
     int item_cap = (int)(want_items < max_items ? want_items : max_items);
+    item_cap = (item_cap + 1) & ~1;                  // keeps the fp32 query row behind it 16-byte aligned
     if (a.P > FIN_MAX_LISTS) item_cap = 0;
     const size_t smem = fixed + (size_t)item_cap * sizeof(uint64_t);
     cudaFuncSetAttribute(finalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));

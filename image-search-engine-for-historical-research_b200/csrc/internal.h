@@ -14,7 +14,9 @@ constexpr int GEMM_BK = 64;       // K elements per pipeline stage (= one 128-by
 constexpr int ROW_ALIGN = 256;    // database rows are padded to a multiple of this
 constexpr int COL_ALIGN = 64;     // descriptor length is padded to a multiple of this
 
-constexpr int SLICE_ROWS = 4096;  // rows per partial list in the score-matrix -> pools kernel
+constexpr int SLICE_ROWS = 4096;
+constexpr int HIST_BINS = 4096;   // database-wide histogram of score keys (top 12 bits), filled by the scoring kernels
+constexpr int HIST_SHIFT = 20;  // rows per partial list in the score-matrix -> pools kernel
 
 // status bits written by the finalise kernel (one int32 per query)
 constexpr int ST_UNCERTIFIED = 1;
@@ -42,22 +44,19 @@ bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16,
                                bool renorm, const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
 
 // ---- scan.cu ------------------------------------------------------------------------------------
-// Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  nq <= 4.
+// Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  Both scoring kernels also
+// add every score to ghist[q][score_key >> HIST_SHIFT] (zeroed by the caller).
 void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
-                        float* scores, int64_t score_pitch, int num_sms, cudaStream_t st);
+                        float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st);
 // Exact scoring: scores[q][row] = fp32( sum_fp64 db32[row][i] * q32[q][i] ).  Any nq (looped in 4s).
 void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n, int d_pad,
-                         float* scores, int64_t score_pitch, int num_sms, cudaStream_t st);
+                         float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st);
 // Score matrix -> candidate pools (one partial list per SLICE_ROWS rows).
 //   exact = false: keep items within the eps band below the slice's k-th best
 //   exact = true : keep exactly the slice's k best (full 64-bit item order)
 void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                            const float* eps, const float* thr0, bool exact, uint64_t* pool_items, int* pool_count,
+                            const float* eps, const uint32_t* ghist, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st);
-// thr0[q] = lower bound of query q's k-th best score, from 16384 scores sampled at a fixed stride
-// (minus the 2*eps band unless exact); -inf when the sample is too small for k.
-void launch_scores_sample_threshold(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                                    const float* eps, bool exact, float* thr0, cudaStream_t st);
 
 // ---- gemm_topk.cu -------------------------------------------------------------------------------
 struct GemmPlan {

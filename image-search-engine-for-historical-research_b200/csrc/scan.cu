@@ -18,9 +18,11 @@ namespace xs {
 template <int QB, int R>
 __global__ void __launch_bounds__(256, 2)
 scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32, int64_t n, int d_pad,
-                   float* __restrict__ scores, int64_t pitch) {
-    extern __shared__ float qs[];                       // [QB][d_pad]
+                   float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist) {
+    extern __shared__ float qs[];                       // [QB][d_pad] query rows | [QB][HIST_BINS] score-key histogram
+    uint32_t* sh = reinterpret_cast<uint32_t*>(qs + QB * d_pad);
     for (int i = threadIdx.x; i < QB * d_pad; i += blockDim.x) qs[i] = q32[i];
+    for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const int chunks = d_pad >> 3;                      // 16-byte chunks per row
     const int lane = lane_id();
@@ -75,24 +77,34 @@ scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32
 #pragma unroll
             for (int b = 0; b < QB; ++b) {
                 float s = warp_sum(acc[r][b]);
-                if (lane == 0 && row0 + r < n) scores[(int64_t)b * pitch + row0 + r] = s;
+                if (lane == 0 && row0 + r < n) {
+                    scores[(int64_t)b * pitch + row0 + r] = s;
+                    atomicAdd(&sh[b * HIST_BINS + (score_key(s) >> HIST_SHIFT)], 1u);
+                }
             }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
 void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
-                        float* scores, int64_t score_pitch, int num_sms, cudaStream_t st) {
+                        float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st) {
     const int grid = num_sms * 2;
     const uint4* db = reinterpret_cast<const uint4*>(db16);
+    const size_t per_q = (size_t)d_pad * sizeof(float) + HIST_BINS * sizeof(uint32_t);
+    cudaFuncSetAttribute(scan_scores_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per_q));
+    cudaFuncSetAttribute(scan_scores_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_q);
     for (int q0 = 0; q0 < nq;) {
         const int left = nq - q0;
         const float* q = q32 + (int64_t)q0 * d_pad;
         float* s = scores + (int64_t)q0 * score_pitch;
+        uint32_t* h = ghist + (size_t)q0 * HIST_BINS;
         if (left >= 2) {
-            scan_scores_kernel<2, 4><<<grid, 256, 2 * d_pad * sizeof(float), st>>>(db, q, n, d_pad, s, score_pitch);
+            scan_scores_kernel<2, 4><<<grid, 256, 2 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
             q0 += 2;
         } else {
-            scan_scores_kernel<1, 4><<<grid, 256, 1 * d_pad * sizeof(float), st>>>(db, q, n, d_pad, s, score_pitch);
+            scan_scores_kernel<1, 4><<<grid, 256, per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
             q0 += 1;
         }
     }
@@ -102,9 +114,11 @@ void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int
 template <int QB, int R>
 __global__ void __launch_bounds__(256, 2)
 exact_scores_kernel(const float4* __restrict__ db32, const float* __restrict__ q32, int64_t n, int d_pad,
-                    float* __restrict__ scores, int64_t pitch) {
+                    float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist) {
     extern __shared__ float qs[];
+    uint32_t* sh = reinterpret_cast<uint32_t*>(qs + QB * d_pad);
     for (int i = threadIdx.x; i < QB * d_pad; i += blockDim.x) qs[i] = q32[i];
+    for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const int chunks = d_pad >> 2;                      // float4 per row
     const int lane = lane_id();
@@ -142,27 +156,38 @@ exact_scores_kernel(const float4* __restrict__ db32, const float* __restrict__ q
 #pragma unroll
             for (int b = 0; b < QB; ++b) {
                 double s = warp_sum(acc[r][b]);
-                if (lane == 0 && row0 + r < n) scores[(int64_t)b * pitch + row0 + r] = (float)s;
+                if (lane == 0 && row0 + r < n) {
+                    scores[(int64_t)b * pitch + row0 + r] = (float)s;
+                    atomicAdd(&sh[b * HIST_BINS + (score_key((float)s) >> HIST_SHIFT)], 1u);
+                }
             }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
 void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n, int d_pad,
-                         float* scores, int64_t score_pitch, int num_sms, cudaStream_t st) {
+                         float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st) {
     const int grid = num_sms * 2;
     const float4* db = reinterpret_cast<const float4*>(db32);
+    const size_t per_q = (size_t)d_pad * sizeof(float) + HIST_BINS * sizeof(uint32_t);
+    cudaFuncSetAttribute(exact_scores_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per_q));
+    cudaFuncSetAttribute(exact_scores_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per_q));
+    cudaFuncSetAttribute(exact_scores_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_q);
     for (int q0 = 0; q0 < nq;) {
         const int left = nq - q0;
         const float* q = q32 + (int64_t)q0 * d_pad;
         float* s = scores + (int64_t)q0 * score_pitch;
+        uint32_t* h = ghist + (size_t)q0 * HIST_BINS;
         if (left >= 4) {
-            exact_scores_kernel<4, 2><<<grid, 256, 4 * d_pad * sizeof(float), st>>>(db, q, n, d_pad, s, score_pitch);
+            exact_scores_kernel<4, 2><<<grid, 256, 4 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
             q0 += 4;
         } else if (left >= 2) {
-            exact_scores_kernel<2, 2><<<grid, 256, 2 * d_pad * sizeof(float), st>>>(db, q, n, d_pad, s, score_pitch);
+            exact_scores_kernel<2, 2><<<grid, 256, 2 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
             q0 += 2;
         } else {
-            exact_scores_kernel<1, 2><<<grid, 256, 1 * d_pad * sizeof(float), st>>>(db, q, n, d_pad, s, score_pitch);
+            exact_scores_kernel<1, 2><<<grid, 256, per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
             q0 += 1;
         }
     }
@@ -170,22 +195,51 @@ void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n,
 
 // ---- scores_to_pools -----------------------------------------------------------------------------
 // grid = (P, nq); CTA (p, q) reduces rows [p*SLICE_ROWS, ...) of query q to one partial list.
+// The database-wide histogram of score keys (filled by the scoring kernel) gives every CTA the bin
+// that holds the k-th best score; its lower edge is a lower bound of that score, so
+//   coarse scores: emit what lies within 2*eps below the edge (a pure filter, no per-slice select)
+//   exact scores : emit the slice's own k best that are not below the edge (bounded by k per slice)
 __global__ void __launch_bounds__(256)
 scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t n, int k,
-                       const float* __restrict__ eps, const float* __restrict__ thr0, int exact,
+                       const float* __restrict__ eps, const uint32_t* __restrict__ ghist, int exact,
                        uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr,
                        int P, int cap) {
     __shared__ uint32_t keys[SLICE_ROWS];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[2];
-    __shared__ uint32_t n_out;
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t n_out, edge_key;
     const int p = blockIdx.x;
     const int64_t q = blockIdx.y;
     const int64_t row0 = (int64_t)p * SLICE_ROWS;
     const int cnt = (int)min((int64_t)SLICE_ROWS, n - row0);
     const float* s = scores + q * pitch + row0;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) keys[i] = score_key(s[i]);
-    if (threadIdx.x == 0) n_out = 0;
+    if (threadIdx.x == 0) { n_out = 0; edge_key = 0; }
+    {   // bin of the database's k-th best score: thread t owns HIST_BINS/256 consecutive bins, suffix sums from the top
+        constexpr int PER = HIST_BINS / 256;
+        const uint32_t* gh = ghist + q * HIST_BINS + threadIdx.x * PER;
+        uint32_t h[PER], mine = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { h[j] = gh[j]; mine += h[j]; }
+        const int lane = lane_id(), warp = threadIdx.x >> 5;
+        uint32_t suf = mine;                              // suffix over lanes >= lane within the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
+        if (lane == 0) wsum[warp] = suf;
+        __syncthreads();
+        uint32_t above = 0;                               // everything in higher warps
+        for (int w = warp + 1; w < 8; ++w) above += wsum[w];
+        const uint32_t incl = above + suf, excl = incl - mine;   // counts of bins >= my first bin / > my last bin
+        if (incl >= (uint32_t)k && excl < (uint32_t)k) {          // exactly one thread (if the database holds >= k rows)
+            uint32_t run = excl;
+#pragma unroll
+            for (int j = PER - 1; j >= 0; --j) {
+                run += h[j];
+                if (run >= (uint32_t)k) { edge_key = (uint32_t)(threadIdx.x * PER + j) << HIST_SHIFT; break; }
+            }
+        }
+    }
     __syncthreads();
     const int cnt_up = (cnt + 255) & ~255;
     auto each = [&](auto fn) {
@@ -196,15 +250,16 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
             fn(it, valid);
         }
     };
-    uint64_t cut = 0;                                   // keep items >= cut
-    if (cnt > k) {
-        uint64_t T = block_kth_largest(each, (uint32_t)k, exact ? 8 : 4, hist, misc);
-        if (exact) cut = T;
-        else cut = (uint64_t)score_key(key_score((uint32_t)(T >> 32)) - 2.f * eps[q]) << 32;
-    }
-    if (thr0) {                                         // database-wide lower bound from the sampled scores
-        const uint64_t c0 = (uint64_t)score_key(thr0[q]) << 32;
-        cut = cut > c0 ? cut : c0;
+    uint64_t cut;                                        // keep items >= cut
+    if (!exact) {
+        const uint32_t ck = edge_key ? score_key(key_score(edge_key) - 2.f * eps[q]) : 0u;
+        cut = (uint64_t)ck << 32;
+    } else {
+        cut = (uint64_t)edge_key << 32;
+        if (cnt > k) {
+            const uint64_t T = block_kth_largest(each, (uint32_t)k, 8, hist, misc);
+            cut = cut > T ? cut : T;
+        }
     }
     const int64_t slot = pool_slot(q, p, P);
     uint64_t* out = pool_items + slot * cap;
@@ -225,54 +280,11 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
 }
 
 void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                            const float* eps, const float* thr0, bool exact, uint64_t* pool_items, int* pool_count,
+                            const float* eps, const uint32_t* ghist, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st) {
     dim3 grid((unsigned)P, (unsigned)nq);
-    scores_to_pools_kernel<<<grid, 256, 0, st>>>(scores, score_pitch, n, k, eps, thr0, exact ? 1 : 0,
+    scores_to_pools_kernel<<<grid, 256, 0, st>>>(scores, score_pitch, n, k, eps, ghist, exact ? 1 : 0,
                                                  pool_items, pool_count, pool_thr, P, cap);
-}
-
-// ---- scores_sample_threshold -----------------------------------------------------------------------
-// One CTA per query: the k-th best of SCORE_SAMPLE scores taken at a fixed stride over the row range
-// is a lower bound of the k-th best of all rows; slices then emit only what can still matter.
-constexpr int SCORE_SAMPLE = 16384;
-__global__ void __launch_bounds__(1024)
-scores_sample_threshold_kernel(const float* __restrict__ scores, int64_t pitch, int64_t n, int k,
-                               const float* __restrict__ eps, int exact, float* __restrict__ thr0) {
-    extern __shared__ uint32_t skeys[];                 // [SCORE_SAMPLE]
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t misc[2];
-    const int64_t q = blockIdx.x;
-    const int64_t stride = n / SCORE_SAMPLE > 0 ? n / SCORE_SAMPLE : 1;
-    const int cnt = (int)min((int64_t)SCORE_SAMPLE, n / stride);
-    const float* s = scores + q * pitch;
-    for (int i0 = threadIdx.x; i0 < cnt; i0 += blockDim.x * 8) {      // 8 independent strided loads in flight per thread
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const int i = i0 + j * blockDim.x; v[j] = (i < cnt) ? s[(int64_t)i * stride] : 0.f; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const int i = i0 + j * blockDim.x; if (i < cnt) skeys[i] = score_key(v[j]); }
-    }
-    __syncthreads();
-    if (cnt < 4 * k) { if (threadIdx.x == 0) thr0[q] = -INFINITY; return; }
-    const int cnt_up = (cnt + (int)blockDim.x - 1) / (int)blockDim.x * (int)blockDim.x;
-    auto each = [&](auto fn) {
-        for (int i = threadIdx.x; i < cnt_up; i += blockDim.x) {
-            bool valid = i < cnt;
-            fn(valid ? ((uint64_t)skeys[i] << 32) : 0ull, valid);
-        }
-    };
-    const uint64_t T = block_kth_largest(each, (uint32_t)k, 4, hist, misc);
-    if (threadIdx.x == 0) {
-        const float kth = key_score((uint32_t)(T >> 32));
-        thr0[q] = exact ? kth : nextafterf(kth - 2.f * eps[q], -INFINITY);
-    }
-}
-
-void launch_scores_sample_threshold(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                                    const float* eps, bool exact, float* thr0, cudaStream_t st) {
-    cudaFuncSetAttribute(scores_sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCORE_SAMPLE * 4);
-    scores_sample_threshold_kernel<<<(unsigned)nq, 1024, SCORE_SAMPLE * 4, st>>>(scores, score_pitch, n, k, eps, exact ? 1 : 0, thr0);
 }
 
 }  // namespace xs
