@@ -68,11 +68,13 @@ class ShardedSearcher:
         ids, sims = self.local_search(queries, k)
         if self.world == 1:
             return ids, sims
-        ids_all = torch.empty((self.world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-        sims_all = torch.empty((self.world,) + tuple(sims.shape), dtype=sims.dtype, device=sims.device)
+        nq, kk = ids.shape
+        # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [G, nq, k]
+        ids_all = torch.empty((self.world * nq, kk), dtype=ids.dtype, device=ids.device)
+        sims_all = torch.empty((self.world * nq, kk), dtype=sims.dtype, device=sims.device)
         self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
         self.dist.all_gather_into_tensor(sims_all, sims.contiguous(), group=self.group)
-        return self.merge(ids_all, sims_all, k)
+        return self.merge(ids_all.view(self.world, nq, kk), sims_all.view(self.world, nq, kk), k)
 
 
 class CudaShard:

@@ -1,0 +1,87 @@
+"""world_size-2 gloo test of the row-sharded search logic on CPU.
+
+The CUDA local searcher cannot run here, so the test injects the oracle as each rank's local
+searcher and the host restatement of the merge; what is under test is the product's sharding
+code: shard bounds, global id offsets, the all-gather layout [G, nq, k] and the merge semantics
+(descending score, ties by ascending id) -- SURVEY.md section 8(e).
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = "image-search-engine-for-historical-research_b200"
+
+
+def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded = importlib.import_module(PKG + ".sharded")
+    synth = importlib.import_module(PKG + ".synth")
+    oracle = importlib.import_module("oracle.oracle")
+    vecs, qvecs = (synth.ties(n, nq, d=d, n_distinct=8) if ties else synth.gaussian(n, nq, d=d))
+    bounds = sharded.shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    shard = np.ascontiguousarray(vecs[:, lo:hi])
+
+    def local_search(queries, kk):
+        ids, sims = oracle.topk_ip(shard, queries.numpy().T, min(kk, hi - lo))
+        pad = kk - ids.shape[1]
+        if pad:
+            ids = np.concatenate([ids, -np.ones((ids.shape[0], pad), np.int64) - lo], axis=1)
+            sims = np.concatenate([sims, np.full((sims.shape[0], pad), -np.inf, np.float32)], axis=1)
+        return torch.from_numpy(ids + lo), torch.from_numpy(sims)
+
+    def merge(ids_all, sims_all, kk):
+        i, s = sharded.merge_parts_host(ids_all.numpy(), sims_all.numpy(), kk)
+        return torch.from_numpy(i), torch.from_numpy(s)
+
+    searcher = sharded.ShardedSearcher(local_search, merge)
+    ids, sims = searcher.search(torch.from_numpy(np.ascontiguousarray(qvecs.T)), k)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=ids.numpy(), sims=sims.numpy())
+    dist.destroy_process_group()
+
+
+def _run(tmp_path, n, nq, d, k, ties=False, world=2):
+    port = 29000 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, n, nq, d, k, ties, str(tmp_path)), nprocs=world, join=True)
+    return [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+
+
+def test_shard_bounds():
+    sharded = importlib.import_module(PKG + ".sharded")
+    assert sharded.shard_bounds(10, 3) == [0, 4, 7, 10]
+    assert sharded.shard_bounds(1_007_000, 8)[-1] == 1_007_000
+    b = sharded.shard_bounds(1_007_000, 8)
+    assert max(b[i + 1] - b[i] for i in range(8)) - min(b[i + 1] - b[i] for i in range(8)) <= 1
+
+
+def test_two_rank_search_matches_unsharded(tmp_path, synth, oracle):
+    outs = _run(tmp_path, n=601, nq=5, d=48, k=9)
+    vecs, qvecs = synth.gaussian(601, 5, d=48)
+    ref_ids, ref_sims = oracle.topk_ip(vecs, qvecs, 9)
+    for o in outs:                       # every rank ends up with the full answer
+        np.testing.assert_array_equal(o["ids"], ref_ids)
+        np.testing.assert_array_equal(o["sims"], ref_sims)
+
+
+def test_two_rank_ties_prefer_lower_global_id(tmp_path, synth, oracle):
+    outs = _run(tmp_path, n=64, nq=3, d=16, k=20, ties=True)
+    vecs, qvecs = synth.ties(64, 3, d=16, n_distinct=8)
+    ref_ids, ref_sims = oracle.topk_ip(vecs, qvecs, 20)
+    np.testing.assert_array_equal(outs[0]["ids"], ref_ids)
+    np.testing.assert_array_equal(outs[1]["ids"], ref_ids)
+
+
+def test_k_larger_than_a_shard(tmp_path, synth, oracle):
+    outs = _run(tmp_path, n=21, nq=2, d=8, k=15)      # shards of 11 and 10 rows, k = 15
+    vecs, qvecs = synth.gaussian(21, 2, d=8)
+    ref_ids, _ = oracle.topk_ip(vecs, qvecs, 15)
+    np.testing.assert_array_equal(outs[0]["ids"], ref_ids)

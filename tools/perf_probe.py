@@ -57,6 +57,20 @@ run("scan nq=1", 1, force_path=1)
 run("scan nq=2", 2, force_path=1)
 run("exact nq=4", 4, reps=3, force_path=3)
 
+# compute-bound regime: large query batches through the tcgen05 path
+if len(sys.argv) > 3:
+    for nq_big in (1024, 4096, 8192):
+        qb = bench.synth_rows_device(torch, nq_big, 2048, dev, 2)
+        ib = torch.empty((nq_big, K), dtype=torch.int64, device=dev)
+        sb = torch.empty((nq_big, K), dtype=torch.float32, device=dev)
+        stb = torch.zeros((nq_big,), dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ix.search_device(qb.data_ptr(), nq_big, K, ib.data_ptr(), sb.data_ptr(), status_ptr=stb.data_ptr())
+        st = ix.stats()
+        tf = 2.0 * N * 2048 * nq_big / (st["ms_coarse"] * 1e-3) / 1e12
+        print(f"gemm nq={nq_big}: coarse {st['ms_coarse']:.3f} ms = {tf:.0f} TFLOP/s (bf16 dense), call {st['ms_total']:.3f} ms, "
+              f"uncert {int(stb.sum())}, launches {st['gpu_launches']}", flush=True)
+
 # host-buffer API (e2e): pinned queries in, ids + scores back to the host
 import time
 qh = queries.cpu().pin_memory().numpy()
