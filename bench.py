@@ -280,6 +280,12 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     shard_rows = hi - lo
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get("gemm_topk_kernel", {})
+        if t.get("rows") == shard_rows:
+            traffic = t["bytes"] / 1e9                 # GB per launch, from the committed ncu --set full capture
     algo_bytes = shard_rows * DIM * 2                    # one pass over the bf16 shard
     achieved = algo_bytes / (coarse_ms * 1e-3) / 1e9
     qps = N_QUERIES * args.steps / (ms * 1e-3)
@@ -297,7 +303,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": N_QUERIES * TOPK * 12 + N_QUERIES * 4 + 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "gemm_topk_kernel", "kernel_ms": coarse_ms, "algorithmic_bytes": algo_bytes,
+                     "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write, profiles/)", "kernel": "gemm_topk_kernel", "kernel_ms": coarse_ms, "algorithmic_bytes": algo_bytes,
                      "peak_source": peak_src},
         "clocks": clocks,
     }
@@ -311,7 +317,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

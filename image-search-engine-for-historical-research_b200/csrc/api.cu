@@ -70,7 +70,7 @@ struct xs_index {
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; float debug_thr = 0.f;
     // workspace
-    Buf q_raw, q32, q16, eps, thr0, ghist, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -153,7 +153,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
@@ -629,8 +629,58 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
 
 extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, int64_t stride_row, int64_t stride_col,
                            int renormalise_q, int64_t* out_ranks, float* out_scores_sorted) {
-    (void)ix; (void)q; (void)dtype; (void)nq; (void)stride_row; (void)stride_col; (void)renormalise_q; (void)out_ranks; (void)out_scores_sorted;
-    return fail(XS_ERR_UNSUPPORTED, "xs_rank_all: full-ranking sort kernel not built yet");
+    if (!ix) return fail(XS_ERR_ARG, "null index");
+    if (!q || !out_ranks) return fail(XS_ERR_ARG, "null pointer");
+    if (nq <= 0) return fail(XS_ERR_ARG, "no queries (nq=%lld)", (long long)nq);
+    bool colmajor = false;
+    XS_TRY(check_layout(dtype, nq, ix->d, stride_row, stride_col, &colmajor));
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    const size_t es = dtype == XS_F64 ? 8 : 4;
+    const int64_t n = ix->n;
+    const int64_t col_block = 128;                     // queries per device-resident output block
+    const int chunk = 8;                               // queries per scoring + sort pass
+    XS_TRY(ix->q_raw.ensure((size_t)nq * ix->d * es));
+    XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
+    XS_TRY(ix->eps.ensure((size_t)nq * sizeof(float)));
+    XS_TRY(ix->scores.ensure((size_t)chunk * n * sizeof(float)));
+    XS_TRY(ix->ghist.ensure((size_t)chunk * HIST_BINS * sizeof(uint32_t)));
+    XS_TRY(ix->sort_work.ensure(rank_all_work_bytes(chunk, n)));
+    const int64_t cb_max = nq < col_block ? nq : col_block;
+    XS_TRY(ix->rank_out.ensure((size_t)n * cb_max * sizeof(int64_t)));
+    if (out_scores_sorted) XS_TRY(ix->rank_scores.ensure((size_t)n * cb_max * sizeof(float)));
+    XS_TRY(stage_host_rows(q, dtype, colmajor, colmajor ? stride_col : stride_row, 0, nq, ix->d, ix->q_raw.p, ix->stream));
+    int launches = 0;
+    ix->stats = xs_stats{};
+    ix->stats.n_queries = nq; ix->stats.path = PATH_EXACT;
+    ix->ev_valid = false;
+    CoreArgs a{};
+    if (dtype == XS_F32 && !colmajor) a.raw = ix->q_raw.as<float>();
+    else { launch_layout_rows(ix->q_raw.p, dtype, colmajor, colmajor ? nq : ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream); ++launches; }
+    a.q32 = ix->q32.as<float>(); a.nq = nq; a.prep = true; a.prep_renorm = renormalise_q != 0;
+    XS_TRY(prepare_queries(ix, a, nullptr, &launches));
+    for (int64_t b0 = 0; b0 < nq; b0 += col_block) {
+        const int64_t cb = (nq - b0 < col_block) ? nq - b0 : col_block;
+        for (int64_t q0 = 0; q0 < cb; q0 += chunk) {
+            const int c = (int)((cb - q0 < chunk) ? cb - q0 : chunk);
+            CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->stream));
+            launch_exact_scores(ix->db32, ix->q32.as<float>() + (b0 + q0) * ix->d_pad, c, n, ix->d_pad, ix->scores.as<float>(), n,
+                                ix->ghist.as<uint32_t>(), ix->num_sms, ix->stream);
+            launch_rank_all(ix->scores.as<float>(), n, c, n, (int)q0, (int)cb, ix->id_offset, ix->sort_work.p,
+                            ix->rank_out.as<int64_t>(), out_scores_sorted ? ix->rank_scores.as<float>() : nullptr, ix->stream);
+            launches += (c + 3) / 4 + 13;
+        }
+        CU_TRY(cudaGetLastError());
+        // block of columns [b0, b0+cb) of the caller's [n][nq] arrays
+        CU_TRY(cudaMemcpy2DAsync(out_ranks + b0, (size_t)nq * sizeof(int64_t), ix->rank_out.p, (size_t)cb * sizeof(int64_t),
+                                 (size_t)cb * sizeof(int64_t), (size_t)n, cudaMemcpyDeviceToHost, ix->stream));
+        if (out_scores_sorted)
+            CU_TRY(cudaMemcpy2DAsync(out_scores_sorted + b0, (size_t)nq * sizeof(float), ix->rank_scores.p, (size_t)cb * sizeof(float),
+                                     (size_t)cb * sizeof(float), (size_t)n, cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(cudaStreamSynchronize(ix->stream));
+    }
+    ix->stats.gpu_launches = launches;
+    return XS_OK;
 }
 
 extern "C" int xs_merge_candidates(int device, const int64_t* in_idx, const float* in_score, int n_parts, int64_t nq, int k,

@@ -98,9 +98,11 @@ void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, 
 // Multi-GPU merge of [parts][nq][k] lists.
 void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts, int64_t nq, int k,
                         int64_t* out_idx, float* out_score, cudaStream_t st);
-// Full ranking helpers (K == N).
-void launch_rank_all(const float* scores, int64_t score_pitch, int nq, int64_t n, int64_t id_offset,
-                     uint64_t* work_a, uint64_t* work_b, int64_t* out_ranks, float* out_sorted,
-                     cudaStream_t st);
+// ---- sort.cu ------------------------------------------------------------------------------------
+// Full ranking (K == N): stable segmented radix sort of c exact score rows; writes columns q0..q0+c of
+// out_ranks [n][nq_total] int64 (+ id_offset) and, optionally, out_scores [n][nq_total] fp32.
+size_t rank_all_work_bytes(int c, int64_t n);
+void launch_rank_all(const float* scores, int64_t pitch, int c, int64_t n, int q0, int nq_total, int64_t id_offset,
+                     void* work, int64_t* out_ranks, float* out_scores, cudaStream_t st);
 
 }  // namespace xs

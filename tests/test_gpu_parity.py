@@ -186,3 +186,31 @@ def test_merge_kernel_matches_host_merge(pkg, synth, oracle):
     _check_lists(oracle, hi, rid, s64, "sharded merge")
     for ix in shards:
         ix.close()
+
+
+def test_rank_all_full_ranking(pkg, synth, oracle, golden):
+    """K == N: the full `ranks` array of main_retrieve.py:176, plus mAP identical to the reference's."""
+    v, q, gnd = synth.clustered(3000, 12, d=256, n_clusters=40, noise=1.6, spread=0.5)
+    ranks, sc = pkg.rank_ip(v, q, K=None, return_scores=True)
+    assert ranks.shape == (3000, 12) and ranks.dtype == np.int64 and sc.shape == (3000, 12)
+    for j in range(12):
+        assert sorted(ranks[:, j].tolist()) == list(range(3000))
+    assert (np.diff(sc, axis=0) <= 0).all()
+    s64 = oracle.scores_f64(v, q)
+    _, ref_ranks = oracle.rank_ip(v, q)
+    _check_lists(oracle, ranks.T, ref_ranks.T, s64, "rank_all")
+    m, aps, pr, prs = oracle.compute_map(ranks, gnd, [1, 5, 10])
+    assert abs(m - golden["D_map"]) < 1e-12
+    np.testing.assert_allclose(aps, golden["D_aps"], rtol=0, atol=1e-12)
+    e, mm, h = oracle.protocol_maps(ranks, gnd)
+    assert abs(e - golden["D_mapE"]) < 1e-12 and abs(mm - golden["D_mapM"]) < 1e-12 and abs(h - golden["D_mapH"]) < 1e-12
+    # matching_L2 with K == N (mAP mode of test_rOP1m.py:147-148) goes through the same sort
+    idx, _ = pkg.matching_L2(3000, v.T, q.T)
+    assert idx.shape == (12, 3000)
+    _check_lists(oracle, idx, ref_ranks.T, s64, "matching_L2 K=N")
+    # ties: equal scores come out in ascending id order
+    vt, qt = synth.ties(256, 4, d=64, n_distinct=16)
+    rt = pkg.rank_ip(vt, qt)
+    rid, _ = oracle.topk_ip(vt, qt, 256)
+    np.testing.assert_array_equal(rt.T, rid)
+    pkg.clear_index_cache()
