@@ -68,7 +68,7 @@ struct xs_index {
     __nv_bfloat16* db16 = nullptr; float* db32 = nullptr; DevStats* dstats = nullptr;
     CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
     // tunables
-    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; float debug_thr = 0.f;
+    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; float debug_thr = 0.f;
     // workspace
     Buf q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
@@ -252,6 +252,7 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "force_path")) ix->force_path = (int)value;
     else if (!strcmp(name, "gemm_splits")) ix->gemm_splits = (int)value;
     else if (!strcmp(name, "sample_pass")) ix->sample_pass = (int)value;
+    else if (!strcmp(name, "pair_mode")) ix->pair_mode = (int)value;
     else if (!strcmp(name, "debug_thr")) ix->debug_thr = (float)value;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
@@ -404,8 +405,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         (void)nq_pad;
         for (int64_t q0 = 0; q0 < nq; q0 += batch_max) {
             const int64_t c = (nq - q0 < batch_max) ? nq - q0 : batch_max;
-            GemmPlan plan = plan_gemm(c, ix->n_pad, k, ix->num_sms, ix->gemm_splits);
-            const int64_t slots = (int64_t)plan.m_tiles * plan.splits * GEMM_BM;
+            GemmPlan plan = plan_gemm(c, ix->n_pad, k, ix->num_sms, ix->gemm_splits, ix->pair_mode != 0);
+            const int64_t slots = (int64_t)((plan.m_tiles + 1) & ~1) * plan.splits * GEMM_BM;
             XS_TRY(ix->pool_items.ensure((size_t)slots * plan.cap * 8));
             XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
             XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
@@ -439,7 +440,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 thr0 = ix->thr0.as<float>();
             }
             if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
-            cudaError_t e = launch_gemm_topk(*ta, ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+            cudaError_t e = launch_gemm_topk(*ta, plan.pair ? ix->tmap_db_a : ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                              (int)row0, thr0, ix->stream);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));

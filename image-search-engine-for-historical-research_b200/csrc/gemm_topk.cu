@@ -22,10 +22,23 @@
 
 namespace xs {
 
-constexpr int STAGES = 4;
+// Two shapes of the same kernel:
+//   PAIR = false  one CTA per 128 x 256 tile (cta_group::1), 4 stages x 48 KB.  Small query batches: HBM-bound.
+//   PAIR = true   a cluster of two CTAs per 256 x 256 tile (cta_group::2): each CTA stages ITS 128 query rows and
+//                 ITS 128 of the 256 database rows (16 + 16 KB per stage, 6 stages), the leader issues M=256 MMAs
+//                 that read both CTAs' shared memory and write both CTAs' TMEM.  Halves the L2->SM operand
+//                 traffic per flop and deepens the ring: large query batches, tensor-pipe-bound.
+constexpr int MAX_STAGES = 6;
 constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB
-constexpr int B_BYTES = GEMM_BN * GEMM_BK * 2;          // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+template <bool PAIR> struct Shape {
+    static constexpr int STAGES = PAIR ? 6 : 4;
+    static constexpr int B_ROWS = PAIR ? GEMM_BN / 2 : GEMM_BN;
+    static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int UMMA_M = PAIR ? 256 : 128;
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128|256
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GEMM_BN >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+};
 constexpr int GEMM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 constexpr int TMEM_COLS = 512;
@@ -33,12 +46,15 @@ constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;   // database tiles
 constexpr uint64_t HINT_EVICT_LAST  = 0x14F0000000000000ull;   // query tiles: re-read by every CTA
 
 struct __align__(8) GemmBarriers {
-    uint64_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES], tfull[2], tempty[2];
     uint32_t tmem_base;
     uint32_t pad;
 };
-constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t);
+// both shapes stage 192 KB of operands
+constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t);
+static_assert(Shape<true>::STAGES * Shape<true>::STAGE_BYTES == Shape<false>::STAGES * Shape<false>::STAGE_BYTES, "ring sizes differ");
 size_t gemm_smem_bytes() { return GEMM_SMEM; }
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in the pair's leader CTA
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,6 +86,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  " [%0], [%1, {%3, %4}], [%2], %5;"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
 }
+// cta_group::2 load: lands in THIS CTA's shared memory, completes bytes on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t hint) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                 " [%0], [%1, {%3, %4}], [%2], %5;"
+                 :: "r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "l"(hint) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 :: "r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -99,10 +139,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
          | (1ull << 46)                                 // descriptor version (sm_100)
          | (2ull << 61);                                // SWIZZLE_128B
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128.
-constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GEMM_BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 
 // ---- the kernel ------------------------------------------------------------------------------------
+template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
@@ -110,6 +149,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using S = Shape<PAIR>;
+    constexpr int STAGES = S::STAGES, B_BYTES = S::B_BYTES, STAGE_BYTES = S::STAGE_BYTES;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + STAGES * STAGE_BYTES);
@@ -117,22 +158,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_jobs = m_tiles * splits;
+    // scheduling unit = CTA (or CTA pair); a unit works on jobs (query-tile unit mu, database split sp), dealt
+    // split-major so that units running at the same time sweep the SAME database tiles (L2 reuse) for different queries
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+    const int n_jobs = m_units * splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_db) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 128); }
+        // pair: the leader's `full` collects its own arrive(+expect_tx) and the peer's remote arrive; the
+        // leader's `tempty` collects the 128 epilogue threads of BOTH CTAs
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), PAIR ? 2 : 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), PAIR ? 256 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(&bars->tmem_base)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();              // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
@@ -140,16 +196,25 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-                const int mt = job / splits, sp = job - mt * splits;
+            for (int job = unit; job < n_jobs; job += n_units) {
+                const int sp = job / m_units, mu = job - sp * m_units;
+                const int mt = PAIR ? 2 * mu + (int)cta_rank : mu;
                 const int t0 = (int)((int64_t)sp * n_tiles / splits), t1 = (int)((int64_t)(sp + 1) * n_tiles / splits);
                 for (int t = t0; t < t1; ++t) {
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
                         const uint32_t full = smem_u32(&bars->full[stage]);
-                        mbar_expect_tx(full, STAGE_BYTES);
-                        tma_load_2d(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
-                        tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * tile_stride * GEMM_BN, HINT_EVICT_FIRST);
+                        if constexpr (PAIR) {
+                            if (cta_rank == 0) mbar_expect_tx(full, 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
+                            else mbar_arrive_remote(full, 0);
+                            tma_load_2d_pair(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
+                            tma_load_2d_pair(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK,
+                                             t * tile_stride * GEMM_BN + (int)cta_rank * S::B_ROWS, HINT_EVICT_LAST);
+                        } else {
+                            mbar_expect_tx(full, STAGE_BYTES);
+                            tma_load_2d(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
+                            tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * tile_stride * GEMM_BN, HINT_EVICT_FIRST);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -158,26 +223,31 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {                      // pair: only the leader issues
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-                const int mt = job / splits, sp = job - mt * splits;
+            for (int job = unit; job < n_jobs; job += n_units) {
+                const int sp = job / m_units;
                 const int t0 = (int)((int64_t)sp * n_tiles / splits), t1 = (int)((int64_t)(sp + 1) * n_tiles / splits);
                 for (int t = t0; t < t1; ++t, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                    mbar_wait(smem_u32(&bars->tempty[acc]), acc_phase ^ 1);      // epilogue drained this accumulator
+                    mbar_wait(smem_u32(&bars->tempty[acc]), acc_phase ^ 1);      // epilogue(s) drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
                     for (int kb = 0; kb < k_blocks; ++kb) {
-                        mbar_wait(smem_u32(&bars->full[stage]), phase);          // TMA bytes landed
+                        mbar_wait(smem_u32(&bars->full[stage]), phase);          // TMA bytes landed (in both CTAs)
                         tc_fence_after();
                         const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
                         const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
-                        for (int kk = 0; kk < GEMM_BK / 16; ++kk)                 // +32 B per K=16 step inside the atom
-                            tc_mma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, UMMA_IDESC, (kb | kk) != 0);
-                        tc_commit(smem_u32(&bars->empty[stage]));                 // frees the smem slot when the MMAs retire
-                        if (kb == k_blocks - 1) tc_commit(smem_u32(&bars->tfull[acc]));
+                        for (int kk = 0; kk < GEMM_BK / 16; ++kk) {               // +32 B per K=16 step inside the atom
+                            if constexpr (PAIR) tc_mma_bf16_pair(d_tmem, da + 2 * kk, db + 2 * kk, S::IDESC, (kb | kk) != 0);
+                            else                tc_mma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, S::IDESC, (kb | kk) != 0);
+                        }
+                        // frees the smem slot (in both CTAs) when the MMAs retire
+                        if constexpr (PAIR) tc_commit_pair(smem_u32(&bars->empty[stage])); else tc_commit(smem_u32(&bars->empty[stage]));
+                        if (kb == k_blocks - 1) {
+                            if constexpr (PAIR) tc_commit_pair(smem_u32(&bars->tfull[acc])); else tc_commit(smem_u32(&bars->tfull[acc]));
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -191,8 +261,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int m = sub * 32 + lane;                         // query row inside the tile = TMEM lane
         uint32_t* my_hist = whist + ew * 256;
         uint32_t it = 0;
-        for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-            const int mt = job / splits, sp = job - mt * splits;
+        // accumulator hand-back: the leader's MMA thread waits for both CTAs' epilogues
+        auto release_acc = [&](uint32_t acc) {
+            tc_fence_before();
+            if (PAIR && cta_rank != 0) mbar_arrive_remote(smem_u32(&bars->tempty[acc]), 0);
+            else mbar_arrive(smem_u32(&bars->tempty[acc]));
+        };
+        for (int job = unit; job < n_jobs; job += n_units) {
+            const int sp = job / m_units, mu = job - sp * m_units;
+            const int mt = PAIR ? 2 * mu + (int)cta_rank : mu;
             const int t0 = (int)((int64_t)sp * n_tiles / splits), t1 = (int)((int64_t)(sp + 1) * n_tiles / splits);
             const int64_t q = (int64_t)mt * GEMM_BM + m;
             const bool active = q < nq;
@@ -228,8 +305,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             }
                         }
                     }
-                    tc_fence_before();
-                    mbar_arrive(smem_u32(&bars->tempty[acc]));
+                    release_acc(acc);
                 }
                 if (active) {
 #pragma unroll
@@ -276,8 +352,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         if (lane == src) { cnt = c_new; thr = fmaxf(thr, key_score(T)); thr_rec = max(thr_rec, T); }
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(smem_u32(&bars->tempty[acc]));
+                release_acc(acc);
             }
             // end of job: keep only what can still matter -- everything within 2*eps below this
             // split's k-th best (the global k-th best is at least as large)
@@ -299,33 +374,37 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();              // the leader's MMAs wrote the peer's TMEM: both must be done
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else                asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
 // ---- host side -------------------------------------------------------------------------------------
-GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits) {
+GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits, bool allow_pair) {
     GemmPlan p{};
     p.m_tiles = (int)((nq + GEMM_BM - 1) / GEMM_BM);
     p.n_tiles = (int)(n_pad / GEMM_BN);
+    p.pair = (allow_pair && p.m_tiles >= 2) ? 1 : 0;
+    const int units = p.pair ? num_sms / 2 : num_sms;             // CTAs or CTA pairs
+    const int m_units = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
     int best = 1;
     if (forced_splits > 0) best = forced_splits;
     else {
-        // pick the split count that fills whole waves of `num_sms` jobs while keeping jobs long
+        // pick the split count that fills whole waves of `units` jobs while keeping jobs long
         double best_score = -1.0;
         const int s_max = (int)((p.n_tiles < 4096) ? p.n_tiles : 4096);
         for (int s = 1; s <= s_max; ++s) {
-            const int64_t jobs = (int64_t)p.m_tiles * s;
-            const int64_t rounds = (jobs + num_sms - 1) / num_sms;
-            // tiles per CTA on the critical path
-            const double tiles_per_job = (double)((p.n_tiles + s - 1) / s);
+            const int64_t jobs = (int64_t)m_units * s;
+            const int64_t rounds = (jobs + units - 1) / units;
+            const double tiles_per_job = (double)((p.n_tiles + s - 1) / s);     // tiles per unit on the critical path
             const double crit = (double)rounds * tiles_per_job;
-            const double ideal = (double)p.m_tiles * p.n_tiles / num_sms;
+            const double ideal = (double)m_units * p.n_tiles / units;
             const double score = ideal / crit - 0.0005 * s;      // prefer fewer, longer jobs on ties
             if (score > best_score) { best_score = score; best = s; }
-            if (jobs > (int64_t)num_sms * 64) break;
+            if (jobs > (int64_t)units * 64) break;
         }
     }
     if (best > p.n_tiles) best = p.n_tiles > 0 ? p.n_tiles : 1;
@@ -333,8 +412,9 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
     int keep = k + (k / 2 > 156 ? k / 2 : 156);
     p.k_keep = (keep + 31) & ~31;
     p.cap = 2 * p.k_keep;
-    const int64_t jobs = (int64_t)p.m_tiles * p.splits;
-    p.grid = (int)(jobs < num_sms ? jobs : num_sms);
+    const int64_t jobs = (int64_t)m_units * p.splits;
+    const int used = (int)(jobs < units ? jobs : units);
+    p.grid = p.pair ? 2 * used : used;
     p.tile_stride = 1;
     p.sample_mode = 0;
     return p;
@@ -344,6 +424,7 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
 // The k-th best score of that sample is a valid lower bound of the k-th best of the whole database.
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms) {
     GemmPlan p = main_plan;
+    p.pair = 0;                                      // the bootstrap pass always runs one CTA per tile
     const int all_tiles = main_plan.n_tiles;
     int s = (num_sms / 2) / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
     if (s < 16) s = 16;
@@ -361,12 +442,25 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
                              const float* thr0, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    auto kern = plan.pair ? gemm_topk_kernel<true> : gemm_topk_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
-    gemm_topk_kernel<<<plan.grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits,
-                                                                  d_pad / GEMM_BK, a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, eps, thr0,
-                                                                  pool_items, pool_count, pool_thr);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan.pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int k_blocks = d_pad / GEMM_BK;
+    return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, k_blocks,
+                              a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, eps, thr0,
+                              pool_items, pool_count, pool_thr);
 }
 
 }  // namespace xs

@@ -66,13 +66,14 @@ struct GemmPlan {
     int k_keep;       // items kept by a mid-job trim
     int cap;          // capacity of one partial list (>= 2 * k_keep)
     int grid;         // CTAs launched
+    int pair;         // 1: cta_group::2 kernel, clusters of two CTAs, 256 x 256 tiles (needs the box-128 database map)
     int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)
     int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
 };
-GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits);
+GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits, bool allow_pair);
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms);
 size_t   gemm_smem_bytes();
-// tmap_q: [nq_pad128][d_pad] bf16, box {64,128};  tmap_db: [n_pad][d_pad] bf16, box {64,256}
+// tmap_q: [nq_pad128][d_pad] bf16, box {64,128};  tmap_db: [n_pad][d_pad] bf16, box {64,256} (box {64,128} when plan.pair)
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
