@@ -419,7 +419,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             // threshold bootstrap on a strided sample of database tiles (skipped when the sample would be the whole database)
             const float* thr0 = nullptr;
             XS_TRY(ix->thr0.ensure((size_t)c * sizeof(float)));
-            GemmPlan sp = plan_gemm_sample(plan, ix->num_sms);
+            GemmPlan sp = plan_gemm_sample(plan, ix->num_sms, k);
             if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 4 * k) {
                 const int64_t sslots = (int64_t)sp.m_tiles * sp.splits * GEMM_BM;
                 XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));

@@ -357,7 +357,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             // end of job: keep only what can still matter -- everything within 2*eps below this
             // split's k-th best (the global k-th best is at least as large)
             const float band = active ? 2.f * eps[q] : 0.f;
-            uint32_t need = __ballot_sync(0xffffffffu, cnt > k);
+            // (short lists are left alone: the finaliser reads them anyway and a trim costs more than it saves)
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > k_keep);
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
@@ -422,12 +423,13 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
 
 // Threshold bootstrap: S database tiles spread evenly over the database (stride), one tile per job.
 // The k-th best score of that sample is a valid lower bound of the k-th best of the whole database.
-GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms) {
+GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
     GemmPlan p = main_plan;
     p.pair = 0;                                      // the bootstrap pass always runs one CTA per tile
     const int all_tiles = main_plan.n_tiles;
     int s = (num_sms / 2) / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
     if (s < 16) s = 16;
+    if (s < (3 * k + 3) / 4) s = (3 * k + 3) / 4;      // 8 scores per tile: the union must hold well over k of them
     if (s > all_tiles) s = all_tiles;
     p.n_tiles = s;
     p.tile_stride = all_tiles / s;
