@@ -90,15 +90,23 @@ __device__ void block_exclusive_scan(int* offs, int P, int* scratch) {
     __syncthreads();
 }
 
-// Copies every pooled item of query q into shared memory (flat), all loads independent.
-// offs[] must hold the exclusive scan of the list counts.  Returns nothing; items[0..total) filled.
+// Copies every pooled item of query q into shared memory (flat).  offs[] holds the exclusive scan of
+// the list counts.  Lists are short (tens of items), so the copy is laid out as a flat loop over
+// (list, position < 32) pairs -- every load independent of every other -- plus a remainder loop for
+// the rare longer list.
 __device__ void gather_pool(const uint64_t* __restrict__ pool_items, int64_t q, int P, int cap,
                             const int* offs, int total, uint64_t* items) {
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        int lo = 0, hi = P - 1;                       // largest p with offs[p] <= i
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid - 1; }
-        items[i] = pool_items[pool_slot(q, lo, P) * cap + (i - offs[lo])];
+    const int flat = P * 32;
+    for (int i = threadIdx.x; i < flat; i += blockDim.x) {
+        const int p = i >> 5, j = i & 31;
+        const int o = offs[p], c = offs[p + 1] - o;
+        if (j < c) items[o + j] = pool_items[pool_slot(q, p, P) * cap + j];
     }
+    for (int p = threadIdx.x >> 5; p < P; p += blockDim.x >> 5) {
+        const int o = offs[p], c = offs[p + 1] - o;
+        for (int j = 32 + (threadIdx.x & 31); j < c; j += 32) items[o + j] = pool_items[pool_slot(q, p, P) * cap + j];
+    }
+    (void)total;
     __syncthreads();
 }
 
