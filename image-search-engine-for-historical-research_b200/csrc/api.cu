@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -70,7 +71,7 @@ struct xs_index {
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; float debug_thr = 0.f;
     // workspace
-    Buf q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf dbg, fin_work, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -153,7 +154,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->dbg, &ix->fin_work, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
@@ -392,8 +393,10 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset; fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
+            XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
+            fa.work = ix->fin_work.p;
             launch_finalise(fa, c, ix->stream);
-            launches += 2;
+            launches += 1 + finalise_launches(fa, c);
         }
     } else {
         // tcgen05 GEMM with fused top-K, queries in batches that bound the pool workspace
@@ -452,8 +455,11 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
+            if (getenv("XS_FIN_DEBUG")) { XS_TRY(ix->dbg.ensure(16 * sizeof(long long))); fa.dbg = ix->dbg.as<long long>(); }
+            XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
+            fa.work = ix->fin_work.p;
             launch_finalise(fa, c, ix->stream);
-            launches += 2;
+            launches += 1 + finalise_launches(fa, c);
         }
     }
     CU_TRY(cudaEventRecord(ix->ev[3], ix->stream));
@@ -509,6 +515,13 @@ static int finish_to_host(xs_index* ix, float* q32, int64_t nq, int k, int64_t s
         CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
     }
     CU_TRY(cudaStreamSynchronize(ix->stream));
+    if (ix->dbg.p && getenv("XS_FIN_DEBUG")) {
+        long long h[16];
+        if (cudaMemcpy(h, ix->dbg.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "finalise CTA0 phases (cycles): count/scan %lld, gather %lld, select %lld, collect %lld, rescore %lld, self+sort %lld, emit %lld | pooled %lld cand %lld\n",
+                    h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[14], h[15]);
+        }
+    }
     if (coarse) {
         const int* st = ix->h_status.as<int>() + 1;
         ix->stats.n_candidates = ix->h_status.as<int>()[0];

@@ -14,6 +14,7 @@ namespace xs {
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_MAX_LISTS = 4096;          // partial lists per query that the shared-memory gather supports
 constexpr int FIN_SMEM_BUDGET = 200 * 1024;  // dynamic shared memory the finalise kernel may ask for
+constexpr int FIN_SPLIT_MAX_Q = 1 << 20;     // coarse-mode batches use the select -> rescore -> emit split (the fused kernel serves exact mode)
 
 // Exact inner products of TWO database rows with the query row held in shared memory: fp32
 // operands, fp64 accumulation, fixed order (lane-strided float4s, chunk by chunk), warp-reduced.
@@ -31,6 +32,7 @@ __device__ __forceinline__ void exact_dot2(const float* __restrict__ v0, const f
             x[j] = in ? ld_stream_f4(v0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             y[j] = (in && has1) ? ld_stream_f4(v1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        asm volatile("" ::: "memory");                  // keep every load of the chunk ahead of the arithmetic
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int i = base + j * 128 + lane * 4;
@@ -45,6 +47,32 @@ __device__ __forceinline__ void exact_dot2(const float* __restrict__ v0, const f
     }
     r0 = warp_sum(a0);
     r1 = warp_sum(a1);
+}
+
+// One row, the query row read through the read-only path (L1-resident after the first warp): up to
+// 16 x 512 B in flight per warp -- used where many CTAs share the rescoring of one query.
+__device__ __forceinline__ double exact_dot1(const float* __restrict__ v, const float* __restrict__ qrow, int d_pad) {
+    const int lane = lane_id();
+    double a = 0.0;
+    for (int base = 0; base < d_pad; base += 2048) {
+        float4 x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = base + j * 128 + lane * 4;
+            x[j] = (i < d_pad) ? ld_stream_f4(v + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("" ::: "memory");                  // keep every load of the chunk ahead of the arithmetic
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = base + j * 128 + lane * 4;
+            if (i < d_pad) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(qrow + i));
+                a = fma((double)x[j].x, (double)w.x, a); a = fma((double)x[j].y, (double)w.y, a);
+                a = fma((double)x[j].z, (double)w.z, a); a = fma((double)x[j].w, (double)w.w, a);
+            }
+        }
+    }
+    return warp_sum(a);
 }
 
 // Descending bitonic sort of m (power of two) 64-bit items in shared memory.
@@ -62,6 +90,55 @@ __device__ void block_sort_desc(uint64_t* a, int m) {
         }
     }
     __syncthreads();
+}
+
+// Conservative k-th-largest for COARSE scores (whole CTA of FIN_THREADS threads): one min/max pass
+// and one pass into 4096 bins spread over [min, max]; returns the lower edge of the bin that holds
+// the kk-th largest key -- never above it, at most one bin (typically 1-3 items) below.  The exactness
+// band is cut from that edge, so a lower value only adds a few candidates.  Replaces four 8-bit radix
+// passes with warp-match aggregation (28k cycles at 6.6k items) by ~4k cycles.
+template <typename Each>
+__device__ uint32_t block_kth_edge(Each each, uint32_t kk, uint32_t* bins, uint32_t* sh, uint32_t* wsum) {
+    constexpr int NB = 4096, PER = NB / FIN_THREADS;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; sh[2] = 0u; }
+    for (int i = threadIdx.x; i < NB; i += FIN_THREADS) bins[i] = 0;
+    __syncthreads();
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+    each([&](uint64_t it, bool valid) { if (valid) { const uint32_t key = item_key(it); kmin = min(kmin, key); kmax = max(kmax, key); } });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) { atomicMin(&sh[0], kmin); atomicMax(&sh[1], kmax); }
+    __syncthreads();
+    kmin = sh[0]; kmax = sh[1];
+    const uint32_t range = kmax - kmin;
+    const int shift = (range >> 12) ? (32 - __clz(range) - 12) : 0;
+    each([&](uint64_t it, bool valid) { if (valid) atomicAdd(&bins[(item_key(it) - kmin) >> shift], 1u); });
+    __syncthreads();
+    uint32_t h[PER], mine = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { h[j] = bins[threadIdx.x * PER + j]; mine += h[j]; }
+    uint32_t suf = mine;                                // suffix over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
+    if (lane == 0) wsum[warp] = suf;
+    __syncthreads();
+    uint32_t above = 0;
+    for (int w = warp + 1; w < FIN_THREADS / 32; ++w) above += wsum[w];
+    const uint32_t incl = above + suf, excl = incl - mine;
+    if (incl >= kk && excl < kk) {                      // exactly one thread
+        uint32_t run = excl;
+#pragma unroll
+        for (int j = PER - 1; j >= 0; --j) {
+            run += h[j];
+            if (run >= kk) { sh[2] = (uint32_t)(threadIdx.x * PER + j); break; }
+        }
+    }
+    __syncthreads();
+    return kmin + (sh[2] << shift);
 }
 
 // Exclusive prefix sum of offs[0..P) in place (offs[P] = total), whole CTA.  scratch: 33 words.
@@ -110,6 +187,10 @@ __device__ void gather_pool(const uint64_t* __restrict__ pool_items, int64_t q, 
     __syncthreads();
 }
 
+// SPLIT = false: the whole of stage 2 in one CTA per query (large batches, exact mode).
+// SPLIT = true : stops after the candidate gather and hands the list to rescore / emit kernels that use
+//                every SM (small batches, where one SM per query would be latency-bound on ~120 row reads).
+template <bool SPLIT>
 __global__ void __launch_bounds__(FIN_THREADS, 1)
 finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     extern __shared__ uint64_t fin_smem[];              // [cand_max] candidates | [item_cap] gathered items | [P+1] offsets
@@ -117,17 +198,24 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     uint64_t* items = fin_smem + cand_max;
     int* offs = reinterpret_cast<int*>(items + item_cap);
     float* qs = reinterpret_cast<float*>(offs + ((a.P <= FIN_MAX_LISTS) ? ((a.P + 4) & ~3) : 4));   // [d_pad] query row
+    uint32_t* bins = reinterpret_cast<uint32_t*>(qs + a.d_pad);                                     // [4096] (coarse mode)
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t edge_sh[4];
+    __shared__ uint32_t edge_wsum[FIN_THREADS / 32];
     __shared__ uint32_t misc[2];
     __shared__ int scan_scratch[33];
     __shared__ uint32_t sh_ncand, sh_flag, sh_selfkey;
     const int64_t q = blockIdx.x;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool staged = a.P <= FIN_MAX_LISTS;           // offsets fit -> try the shared-memory gather
+    int dbg_i = 0;
+#define FIN_STAMP() do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
+    FIN_STAMP();
 
     if (threadIdx.x == 0) { sh_ncand = 0; sh_flag = 0; sh_selfkey = 0; }
-    for (int i = threadIdx.x * 4; i < a.d_pad; i += blockDim.x * 4)
-        *reinterpret_cast<float4*>(qs + i) = *reinterpret_cast<const float4*>(a.q32 + q * a.d_pad + i);
+    if (!SPLIT)
+        for (int i = threadIdx.x * 4; i < a.d_pad; i += blockDim.x * 4)
+            *reinterpret_cast<float4*>(qs + i) = *reinterpret_cast<const float4*>(a.q32 + q * a.d_pad + i);
     __syncthreads();
     uint32_t total = 0;
     {   // list sizes, and the largest "something above this key was dropped upstream" mark
@@ -146,7 +234,9 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     }
     const uint32_t max_thr = sh_flag;
     const bool in_smem = staged && total <= (uint32_t)item_cap;
+    FIN_STAMP();
     if (in_smem) gather_pool(a.pool_items, q, a.P, a.cap, offs, (int)total, items);
+    FIN_STAMP();
 
     auto each = [&](auto fn) {
         if (in_smem) {
@@ -173,14 +263,17 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     uint64_t cut = 0;
     uint32_t cut_key = 0;
     if (total > kk) {
-        uint64_t T = block_kth_largest(each, kk, a.exact ? 8 : 4, hist, misc);
-        if (a.exact) { cut = T; cut_key = (uint32_t)(T >> 32); }
-        else {
-            cut_key = score_key(key_score((uint32_t)(T >> 32)) - 2.f * a.eps[q]);
+        if (a.exact) {
+            const uint64_t T = block_kth_largest(each, kk, 8, hist, misc);
+            cut = T; cut_key = (uint32_t)(T >> 32);
+        } else {
+            const uint32_t edge = block_kth_edge(each, kk, bins, edge_sh, edge_wsum);
+            cut_key = score_key(key_score(edge) - 2.f * a.eps[q]);
             cut = (uint64_t)cut_key << 32;
         }
     }
     __syncthreads();
+    FIN_STAMP();
     each([&](uint64_t it, bool valid) {
         bool take = valid && it >= cut;
         uint32_t m = __ballot_sync(0xffffffffu, take);
@@ -191,6 +284,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         if (take && pos < (uint32_t)cand_max) cand[pos] = it;
     });
     __syncthreads();
+    FIN_STAMP();
     const uint32_t found = sh_ncand;
     const int ncand = (int)min(found, (uint32_t)cand_max);
     // certificate: nothing that could belong to the exact top-k was dropped upstream
@@ -198,6 +292,11 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     if (!a.exact) uncertified = (found > (uint32_t)cand_max) || (max_thr != 0 && max_thr >= cut_key);
     else          uncertified = (max_thr != 0);
 
+    if (SPLIT) {      // hand over to finalise_rescore_kernel / finalise_emit_kernel
+        for (int c = threadIdx.x; c < ncand; c += blockDim.x) a.w_cand[q * cand_max + c] = cand[c];
+        if (threadIdx.x == 0) { a.w_ncand[q] = ncand; a.w_flag[q] = uncertified ? ST_UNCERTIFIED : 0; }
+        return;
+    }
     if (!a.exact) {   // exact rescoring, one warp per PAIR of candidates
         for (int c = warp * 2; c < ncand; c += nwarps * 2) {
             const bool has1 = c + 1 < ncand;
@@ -211,6 +310,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         }
     }
     __syncthreads();
+    FIN_STAMP();
     if (a.self_base >= 0) {   // self-kNN: the query's own row ranks first whatever the ties
         const uint32_t self_row = (uint32_t)(a.self_base + q);
         for (int c = threadIdx.x; c < ncand; c += blockDim.x)
@@ -228,6 +328,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     if (m < 2) m = 2;
     for (int c = ncand + threadIdx.x; c < m; c += blockDim.x) cand[c] = 0ull;
     block_sort_desc(cand, m);
+    FIN_STAMP();
 
     const int kout = min(a.k, ncand);
     for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
@@ -243,8 +344,95 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         a.out_idx[q * a.out_pitch + r] = id;
         if (a.out_score) a.out_score[q * a.out_pitch + r] = sc;
     }
+    FIN_STAMP();
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { a.dbg[14] = total; a.dbg[15] = ncand; }
     if (threadIdx.x == 0) {
         if (a.status) a.status[q] = uncertified ? ST_UNCERTIFIED : 0;
+        if (a.n_cand) atomicAdd(a.n_cand, ncand);
+    }
+}
+
+// ---- split pipeline: rescore on every SM, then sort + emit ---------------------------------------------
+constexpr int RS_SPLIT = 8;                  // CTAs per query in the rescoring kernel
+constexpr int RS_WARPS = 8;
+
+// grid (nq, RS_SPLIT): warp w of CTA (q, j) rescores candidates j*RS_WARPS + w, + RS_SPLIT*RS_WARPS, ...
+// The row is staged with cp.async (16 B per lane and step, all steps issued back to back) so the whole
+// 8 KB row is in flight at once -- with register loads ptxas interleaves each load with its use and a
+// warp never has more than ~3 outstanding.  24 resident warps per SM -> ~190 KB in flight per SM.
+__global__ void __launch_bounds__(RS_WARPS * 32)
+finalise_rescore_kernel(FinaliseArgs a, int cand_max) {
+    extern __shared__ float rs_rows[];                  // [RS_WARPS][d_pad]
+    const int64_t q = blockIdx.x;
+    const int ncand = a.w_ncand[q];
+    uint64_t* cand = a.w_cand + q * cand_max;
+    const float* qrow = a.q32 + q * a.d_pad;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    float* buf = rs_rows + (size_t)warp * a.d_pad;
+    const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
+    for (int c = blockIdx.y * RS_WARPS + warp; c < ncand; c += RS_SPLIT * RS_WARPS) {
+        const uint32_t row = item_row(cand[c]);
+        const float* v = a.db32 + (int64_t)row * a.d_pad;
+        for (int i = lane * 4; i < a.d_pad; i += 128)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbuf + (uint32_t)i * 4u), "l"(v + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        double acc = 0.0;
+        for (int i = lane * 4; i < a.d_pad; i += 128) {
+            const float4 x = *reinterpret_cast<const float4*>(buf + i);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(qrow + i));
+            acc = fma((double)x.x, (double)w.x, acc); acc = fma((double)x.y, (double)w.y, acc);
+            acc = fma((double)x.z, (double)w.z, acc); acc = fma((double)x.w, (double)w.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) cand[c] = make_item((float)acc, row);
+        __syncwarp();
+    }
+}
+
+// grid nq: sort the rescored candidates, apply the self-first rule, emit the first k
+__global__ void __launch_bounds__(256)
+finalise_emit_kernel(FinaliseArgs a, int cand_max) {
+    extern __shared__ uint64_t emit_cand[];             // [cand_max]
+    __shared__ uint32_t sh_selfkey;
+    const int64_t q = blockIdx.x;
+    const int ncand = a.w_ncand[q];
+    const uint64_t* src = a.w_cand + q * cand_max;
+    int m = 1;
+    while (m < ncand) m <<= 1;
+    if (m < 2) m = 2;
+    for (int c = threadIdx.x; c < m; c += blockDim.x) emit_cand[c] = (c < ncand) ? src[c] : 0ull;
+    if (threadIdx.x == 0) sh_selfkey = 0;
+    __syncthreads();
+    if (a.self_base >= 0) {
+        const uint32_t self_row = (uint32_t)(a.self_base + q);
+        for (int c = threadIdx.x; c < ncand; c += blockDim.x)
+            if (item_row(emit_cand[c]) == self_row)
+                emit_cand[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
+        if (threadIdx.x < 32) {
+            const float* vrow = a.db32 + (int64_t)self_row * a.d_pad;
+            const double s = exact_dot1(vrow, a.q32 + q * a.d_pad, a.d_pad);
+            if (threadIdx.x == 0) sh_selfkey = score_key((float)s);
+        }
+    }
+    block_sort_desc(emit_cand, m);
+    const int kout = min(a.k, ncand);
+    for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
+        int64_t id = -1;
+        float sc = -INFINITY;
+        if (r < kout) {
+            const uint64_t it = emit_cand[r];
+            uint32_t key = item_key(it);
+            if (a.self_base >= 0 && key == 0xFFFFFFFFu) key = sh_selfkey;
+            id = (int64_t)item_row(it) + a.id_offset;
+            sc = key_score(key);
+        }
+        a.out_idx[q * a.out_pitch + r] = id;
+        if (a.out_score) a.out_score[q * a.out_pitch + r] = sc;
+    }
+    if (threadIdx.x == 0) {
+        if (a.status) a.status[q] = a.w_flag[q];
         if (a.n_cand) atomicAdd(a.n_cand, ncand);
     }
 }
@@ -254,12 +442,20 @@ int finalise_cand_max(int k) {
     while (m < 2 * k) m <<= 1;
     return m;
 }
+size_t finalise_work_bytes(int64_t nq, int k) { return (size_t)nq * finalise_cand_max(k) * sizeof(uint64_t) + (size_t)nq * 2 * sizeof(int); }
 
-void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st) {
+void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
+    FinaliseArgs a = a_in;
     const int cand_max = finalise_cand_max(a.k);
+    const bool split = !a.exact && a.work && nq <= FIN_SPLIT_MAX_Q;
+    if (split) {
+        a.w_cand = static_cast<uint64_t*>(a.work);
+        a.w_ncand = reinterpret_cast<int*>(a.w_cand + (size_t)nq * cand_max);
+        a.w_flag = a.w_ncand + nq;
+    }
     const size_t offs_bytes = ((a.P <= FIN_MAX_LISTS) ? (size_t)((a.P + 4) & ~3) : 4) * sizeof(int);
-    const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float);
+    const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float) + 4096 * sizeof(uint32_t);
     // room for the gathered pool items: what the pools can hold, capped by the shared-memory budget
     size_t want_items = (size_t)a.P * (size_t)a.cap;
     size_t max_items = (FIN_SMEM_BUDGET > fixed) ? (FIN_SMEM_BUDGET - fixed) / sizeof(uint64_t) : 0;
@@ -268,9 +464,21 @@ void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st) {
     item_cap = (item_cap + 1) & ~1;                  // keeps the fp32 query row behind it 16-byte aligned
     if (a.P > FIN_MAX_LISTS) item_cap = 0;
     const size_t smem = fixed + (size_t)item_cap * sizeof(uint64_t);
-    cudaFuncSetAttribute(finalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
-    finalise_kernel<<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max, item_cap);
+    if (split) {
+        cudaFuncSetAttribute(finalise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
+        finalise_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max, item_cap);
+        const size_t rsm = (size_t)RS_WARPS * a.d_pad * sizeof(float);
+        if (rsm > 48 * 1024) cudaFuncSetAttribute(finalise_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+        finalise_rescore_kernel<<<dim3((unsigned)nq, RS_SPLIT), RS_WARPS * 32, rsm, st>>>(a, cand_max);
+        const size_t esm = (size_t)cand_max * sizeof(uint64_t);
+        if (esm > 48 * 1024) cudaFuncSetAttribute(finalise_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm);
+        finalise_emit_kernel<<<(unsigned)nq, 256, esm, st>>>(a, cand_max);
+    } else {
+        cudaFuncSetAttribute(finalise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
+        finalise_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max, item_cap);
+    }
 }
+int finalise_launches(const FinaliseArgs& a, int64_t nq) { return (!a.exact && a.work && nq <= FIN_SPLIT_MAX_Q) ? 3 : 1; }
 
 // ---- threshold bootstrap ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
