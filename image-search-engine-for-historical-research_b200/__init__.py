@@ -5,6 +5,7 @@ Public surface = the reference's three call shapes for this path (SURVEY.md sect
 * ``matching_L2(K, train, test) -> (idx, time_per_query)``      src/utils/nnsearch.py:687
 * ``rank_ip(vecs, qvecs, K=None) -> ranks``                     src/main_retrieve.py:175-176
 * ``KNN(database, 'cosine').search(queries, k) -> (sims, ids)`` src/utils/knn.py:8-40
+* ``qge1(ranks, qvec, vecs, K) -> ranks_aqe`` (AQE second pass)   src/utils/Reranking.py:287-306
 
 backed by hand-written sm_100a CUDA behind the C ABI in ``include/xs_b200.h``.  No CPU fallback.
 """
@@ -12,6 +13,7 @@ from .index import ExactIndex
 from .knn import KNN, BaseKNN
 from .nnsearch import matching, matching_L2, cached_index, clear_index_cache
 from .ranking import rank_ip
+from .reranking import feature_enhancement, qge1
 
 __all__ = ["ExactIndex", "KNN", "BaseKNN", "matching", "matching_L2", "rank_ip",
-           "cached_index", "clear_index_cache"]
+           "cached_index", "clear_index_cache", "feature_enhancement", "qge1"]

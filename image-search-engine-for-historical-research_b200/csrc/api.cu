@@ -71,7 +71,7 @@ struct xs_index {
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; float debug_thr = 0.f;
     // workspace
-    Buf dbg, fin_work, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf dbg, fin_work, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -154,7 +154,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->dbg, &ix->fin_work, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->dbg, &ix->fin_work, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
@@ -608,6 +608,36 @@ extern "C" int xs_search(xs_index* ix, const void* q, int dtype, int64_t nq, int
     a.path = choose_path(ix, nq, k);
     XS_TRY(search_core(ix, a));
     ix->stats.gpu_launches += extra_launches;
+    return finish_to_host(ix, a.q32, nq, k, -1, a.out_idx, a.out_score, a.status, a.path != PATH_EXACT, out_idx, out_score);
+}
+
+extern "C" int xs_aqe_search(xs_index* ix, const int64_t* top_ids, int64_t nq, int kq, double w, int k,
+                             int64_t* out_idx, float* out_score, float* out_queries) {
+    XS_TRY(check_search_args(ix, nq, k));
+    if (!top_ids || !out_idx) return fail(XS_ERR_ARG, "null pointer");
+    if (kq < 1 || kq > 64) return fail(XS_ERR_ARG, "kq=%d out of range [1, 64]", kq);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    XS_TRY(ix->aqe_ids.ensure((size_t)nq * kq * sizeof(int64_t)));
+    XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
+    XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
+    XS_TRY(ix->out_idx.ensure((size_t)nq * k * sizeof(int64_t)));
+    XS_TRY(ix->out_score.ensure((size_t)nq * k * sizeof(float)));
+    // ids arrive as the caller saw them (row + id_offset); the kernel wants local rows
+    std::vector<int64_t> local((size_t)nq * kq);
+    for (size_t i = 0; i < local.size(); ++i) local[i] = top_ids[i] - ix->id_offset;
+    CU_TRY(cudaMemcpyAsync(ix->aqe_ids.p, local.data(), local.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    launch_aqe_queries(ix->db32, ix->aqe_ids.as<int64_t>(), nq, kq, w, ix->n, ix->d_pad, ix->q32.as<float>(), ix->stream);
+    CU_TRY(cudaStreamSynchronize(ix->stream));          // `local` is pageable and about to go out of scope
+    CoreArgs a{};
+    a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = false; a.tmap_a = nullptr; a.a_row0 = 0;
+    a.self_base = -1; a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
+    a.path = choose_path(ix, nq, k);
+    XS_TRY(search_core(ix, a));
+    ix->stats.gpu_launches += 1;
+    if (out_queries)
+        CU_TRY(cudaMemcpy2DAsync(out_queries, (size_t)ix->d * sizeof(float), ix->q32.p, (size_t)ix->d_pad * sizeof(float),
+                                 (size_t)ix->d * sizeof(float), (size_t)nq, cudaMemcpyDeviceToHost, ix->stream));
     return finish_to_host(ix, a.q32, nq, k, -1, a.out_idx, a.out_score, a.status, a.path != PATH_EXACT, out_idx, out_score);
 }
 

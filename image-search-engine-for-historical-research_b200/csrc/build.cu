@@ -213,6 +213,77 @@ bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16,
     return true;
 }
 
+// ---- AQE query construction ------------------------------------------------------------------------
+// feature_enhancement of src/utils/Reranking.py:195-208 / :288-301 up to the re-score: for every query
+// take its kq best database rows, weight them ((kq-j)/kq)^w (j = 0 best), sum, divide by (norm + 1e-6).
+// One CTA per query, float64 accumulation (the reference's weights are float64, so numpy promotes).
+__global__ void __launch_bounds__(256)
+aqe_queries_kernel(const float* __restrict__ db32, const int64_t* __restrict__ top_ids, int kq, double w, int64_t n,
+                   int d_pad, float* __restrict__ q_out) {
+    __shared__ double red[8];
+    __shared__ double sh_scale;
+    const int64_t q = blockIdx.x;
+    const int64_t* ids = top_ids + q * kq;
+    double acc[8];                                      // d_pad <= 8 * 256 handled per pass; larger rows loop
+    double ss = 0.0;
+    for (int base = 0; base < d_pad; base += 8 * 256) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.0;
+        for (int j = 0; j < kq; ++j) {
+            const int64_t id = ids[j];
+            if (id < 0 || id >= n) continue;
+            const double wj = pow((double)(kq - j) / (double)kq, w);
+            const float* row = db32 + id * d_pad;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int c = base + t * 256 + threadIdx.x;
+                if (c < d_pad) acc[t] += wj * (double)row[c];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = base + t * 256 + threadIdx.x;
+            if (c < d_pad) { ss += acc[t] * acc[t]; q_out[q * d_pad + c] = (float)acc[t]; }   // unscaled for now
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        sh_scale = 1.0 / (sqrt(t) + 1e-6);
+    }
+    __syncthreads();
+    // second pass: recompute in float64 and scale before the single rounding to fp32
+    for (int base = 0; base < d_pad; base += 8 * 256) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.0;
+        for (int j = 0; j < kq; ++j) {
+            const int64_t id = ids[j];
+            if (id < 0 || id >= n) continue;
+            const double wj = pow((double)(kq - j) / (double)kq, w);
+            const float* row = db32 + id * d_pad;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int c = base + t * 256 + threadIdx.x;
+                if (c < d_pad) acc[t] += wj * (double)row[c];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int c = base + t * 256 + threadIdx.x;
+            if (c < d_pad) q_out[q * d_pad + c] = (float)(acc[t] * sh_scale);
+        }
+    }
+}
+
+void launch_aqe_queries(const float* db32, const int64_t* top_ids, int64_t nq, int kq, double w, int64_t n, int d_pad,
+                        float* q_out, cudaStream_t st) {
+    if (nq <= 0) return;
+    aqe_queries_kernel<<<(unsigned)nq, 256, 0, st>>>(db32, top_ids, kq, w, n, d_pad, q_out);
+}
+
 void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
                          const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st) {
     if (nq <= 0) return;

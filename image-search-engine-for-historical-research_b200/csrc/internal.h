@@ -43,6 +43,10 @@ void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, 
 bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16, int64_t nq, int64_t nq_pad, int d, int d_pad,
                                bool renorm, const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
 
+// AQE (Reranking.py:195-208): q_out[q] = normalise( sum_j ((kq-j)/kq)^w * db32[top_ids[q][j]] ), float64 inside.
+void launch_aqe_queries(const float* db32, const int64_t* top_ids, int64_t nq, int kq, double w, int64_t n, int d_pad,
+                        float* q_out, cudaStream_t st);
+
 // ---- scan.cu ------------------------------------------------------------------------------------
 // Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  Both scoring kernels also
 // add every score to ghist[q][score_key >> HIST_SHIFT] (zeroed by the caller).

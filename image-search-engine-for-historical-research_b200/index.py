@@ -109,6 +109,19 @@ class ExactIndex:
         nat.check(self._lib.xs_self_knn(self._h, int(begin), end, int(k), ids.ctypes.data, sims.ctypes.data), "xs_self_knn")
         return sims, ids
 
+    def aqe_search(self, top_ids, k: int, w: float = 4.0, return_queries: bool = False):
+        """Average-query-expansion re-score (src/utils/Reranking.py:195-208): ``top_ids`` is
+        ``(nq, kq)`` -- each query's kq best ids from a previous search; returns ``(ids, sims)`` of the
+        expanded queries (and the expanded queries ``(nq, D)`` fp32 with ``return_queries``)."""
+        t = np.ascontiguousarray(top_ids, dtype=np.int64)
+        nq, kq = t.shape
+        ids = np.empty((nq, int(k)), dtype=np.int64)
+        sims = np.empty((nq, int(k)), dtype=np.float32)
+        qe = np.empty((nq, self.D), dtype=np.float32) if return_queries else None
+        nat.check(self._lib.xs_aqe_search(self._h, t.ctypes.data, nq, kq, float(w), int(k), ids.ctypes.data, sims.ctypes.data,
+                                          qe.ctypes.data if return_queries else None), "xs_aqe_search")
+        return (ids, sims, qe) if return_queries else (ids, sims)
+
     def rank_all(self, queries, renormalise: bool = False, return_scores: bool = False):
         """Full ranking: ``ranks int64 (N, nq)``, one column per query, best first -- the array
         ``np.argsort(-scores, axis=0)`` yields at src/main_retrieve.py:176."""

@@ -123,6 +123,18 @@ XS_API int xs_self_knn(xs_index* index, int64_t q_begin, int64_t q_end, int k,
                 int64_t* out_idx, float* out_score);
 
 /*
+ * Average-query-expansion re-score, on the device end to end.
+ *   replaces: feature_enhancement + re-ranking inside qge1 / QGE   src/utils/Reranking.py:195-208, 287-306
+ *             (the second database scan of every web request, src/online.py:148)
+ * top_ids      HOST [nq, kq] int64: the kq best ids of each query from a previous search (ranks[:kq].T).
+ * The new query is normalise( sum_j ((kq-j)/kq)^w * row(top_ids[q][j]) ), divided by (norm + 1e-6) as at
+ * Reranking.py:203, built in float64 from the index's fp32 rows; it is then searched like xs_search
+ * (no further normalisation).  out_queries (may be NULL): HOST [nq, d] fp32, the expanded queries.
+ */
+XS_API int xs_aqe_search(xs_index* index, const int64_t* top_ids, int64_t nq, int kq, double w, int k,
+                         int64_t* out_idx, float* out_score, float* out_queries);
+
+/*
  * Full ranking (k == n) for nq host queries: out_ranks is [n, nq] int64, one COLUMN per query,
  * best first -- the exact shape of `ranks` at main_retrieve.py:176 / evaluate.py:52-55.
  */

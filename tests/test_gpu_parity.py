@@ -237,3 +237,21 @@ def test_pair_mode_large_batches(pkg, synth, oracle, nq, n):
         ids1, sims1 = ix.search(q.T, 50)
         np.testing.assert_array_equal(ids1, ids)
         np.testing.assert_array_equal(sims1, sims)
+
+
+def test_qge1_aqe_second_pass(pkg, synth, oracle, golden):
+    """AQE re-score (Reranking.py:287-306) built and searched on the device vs the reference's own output."""
+    vecs, qvecs = synth.gaussian(512, 8, d=64)
+    first = pkg.rank_ip(vecs, qvecs, K=10)
+    np.testing.assert_array_equal(first, golden["A_ranks"][:10])
+    r10 = pkg.qge1(first, qvecs, vecs, 10)
+    assert r10.shape == (10, 8) and r10.dtype == np.int64
+    np.testing.assert_array_equal(r10, golden["A_qge1_ranks"][:10])
+    full = pkg.qge1(first, qvecs, vecs, 10, full=True)
+    assert full.shape == (512, 8)
+    qe, _ = oracle.feature_enhancement(1, 3, golden["A_ranks"][:10], qvecs, vecs, 4.0)
+    s64 = np.dot(vecs.T.astype(np.float64), qe)
+    _check_lists(oracle, full.T, golden["A_qge1_ranks"].T, s64, "qge1 full ranking")
+    qe_gpu, _ = pkg.feature_enhancement(1, 3, first, qvecs, vecs, 4.0, K=5)
+    np.testing.assert_allclose(qe_gpu, qe, rtol=2e-6, atol=1e-7)
+    pkg.clear_index_cache()
