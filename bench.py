@@ -243,9 +243,7 @@ def run_ours(args):
     # ---- dominant kernel, timed on its own stream by the library's CUDA events --------------------------
     coarse = []
     for _ in range(min(args.steps, 20)):
-        index.search_device(queries.data_ptr(), N_QUERIES, TOPK, shard._buffers(N_QUERIES, TOPK)[0].data_ptr(),
-                            shard._buffers(N_QUERIES, TOPK)[1].data_ptr(), status_ptr=shard._buffers(N_QUERIES, TOPK)[2].data_ptr(),
-                            stream=torch.cuda.current_stream().cuda_stream)
+        shard.local_search(queries, TOPK)
         coarse.append(index.stats()["ms_coarse"])
     coarse_ms = sum(coarse) / len(coarse)
     stats = index.stats()

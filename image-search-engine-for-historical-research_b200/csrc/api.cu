@@ -732,8 +732,18 @@ extern "C" int xs_merge_candidates(int device, const int64_t* in_idx, const floa
     if (!in_idx || !in_score || !out_idx) return fail(XS_ERR_ARG, "null pointer");
     if (n_parts <= 0 || nq <= 0 || k <= 0) return fail(XS_ERR_ARG, "bad sizes");
     if ((int64_t)n_parts * k > 16384) return fail(XS_ERR_UNSUPPORTED, "n_parts*k = %lld > 16384", (long long)n_parts * k);
+    // two dense arrays: ids advance nq*k*8 bytes per part, scores nq*k*4
+    return xs_merge_candidates_strided(device, in_idx, in_score, nq * k * 8, nq * k * 4, n_parts, nq, k, out_idx, out_score, stream);
+}
+
+extern "C" int xs_merge_candidates_strided(int device, const void* in_idx, const void* in_score, int64_t idx_part_stride,
+                                           int64_t score_part_stride, int n_parts, int64_t nq, int k,
+                                           int64_t* out_idx, float* out_score, void* stream) {
+    if (!in_idx || !in_score || !out_idx) return fail(XS_ERR_ARG, "null pointer");
+    if (n_parts <= 0 || nq <= 0 || k <= 0) return fail(XS_ERR_ARG, "bad sizes");
+    if ((int64_t)n_parts * k > 16384) return fail(XS_ERR_UNSUPPORTED, "n_parts*k = %lld > 16384", (long long)n_parts * k);
     CU_TRY(cudaSetDevice(device));
-    launch_merge_parts(in_idx, in_score, n_parts, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream));
+    launch_merge_parts(in_idx, in_score, idx_part_stride, score_part_stride, n_parts, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream));
     CU_TRY(cudaGetLastError());
     return XS_OK;
 }

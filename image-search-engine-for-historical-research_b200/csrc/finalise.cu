@@ -528,7 +528,7 @@ void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, 
 // in: [parts][nq][k] (score desc, id asc inside every part; parts own increasing id ranges, so the
 // flat position p*k + r orders equal scores by ascending id).  One CTA per query.
 __global__ void __launch_bounds__(512)
-merge_parts_kernel(const int64_t* __restrict__ in_idx, const float* __restrict__ in_score, int parts,
+merge_parts_kernel(const char* __restrict__ in_idx, const char* __restrict__ in_score, int64_t idx_stride, int64_t score_stride, int parts,
                    int64_t nq, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_score, int m) {
     extern __shared__ uint64_t cand[];                  // [m] power of two >= parts*k
     const int64_t q = blockIdx.x;
@@ -536,30 +536,31 @@ merge_parts_kernel(const int64_t* __restrict__ in_idx, const float* __restrict__
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         uint64_t it = 0ull;
         if (i < total) {
-            int p = i / k, r = i - p * k;
-            int64_t src = ((int64_t)p * nq + q) * k + r;
-            if (in_idx[src] >= 0) it = make_item(in_score[src], (uint32_t)i);
+            const int p = i / k, r = i - p * k;
+            const int64_t* ids = reinterpret_cast<const int64_t*>(in_idx + (int64_t)p * idx_stride);
+            const float* sc = reinterpret_cast<const float*>(in_score + (int64_t)p * score_stride);
+            if (ids[q * k + r] >= 0) it = make_item(sc[q * k + r], (uint32_t)i);
         }
         cand[i] = it;
     }
     block_sort_desc(cand, m);
     for (int r = threadIdx.x; r < k; r += blockDim.x) {
-        uint64_t it = cand[r];
+        const uint64_t it = cand[r];
         int64_t id = -1;
-        float sc = -INFINITY;
+        float s = -INFINITY;
         if (it != 0ull) {
-            int i = (int)item_row(it);
-            int p = i / k, rr = i - p * k;
-            int64_t src = ((int64_t)p * nq + q) * k + rr;
-            id = in_idx[src];
-            sc = in_score[src];
+            const int i = (int)item_row(it);
+            const int p = i / k, rr = i - p * k;
+            id = reinterpret_cast<const int64_t*>(in_idx + (int64_t)p * idx_stride)[q * k + rr];
+            s = reinterpret_cast<const float*>(in_score + (int64_t)p * score_stride)[q * k + rr];
         }
         out_idx[q * k + r] = id;
-        if (out_score) out_score[q * k + r] = sc;
+        if (out_score) out_score[q * k + r] = s;
     }
 }
 
-void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts, int64_t nq, int k,
+// part p's id list starts at in_idx + p*idx_stride BYTES, its score list at in_score + p*score_stride BYTES
+void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride, int64_t score_stride, int parts, int64_t nq, int k,
                         int64_t* out_idx, float* out_score, cudaStream_t st) {
     if (nq <= 0) return;
     int m = 2;
@@ -567,7 +568,8 @@ void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts,
     const size_t smem = (size_t)m * sizeof(uint64_t);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(in_idx, in_score, parts, nq, k, out_idx, out_score, m);
+    merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(static_cast<const char*>(in_idx), static_cast<const char*>(in_score), idx_stride, score_stride,
+                                                      parts, nq, k, out_idx, out_score, m);
 }
 
 }  // namespace xs

@@ -106,7 +106,7 @@ void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st);
 // Multi-GPU merge of [parts][nq][k] lists.
-void launch_merge_parts(const int64_t* in_idx, const float* in_score, int parts, int64_t nq, int k,
+void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride_bytes, int64_t score_stride_bytes, int parts, int64_t nq, int k,
                         int64_t* out_idx, float* out_score, cudaStream_t st);
 // ---- sort.cu ------------------------------------------------------------------------------------
 // Full ranking (K == N): stable segmented radix sort of c exact score rows; writes columns q0..q0+c of

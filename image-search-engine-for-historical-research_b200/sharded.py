@@ -51,8 +51,9 @@ def merge_parts_host(ids_parts: np.ndarray, sims_parts: np.ndarray, k: int):
 class ShardedSearcher:
     """Glue between a per-rank local searcher and the process group.
 
-    ``local_search(queries, k) -> (ids [nq,k] int64 GLOBAL ids, sims [nq,k] f32)`` as torch tensors
-    on ``device``; ``merge(ids_all [G,nq,k], sims_all [G,nq,k], k) -> (ids, sims)``.
+    ``local_search(queries, k) -> packed`` : one 1-D uint8 tensor per rank holding the local exact
+    top-k as ``[ids int64 (nq*k) | sims f32 (nq*k)]`` with GLOBAL ids -- packed so that the exchange
+    is ONE all-gather; ``merge(packed_all, world, nq, k) -> (ids [nq,k], sims [nq,k])``.
     """
 
     def __init__(self, local_search, merge, group=None):
@@ -62,19 +63,33 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local_search = local_search
         self.merge = merge
+        self._gathered = {}
 
     def search(self, queries, k: int):
         import torch
-        ids, sims = self.local_search(queries, k)
+        nq = int(queries.shape[0])
+        packed = self.local_search(queries, k)
         if self.world == 1:
-            return ids, sims
-        nq, kk = ids.shape
-        # concatenated along dim 0 (the layout both NCCL and gloo accept), viewed as [G, nq, k]
-        ids_all = torch.empty((self.world * nq, kk), dtype=ids.dtype, device=ids.device)
-        sims_all = torch.empty((self.world * nq, kk), dtype=sims.dtype, device=sims.device)
-        self.dist.all_gather_into_tensor(ids_all, ids.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(sims_all, sims.contiguous(), group=self.group)
-        return self.merge(ids_all.view(self.world, nq, kk), sims_all.view(self.world, nq, kk), k)
+            return unpack(packed, nq, k)
+        key = (nq, k, packed.device)
+        if key not in self._gathered:
+            self._gathered[key] = torch.empty((self.world * packed.numel(),), dtype=torch.uint8, device=packed.device)
+        packed_all = self._gathered[key]
+        self.dist.all_gather_into_tensor(packed_all, packed, group=self.group)
+        return self.merge(packed_all, self.world, nq, k)
+
+
+def packed_bytes(nq: int, k: int) -> int:
+    """Bytes of one rank's packed result, padded to 16 so that every part stays aligned after the gather."""
+    return (nq * k * 12 + 15) // 16 * 16
+
+
+def unpack(packed, nq: int, k: int):
+    """Views (no copy) of one rank's packed result: ``(ids int64 [nq,k], sims f32 [nq,k])``."""
+    import torch
+    ids = packed[: nq * k * 8].view(torch.int64).view(nq, k)
+    sims = packed[nq * k * 8: nq * k * 12].view(torch.float32).view(nq, k)
+    return ids, sims
 
 
 class CudaShard:
@@ -93,26 +108,43 @@ class CudaShard:
         key = (nq, k)
         if key not in self._out:
             dev = torch.device("cuda", self.device)
-            self._out[key] = (torch.empty((nq, k), dtype=torch.int64, device=dev),
-                              torch.empty((nq, k), dtype=torch.float32, device=dev),
-                              torch.zeros((nq,), dtype=torch.int32, device=dev))
+            packed = torch.empty((packed_bytes(nq, k),), dtype=torch.uint8, device=dev)
+            ids, sims = unpack(packed, nq, k)
+            self._out[key] = (ids, sims, torch.zeros((nq,), dtype=torch.int32, device=dev), packed)
         return self._out[key]
 
     def local_search(self, queries, k):
-        """``queries``: fp32 row-major torch tensor on this rank's device."""
+        """``queries``: fp32 row-major torch tensor on this rank's device.  Returns the packed result."""
         torch = self.torch
         nq = int(queries.shape[0])
-        ids, sims, status = self._buffers(nq, k)
+        ids, sims, status, packed = self._buffers(nq, k)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.index.search_device(queries.data_ptr(), nq, k, ids.data_ptr(), sims.data_ptr(),
                                  status_ptr=status.data_ptr(), stream=stream)
-        return ids, sims
+        return packed
 
     def uncertified(self, nq, k) -> int:
         """Number of queries of the last local_search(nq, k) the bf16 pass could not certify."""
         return int(self._buffers(nq, k)[2].sum().item())
 
-    def merge(self, ids_all, sims_all, k):
+    def merge(self, packed_all, world, nq, k):
+        torch = self.torch
+        key = ("m", nq, k)
+        if key not in self._out:
+            self._out[key] = (torch.empty((nq, k), dtype=torch.int64, device=packed_all.device),
+                              torch.empty((nq, k), dtype=torch.float32, device=packed_all.device))
+        out_i, out_s = self._out[key]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stride = packed_bytes(nq, k)
+        base = packed_all.data_ptr()
+        nat.check(self.lib.xs_merge_candidates_strided(self.device, C.c_void_p(base), C.c_void_p(base + nq * k * 8), stride, stride,
+                                                       int(world), int(nq), int(k), C.c_void_p(out_i.data_ptr()),
+                                                       C.c_void_p(out_s.data_ptr()), C.c_void_p(stream) if stream else None),
+                  "xs_merge_candidates_strided")
+        return out_i, out_s
+
+    def merge_lists(self, ids_all, sims_all, k):
+        """Merge of two dense ``[G, nq, k]`` arrays (xs_merge_candidates) -- kept for callers that gather separately."""
         torch = self.torch
         g, nq, kk = ids_all.shape
         out_i = torch.empty((nq, k), dtype=torch.int64, device=ids_all.device)

@@ -152,6 +152,14 @@ XS_API int xs_merge_candidates(int device, const int64_t* in_idx, const float* i
                         int64_t* out_idx, float* out_score, void* stream);
 
 /*
+ * Same merge for lists that were gathered as ONE packed buffer per rank ([ids | scores] bytes back to
+ * back): part p's ids start idx_part_stride BYTES after part p-1's, its scores score_part_stride bytes.
+ */
+XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const void* in_score, int64_t idx_part_stride,
+                                       int64_t score_part_stride, int n_parts, int64_t nq, int k,
+                                       int64_t* out_idx, float* out_score, void* stream);
+
+/*
  * Tunables (set before searching; all have safe defaults):
  *   "eps_sigmas"   float  width of the bf16 error band in standard deviations      (8.0)
  *   "scan_max_q"   int    largest batch served by the batch-1 HBM scan kernel      (1)

@@ -176,8 +176,16 @@ def test_merge_kernel_matches_host_merge(pkg, synth, oracle):
     ids_all = torch.from_numpy(np.stack(ids_parts)).cuda()
     sims_all = torch.from_numpy(np.stack(sims_parts)).cuda()
     cs = sharded.CudaShard(shards[0], 0)
-    mi, ms = cs.merge(ids_all, sims_all, k)
+    mi, ms = cs.merge_lists(ids_all, sims_all, k)
+    # and the packed single-gather layout: [ids | sims] bytes per part, back to back
+    pb = sharded.packed_bytes(6, k)
+    packed_all = torch.zeros((world * pb,), dtype=torch.uint8, device="cuda")
+    for g in range(world):
+        gi, gs = sharded.unpack(packed_all[g * pb:(g + 1) * pb], 6, k)
+        gi.copy_(ids_all[g]); gs.copy_(sims_all[g])
+    pi, ps = cs.merge(packed_all, world, 6, k)
     torch.cuda.synchronize()
+    assert torch.equal(pi, mi) and torch.equal(ps, ms)
     hi, hs = sharded.merge_parts_host(np.stack(ids_parts), np.stack(sims_parts), k)
     np.testing.assert_array_equal(mi.cpu().numpy(), hi)
     np.testing.assert_array_equal(ms.cpu().numpy(), hs)

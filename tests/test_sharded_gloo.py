@@ -37,10 +37,15 @@ def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
         if pad:
             ids = np.concatenate([ids, -np.ones((ids.shape[0], pad), np.int64) - lo], axis=1)
             sims = np.concatenate([sims, np.full((sims.shape[0], pad), -np.inf, np.float32)], axis=1)
-        return torch.from_numpy(ids + lo), torch.from_numpy(sims)
+        packed = torch.empty((sharded.packed_bytes(ids.shape[0], kk),), dtype=torch.uint8)
+        pi, ps = sharded.unpack(packed, ids.shape[0], kk)
+        pi.copy_(torch.from_numpy(ids + lo)); ps.copy_(torch.from_numpy(sims))
+        return packed
 
-    def merge(ids_all, sims_all, kk):
-        i, s = sharded.merge_parts_host(ids_all.numpy(), sims_all.numpy(), kk)
+    def merge(packed_all, world_, nq_, kk):
+        parts = [sharded.unpack(packed_all[g * sharded.packed_bytes(nq_, kk):(g + 1) * sharded.packed_bytes(nq_, kk)], nq_, kk)
+                 for g in range(world_)]
+        i, s = sharded.merge_parts_host(np.stack([p[0].numpy() for p in parts]), np.stack([p[1].numpy() for p in parts]), kk)
         return torch.from_numpy(i), torch.from_numpy(s)
 
     searcher = sharded.ShardedSearcher(local_search, merge)
