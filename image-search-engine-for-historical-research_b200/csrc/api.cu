@@ -71,7 +71,7 @@ struct xs_index {
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; float debug_thr = 0.f;
     // workspace
-    Buf dbg, fin_work, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf fin_work, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -154,7 +154,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->dbg, &ix->fin_work, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->fin_work, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
@@ -455,7 +455,6 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
-            if (getenv("XS_FIN_DEBUG")) { XS_TRY(ix->dbg.ensure(16 * sizeof(long long))); fa.dbg = ix->dbg.as<long long>(); }
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
             fa.work = ix->fin_work.p;
             launch_finalise(fa, c, ix->stream);
@@ -475,20 +474,21 @@ static int choose_path(const xs_index* ix, int64_t nq, int k) {
     return PATH_GEMM;
 }
 
-// After the coarse pass: read the certificate bits, re-run uncertified queries exactly.
+// Device-API epilogue when the caller did not ask for the certificate bits: read them (one
+// synchronisation), re-run uncertified queries exactly into the caller's device buffers.
 static int rerun_uncertified(xs_index* ix, float* q32, int64_t nq, int k, int64_t self_base, int64_t* out_idx, float* out_score, int* status_dev) {
-    std::vector<int> st((size_t)nq);
-    CU_TRY(cudaMemcpyAsync(st.data(), status_dev, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
-    int ncand = 0;
-    CU_TRY(cudaMemcpyAsync(&ncand, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    XS_TRY(ix->h_status.ensure((size_t)(nq + 1) * sizeof(int)));
+    CU_TRY(cudaMemcpyAsync(ix->h_status.as<int>() + 1, status_dev, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
     CU_TRY(cudaStreamSynchronize(ix->stream));
-    ix->stats.n_candidates = ncand;
+    const int* st = ix->h_status.as<int>() + 1;
+    ix->stats.n_candidates = ix->h_status.as<int>()[0];
     int launches = 0;
     int64_t reruns = 0;
     for (int64_t q = 0; q < nq;) {
-        if (!(st[(size_t)q] & ST_UNCERTIFIED)) { ++q; continue; }
+        if (!(st[q] & ST_UNCERTIFIED)) { ++q; continue; }
         int64_t e = q + 1;
-        while (e < nq && e - q < 16 && (st[(size_t)e] & ST_UNCERTIFIED)) ++e;
+        while (e < nq && e - q < 16 && (st[e] & ST_UNCERTIFIED)) ++e;
         XS_TRY(run_exact(ix, q32 + q * ix->d_pad, e - q, k, self_base >= 0 ? self_base + q : -1, out_idx + q * k,
                          out_score ? out_score + q * k : nullptr, nullptr, &launches));
         reruns += e - q;
@@ -515,13 +515,6 @@ static int finish_to_host(xs_index* ix, float* q32, int64_t nq, int k, int64_t s
         CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
     }
     CU_TRY(cudaStreamSynchronize(ix->stream));
-    if (ix->dbg.p && getenv("XS_FIN_DEBUG")) {
-        long long h[16];
-        if (cudaMemcpy(h, ix->dbg.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {
-            fprintf(stderr, "finalise CTA0 phases (cycles): count/scan %lld, gather %lld, select %lld, collect %lld, rescore %lld, self+sort %lld, emit %lld | pooled %lld cand %lld\n",
-                    h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[14], h[15]);
-        }
-    }
     if (coarse) {
         const int* st = ix->h_status.as<int>() + 1;
         ix->stats.n_candidates = ix->h_status.as<int>()[0];

@@ -208,9 +208,6 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     const int64_t q = blockIdx.x;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool staged = a.P <= FIN_MAX_LISTS;           // offsets fit -> try the shared-memory gather
-    int dbg_i = 0;
-#define FIN_STAMP() do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[dbg_i] = clock64(); ++dbg_i; } while (0)
-    FIN_STAMP();
 
     if (threadIdx.x == 0) { sh_ncand = 0; sh_flag = 0; sh_selfkey = 0; }
     if (!SPLIT)
@@ -234,9 +231,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     }
     const uint32_t max_thr = sh_flag;
     const bool in_smem = staged && total <= (uint32_t)item_cap;
-    FIN_STAMP();
     if (in_smem) gather_pool(a.pool_items, q, a.P, a.cap, offs, (int)total, items);
-    FIN_STAMP();
 
     auto each = [&](auto fn) {
         if (in_smem) {
@@ -273,7 +268,6 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         }
     }
     __syncthreads();
-    FIN_STAMP();
     each([&](uint64_t it, bool valid) {
         bool take = valid && it >= cut;
         uint32_t m = __ballot_sync(0xffffffffu, take);
@@ -284,7 +278,6 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         if (take && pos < (uint32_t)cand_max) cand[pos] = it;
     });
     __syncthreads();
-    FIN_STAMP();
     const uint32_t found = sh_ncand;
     const int ncand = (int)min(found, (uint32_t)cand_max);
     // certificate: nothing that could belong to the exact top-k was dropped upstream
@@ -310,7 +303,6 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         }
     }
     __syncthreads();
-    FIN_STAMP();
     if (a.self_base >= 0) {   // self-kNN: the query's own row ranks first whatever the ties
         const uint32_t self_row = (uint32_t)(a.self_base + q);
         for (int c = threadIdx.x; c < ncand; c += blockDim.x)
@@ -328,7 +320,6 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     if (m < 2) m = 2;
     for (int c = ncand + threadIdx.x; c < m; c += blockDim.x) cand[c] = 0ull;
     block_sort_desc(cand, m);
-    FIN_STAMP();
 
     const int kout = min(a.k, ncand);
     for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
@@ -344,8 +335,6 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         a.out_idx[q * a.out_pitch + r] = id;
         if (a.out_score) a.out_score[q * a.out_pitch + r] = sc;
     }
-    FIN_STAMP();
-    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { a.dbg[14] = total; a.dbg[15] = ncand; }
     if (threadIdx.x == 0) {
         if (a.status) a.status[q] = uncertified ? ST_UNCERTIFIED : 0;
         if (a.n_cand) atomicAdd(a.n_cand, ncand);

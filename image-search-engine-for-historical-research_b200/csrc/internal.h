@@ -94,7 +94,6 @@ struct FinaliseArgs {
     int64_t self_base;          // >= 0: query q is database row self_base + q and must rank first
     int64_t* out_idx; float* out_score; int* status; int* n_cand;
     int64_t out_pitch;          // elements between consecutive queries in out_idx / out_score
-    long long* dbg;             // optional: 16 clock64 stamps of CTA 0 (phase timeline, XS_FIN_DEBUG=1)
     void* work;                 // optional: finalise_work_bytes(nq, k) of scratch -> enables the 3-kernel split for small batches
     uint64_t* w_cand; int* w_ncand; int* w_flag;   // carved out of `work` by launch_finalise
 };

@@ -263,3 +263,82 @@ def test_qge1_aqe_second_pass(pkg, synth, oracle, golden):
     qe_gpu, _ = pkg.feature_enhancement(1, 3, first, qvecs, vecs, 4.0, K=5)
     np.testing.assert_allclose(qe_gpu, qe, rtol=2e-6, atol=1e-7)
     pkg.clear_index_cache()
+
+
+@pytest.mark.parametrize("k", [1000, 2048, 3000])
+def test_large_k(pkg, synth, oracle, k):
+    """k up to 2048 stays on the coarse paths (larger pools); above that the dispatch goes exact."""
+    v, q = synth.gaussian(20000, 5, d=256)
+    rid, rs = oracle.topk_ip(v, q, k)
+    s64 = oracle.scores_f64(v, q)
+    with pkg.ExactIndex(v.T) as ix:
+        ids, sims = ix.search(q.T, k)
+        assert ix.stats()["path"] == (2 if k <= 2048 else 3)
+        _check_lists(oracle, ids, rid, s64, f"k={k}")
+        np.testing.assert_allclose(sims, rs, rtol=1e-5, atol=1e-7)
+        if k <= 2048:
+            i1, s1 = ix.search(q.T[:1], k)          # batch 1 -> scan path with the same k
+            assert ix.stats()["path"] == 1
+            _check_lists(oracle, i1, rid[:1], s64, f"scan k={k}")
+
+
+def test_crowded_scores_fall_back_to_exact(pkg, synth, oracle):
+    """Tight clusters: hundreds of rows within the bf16 error band of the k-th score.  Queries the
+    coarse pass cannot certify are re-run on the exact path -- results stay exact, reruns are counted."""
+    v, q, _ = synth.clustered(20000, 16, d=256, n_clusters=10, noise=0.02)
+    rid, rs = oracle.topk_ip(v, q, 100)
+    s64 = oracle.scores_f64(v, q)
+    with pkg.ExactIndex(v.T) as ix:
+        for path in (2, 1):
+            ix.set_param("force_path", path)
+            ids, sims = ix.search(q.T, 100)
+            st = ix.stats()
+            _check_lists(oracle, ids, rid, s64, f"crowded path {path}")
+            np.testing.assert_allclose(sims, rs, rtol=1e-5, atol=1e-7)
+            assert st["n_exact_rerun"] > 0, st       # this family is built to defeat the coarse filter
+
+
+def test_threads_share_one_index(pkg, synth, oracle):
+    """Flask serves requests from threads (online.py:163): concurrent searches on one index."""
+    import threading
+    v, q = synth.gaussian(6000, 32, d=128)
+    rid, _ = oracle.topk_ip(v, q, 20)
+    s64 = oracle.scores_f64(v, q)
+    out = {}
+    with pkg.ExactIndex(v.T) as ix:
+        def work(t):
+            for rep in range(5):
+                sl = slice(t * 8, t * 8 + 8) if rep % 2 == 0 else slice(t * 8, t * 8 + 1)
+                ids, _ = ix.search(q.T[sl], 20)
+                out[(t, rep)] = (sl, ids)
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    assert len(out) == 20
+    for (t, rep), (sl, ids) in out.items():
+        _check_lists(oracle, ids, rid[sl], s64[:, sl], f"thread {t} rep {rep}")
+
+
+def test_argument_errors_and_dtypes(pkg, synth, oracle):
+    v, q = synth.gaussian(500, 4, d=64)
+    rid, _ = oracle.topk_ip(v, q, 5)
+    with pkg.ExactIndex(v.T.astype(np.float16)) as ix:          # fp16 in -> cast to fp32 on the way
+        ids, _ = ix.search(q.T.astype(np.float16), 5)
+        assert ids.shape == (4, 5)
+    with pkg.ExactIndex(v.T) as ix:
+        e_ids, e_sims = ix.search(np.empty((0, 64), np.float32), 5)
+        assert e_ids.shape == (0, 5) and e_sims.shape == (0, 5)
+        for bad_k in (0, -1, 501):
+            with pytest.raises(ValueError):
+                ix.search(q.T, bad_k)
+        with pytest.raises(ValueError):
+            ix.search(q.T[0], 5)                                   # 1-D
+        with pytest.raises(ValueError):
+            ix.set_param("no_such_knob", 1)
+        ids, _ = ix.search(q.T.astype(np.float64), 5)              # fp64 queries
+        np.testing.assert_array_equal(ids, rid)
+        ix.close()
+        with pytest.raises((ValueError, RuntimeError)):
+            ix.search(q.T, 5)                                      # closed index
+    with pytest.raises(ValueError):
+        pkg.matching_L2(600, v.T, q.T)                             # K > N
