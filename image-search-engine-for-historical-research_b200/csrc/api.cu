@@ -73,7 +73,8 @@ struct xs_index {
     // workspace
     Buf fin_work, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                // the index's own stream (host API, build)
+    cudaStream_t cur = nullptr;                   // stream of the call in progress (the caller's for *_dev entry points)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     std::mutex mu;
@@ -315,19 +316,19 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
     XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
     for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
         const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
-        CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->stream));
-        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->stream);
+        CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
+        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
         *launches += (c + 3) / 4;
-        if (self_base >= 0) { boost_self_kernel<<<(c + 127) / 128, 128, 0, ix->stream>>>(ix->scores.as<float>(), ix->n, c, self_base + q0); ++*launches; }
+        if (self_base >= 0) { boost_self_kernel<<<(c + 127) / 128, 128, 0, ix->cur>>>(ix->scores.as<float>(), ix->n, c, self_base + q0); ++*launches; }
         launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, ix->ghist.as<uint32_t>(), true, ix->pool_items.as<uint64_t>(),
-                               ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
+                               ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->cur);
         FinaliseArgs fa{};
         fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
         fa.P = P; fa.cap = cap; fa.db32 = ix->db32; fa.q32 = q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad; fa.eps = nullptr;
         fa.k = k; fa.exact = true; fa.id_offset = ix->id_offset; fa.self_base = self_base >= 0 ? self_base + q0 : -1;
         fa.out_idx = out_idx + q0 * k; fa.out_score = out_score ? out_score + q0 * k : nullptr;
         fa.status = status ? status + q0 : nullptr; fa.n_cand = nullptr; fa.out_pitch = k;
-        launch_finalise(fa, c, ix->stream);
+        launch_finalise(fa, c, ix->cur);
         *launches += 2;
     }
     CU_TRY(cudaGetLastError());
@@ -339,14 +340,14 @@ static int prepare_queries(xs_index* ix, const CoreArgs& a, __nv_bfloat16* q16, 
     if (!a.prep) return XS_OK;
     const int64_t nq_pad = round_up(a.nq, GEMM_BM);
     if (a.raw && launch_prep_queries_fused(a.raw, a.q32, q16, a.nq, nq_pad, ix->d, ix->d_pad, a.prep_renorm, ix->dstats,
-                                           ix->eps_sigmas, ix->eps.as<float>(), ix->stream)) { ++*launches; return XS_OK; }
-    if (a.raw) { launch_layout_rows(a.raw, XS_F32, false, ix->d, a.nq, ix->d, ix->d_pad, a.q32, ix->stream); ++*launches; }
+                                           ix->eps_sigmas, ix->eps.as<float>(), ix->cur)) { ++*launches; return XS_OK; }
+    if (a.raw) { launch_layout_rows(a.raw, XS_F32, false, ix->d, a.nq, ix->d, ix->d_pad, a.q32, ix->cur); ++*launches; }
     if (q16 && nq_pad > a.nq) {
         const int64_t cnt = (nq_pad - a.nq) * ix->d_pad;
-        zero_rows_bf16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->stream>>>(q16 + a.nq * ix->d_pad, cnt);
+        zero_rows_bf16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->cur>>>(q16 + a.nq * ix->d_pad, cnt);
         ++*launches;
     }
-    launch_prep_queries(a.q32, q16, a.nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->stream);
+    launch_prep_queries(a.q32, q16, a.nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->cur);
     ++*launches;
     return XS_OK;
 }
@@ -358,15 +359,15 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
     ix->stats.n_queries = nq; ix->stats.path = a.path;
     XS_TRY(ix->eps.ensure((size_t)nq * sizeof(float)));
     XS_TRY(ix->ncand.ensure(sizeof(int)));
-    CU_TRY(cudaMemsetAsync(ix->ncand.p, 0, sizeof(int), ix->stream));
-    CU_TRY(cudaEventRecord(ix->ev[0], ix->stream));
+    CU_TRY(cudaMemsetAsync(ix->ncand.p, 0, sizeof(int), ix->cur));
+    CU_TRY(cudaEventRecord(ix->ev[0], ix->cur));
     ix->ev_valid = true;
 
     if (a.path == PATH_EXACT) {
         XS_TRY(prepare_queries(ix, a, nullptr, &launches));
-        CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
+        CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
         XS_TRY(run_exact(ix, a.q32, nq, k, a.self_base, a.out_idx, a.out_score, a.status, &launches));
-        CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
+        CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
     } else if (a.path == PATH_SCAN) {
         XS_TRY(prepare_queries(ix, a, nullptr, &launches));
         const int P = (int)((ix->n + SLICE_ROWS - 1) / SLICE_ROWS);
@@ -380,13 +381,13 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
         for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
             const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
-            CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->stream));
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
-            launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->stream);
+            CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
+            launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
             launches += (c + 1) / 2;
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), false, ix->pool_items.as<uint64_t>(),
-                                   ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->stream);
+                                   ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->cur);
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
             fa.P = P; fa.cap = cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad; fa.eps = ix->eps.as<float>() + q0;
@@ -395,7 +396,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
             fa.work = ix->fin_work.p;
-            launch_finalise(fa, c, ix->stream);
+            launch_finalise(fa, c, ix->cur);
             launches += 1 + finalise_launches(fa, c);
         }
     } else {
@@ -430,24 +431,24 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 XS_TRY(ix->pool_thr.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
                 cudaError_t es = launch_gemm_topk(*ta, ix->tmap_db_b, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                                   ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
-                                                  (int)row0, nullptr, ix->stream);
+                                                  (int)row0, nullptr, ix->cur);
                 if (es != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk (sample) launch failed: %s", cudaGetErrorString(es));
                 launch_sample_threshold(ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), sp.splits, sp.cap, k,
-                                        ix->eps.as<float>() + q0, ix->thr0.as<float>(), c, ix->stream);
+                                        ix->eps.as<float>() + q0, ix->thr0.as<float>(), c, ix->cur);
                 thr0 = ix->thr0.as<float>();
                 launches += 2;
             } else if (ix->debug_thr != 0.f) {
                 std::vector<float> h((size_t)c, ix->debug_thr);
-                CU_TRY(cudaMemcpyAsync(ix->thr0.p, h.data(), (size_t)c * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-                CU_TRY(cudaStreamSynchronize(ix->stream));
+                CU_TRY(cudaMemcpyAsync(ix->thr0.p, h.data(), (size_t)c * sizeof(float), cudaMemcpyHostToDevice, ix->cur));
+                CU_TRY(cudaStreamSynchronize(ix->cur));
                 thr0 = ix->thr0.as<float>();
             }
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->stream));
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
             cudaError_t e = launch_gemm_topk(*ta, plan.pair ? ix->tmap_db_a : ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
-                                             (int)row0, thr0, ix->stream);
+                                             (int)row0, thr0, ix->cur);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->stream));
+            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
             fa.P = plan.splits; fa.cap = plan.cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad;
@@ -457,11 +458,11 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
             fa.work = ix->fin_work.p;
-            launch_finalise(fa, c, ix->stream);
+            launch_finalise(fa, c, ix->cur);
             launches += 1 + finalise_launches(fa, c);
         }
     }
-    CU_TRY(cudaEventRecord(ix->ev[3], ix->stream));
+    CU_TRY(cudaEventRecord(ix->ev[3], ix->cur));
     CU_TRY(cudaGetLastError());
     ix->stats.gpu_launches = launches;
     return XS_OK;
@@ -478,9 +479,9 @@ static int choose_path(const xs_index* ix, int64_t nq, int k) {
 // synchronisation), re-run uncertified queries exactly into the caller's device buffers.
 static int rerun_uncertified(xs_index* ix, float* q32, int64_t nq, int k, int64_t self_base, int64_t* out_idx, float* out_score, int* status_dev) {
     XS_TRY(ix->h_status.ensure((size_t)(nq + 1) * sizeof(int)));
-    CU_TRY(cudaMemcpyAsync(ix->h_status.as<int>() + 1, status_dev, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
-    CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
-    CU_TRY(cudaStreamSynchronize(ix->stream));
+    CU_TRY(cudaMemcpyAsync(ix->h_status.as<int>() + 1, status_dev, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->cur));
+    CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->cur));
+    CU_TRY(cudaStreamSynchronize(ix->cur));
     const int* st = ix->h_status.as<int>() + 1;
     ix->stats.n_candidates = ix->h_status.as<int>()[0];
     int launches = 0;
@@ -554,12 +555,9 @@ extern "C" int xs_search_dev(xs_index* ix, const float* q_dev, int64_t nq, int r
     if (!q_dev || !out_idx_dev) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(ix->mu);
     CU_TRY(cudaSetDevice(ix->device));
-    cudaStream_t user = static_cast<cudaStream_t>(stream);
-    // order our stream after the caller's pending work, and the caller's stream after ours
-    cudaEvent_t ev;
-    CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU_TRY(cudaEventRecord(ev, user));
-    CU_TRY(cudaStreamWaitEvent(ix->stream, ev, 0));
+    // everything is enqueued on the caller's stream: no cross-stream hops on the hot path.  The workspace is
+    // reused from call to call, so one index serves one stream at a time.
+    ix->cur = static_cast<cudaStream_t>(stream);
     XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
     XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
     CoreArgs a{};
@@ -571,9 +569,6 @@ extern "C" int xs_search_dev(xs_index* ix, const float* q_dev, int64_t nq, int r
     int rc = search_core(ix, a);
     if (rc == XS_OK && !out_status_dev && a.path != PATH_EXACT)
         rc = rerun_uncertified(ix, a.q32, nq, k, -1, out_idx_dev, out_score_dev, a.status);
-    cudaEventRecord(ev, ix->stream);
-    cudaStreamWaitEvent(user, ev, 0);
-    cudaEventDestroy(ev);
     return rc;
 }
 
@@ -585,6 +580,7 @@ extern "C" int xs_search(xs_index* ix, const void* q, int dtype, int64_t nq, int
     XS_TRY(check_layout(dtype, nq, ix->d, stride_row, stride_col, &colmajor));
     std::lock_guard<std::mutex> lk(ix->mu);
     CU_TRY(cudaSetDevice(ix->device));
+    ix->cur = ix->stream;
     const size_t es = dtype == XS_F64 ? 8 : 4;
     XS_TRY(ix->q_raw.ensure((size_t)nq * ix->d * es));
     XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
@@ -611,6 +607,7 @@ extern "C" int xs_aqe_search(xs_index* ix, const int64_t* top_ids, int64_t nq, i
     if (kq < 1 || kq > 64) return fail(XS_ERR_ARG, "kq=%d out of range [1, 64]", kq);
     std::lock_guard<std::mutex> lk(ix->mu);
     CU_TRY(cudaSetDevice(ix->device));
+    ix->cur = ix->stream;
     XS_TRY(ix->aqe_ids.ensure((size_t)nq * kq * sizeof(int64_t)));
     XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
     XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
@@ -641,6 +638,7 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
     if (!out_idx) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(ix->mu);
     CU_TRY(cudaSetDevice(ix->device));
+    ix->cur = ix->stream;
     const int64_t batch = 8192;
     XS_TRY(ix->status.ensure((size_t)batch * sizeof(int)));
     XS_TRY(ix->out_idx.ensure((size_t)batch * k * sizeof(int64_t)));
@@ -673,6 +671,7 @@ extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, i
     XS_TRY(check_layout(dtype, nq, ix->d, stride_row, stride_col, &colmajor));
     std::lock_guard<std::mutex> lk(ix->mu);
     CU_TRY(cudaSetDevice(ix->device));
+    ix->cur = ix->stream;
     const size_t es = dtype == XS_F64 ? 8 : 4;
     const int64_t n = ix->n;
     const int64_t col_block = 128;                     // queries per device-resident output block
