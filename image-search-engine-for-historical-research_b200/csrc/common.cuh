@@ -73,4 +73,21 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start (and run its prologue)
+// while its predecessor in the stream is still finishing; pdl_wait() blocks until the predecessor has
+// completed and its writes are visible.  EVERY kernel of a chain calls it before its first global access,
+// so completion order along the chain is preserved.  Without the launch attribute it is a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace xs

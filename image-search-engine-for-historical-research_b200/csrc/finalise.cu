@@ -205,6 +205,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     __shared__ uint32_t misc[2];
     __shared__ int scan_scratch[33];
     __shared__ uint32_t sh_ncand, sh_flag, sh_selfkey;
+    pdl_wait();
     const int64_t q = blockIdx.x;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool staged = a.P <= FIN_MAX_LISTS;           // offsets fit -> try the shared-memory gather
@@ -352,6 +353,7 @@ constexpr int RS_WARPS = 8;
 __global__ void __launch_bounds__(RS_WARPS * 32)
 finalise_rescore_kernel(FinaliseArgs a, int cand_max) {
     extern __shared__ float rs_rows[];                  // [RS_WARPS][d_pad]
+    pdl_wait();
     const int64_t q = blockIdx.x;
     const int ncand = a.w_ncand[q];
     uint64_t* cand = a.w_cand + q * cand_max;
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(256)
 finalise_emit_kernel(FinaliseArgs a, int cand_max) {
     extern __shared__ uint64_t emit_cand[];             // [cand_max]
     __shared__ uint32_t sh_selfkey;
+    pdl_wait();
     const int64_t q = blockIdx.x;
     const int ncand = a.w_ncand[q];
     const uint64_t* src = a.w_cand + q * cand_max;
@@ -455,16 +458,16 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     const size_t smem = fixed + (size_t)item_cap * sizeof(uint64_t);
     if (split) {
         cudaFuncSetAttribute(finalise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
-        finalise_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max, item_cap);
+        launch_pdl(finalise_kernel<true>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
         const size_t rsm = (size_t)RS_WARPS * a.d_pad * sizeof(float);
         if (rsm > 48 * 1024) cudaFuncSetAttribute(finalise_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-        finalise_rescore_kernel<<<dim3((unsigned)nq, RS_SPLIT), RS_WARPS * 32, rsm, st>>>(a, cand_max);
+        launch_pdl(finalise_rescore_kernel, dim3((unsigned)nq, RS_SPLIT), dim3(RS_WARPS * 32), rsm, st, a, cand_max);
         const size_t esm = (size_t)cand_max * sizeof(uint64_t);
         if (esm > 48 * 1024) cudaFuncSetAttribute(finalise_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm);
-        finalise_emit_kernel<<<(unsigned)nq, 256, esm, st>>>(a, cand_max);
+        launch_pdl(finalise_emit_kernel, dim3((unsigned)nq), dim3(256), esm, st, a, cand_max);
     } else {
         cudaFuncSetAttribute(finalise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
-        finalise_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, st>>>(a, cand_max, item_cap);
+        launch_pdl(finalise_kernel<false>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
     }
 }
 int finalise_launches(const FinaliseArgs& a, int64_t nq) { return (!a.exact && a.work && nq <= FIN_SPLIT_MAX_Q) ? 3 : 1; }
@@ -477,6 +480,7 @@ sample_threshold_kernel(const uint64_t* __restrict__ pool_items, const int* __re
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[2];
     __shared__ uint32_t sh_total;
+    pdl_wait();
     const int64_t q = blockIdx.x;
     if (threadIdx.x == 0) sh_total = 0;
     __syncthreads();
@@ -510,7 +514,7 @@ sample_threshold_kernel(const uint64_t* __restrict__ pool_items, const int* __re
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
-    sample_threshold_kernel<<<(unsigned)nq, 1024, (size_t)8 * P * sizeof(uint64_t), st>>>(pool_items, pool_count, P, cap, k, eps, thr0);
+    launch_pdl(sample_threshold_kernel, dim3((unsigned)nq), dim3(1024), (size_t)8 * P * sizeof(uint64_t), st, pool_items, pool_count, P, cap, k, eps, thr0);
 }
 
 // ---- multi-GPU merge -------------------------------------------------------------------------------

@@ -190,6 +190,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();              // the peer's barriers exist before anything signals them
     tc_fence_after();
+    pdl_wait();                                          // barriers, TMEM and descriptors are set up; now the predecessor's data
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
@@ -452,13 +453,15 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = GEMM_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = plan.pair ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     const int k_blocks = d_pad / GEMM_BK;
     return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, k_blocks,
                               a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, eps, thr0,

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256, 2)
 scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32, int64_t n, int d_pad,
                    float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist) {
     extern __shared__ float qs[];                       // [QB][d_pad] query rows | [QB][HIST_BINS] score-key histogram
+    pdl_wait();
     uint32_t* sh = reinterpret_cast<uint32_t*>(qs + QB * d_pad);
     for (int i = threadIdx.x; i < QB * d_pad; i += blockDim.x) qs[i] = q32[i];
     for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x) sh[i] = 0;
@@ -101,10 +102,10 @@ void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int
         float* s = scores + (int64_t)q0 * score_pitch;
         uint32_t* h = ghist + (size_t)q0 * HIST_BINS;
         if (left >= 2) {
-            scan_scores_kernel<2, 4><<<grid, 256, 2 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
+            launch_pdl(scan_scores_kernel<2, 4>, dim3(grid), dim3(256), 2 * per_q, st, db, q, n, d_pad, s, score_pitch, h);
             q0 += 2;
         } else {
-            scan_scores_kernel<1, 4><<<grid, 256, per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
+            launch_pdl(scan_scores_kernel<1, 4>, dim3(grid), dim3(256), per_q, st, db, q, n, d_pad, s, score_pitch, h);
             q0 += 1;
         }
     }
@@ -209,6 +210,7 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
     __shared__ uint32_t misc[2];
     __shared__ uint32_t wsum[8];
     __shared__ uint32_t n_out, edge_key;
+    pdl_wait();
     const int p = blockIdx.x;
     const int64_t q = blockIdx.y;
     const int64_t row0 = (int64_t)p * SLICE_ROWS;
@@ -283,8 +285,8 @@ void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, in
                             const float* eps, const uint32_t* ghist, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st) {
     dim3 grid((unsigned)P, (unsigned)nq);
-    scores_to_pools_kernel<<<grid, 256, 0, st>>>(scores, score_pitch, n, k, eps, ghist, exact ? 1 : 0,
-                                                 pool_items, pool_count, pool_thr, P, cap);
+    launch_pdl(scores_to_pools_kernel, grid, dim3(256), 0, st, scores, score_pitch, n, k, eps, ghist, exact ? 1 : 0,
+               pool_items, pool_count, pool_thr, P, cap);
 }
 
 }  // namespace xs
