@@ -69,7 +69,7 @@ struct xs_index {
     __nv_bfloat16* db16 = nullptr; float* db32 = nullptr; DevStats* dstats = nullptr;
     CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
     // tunables
-    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; float debug_thr = 0.f;
+    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0; float debug_thr = 0.f;
     // workspace
     Buf fin_work, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
@@ -255,6 +255,7 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "gemm_splits")) ix->gemm_splits = (int)value;
     else if (!strcmp(name, "sample_pass")) ix->sample_pass = (int)value;
     else if (!strcmp(name, "pair_mode")) ix->pair_mode = (int)value;
+    else if (!strcmp(name, "timing")) ix->timing = (int)value;
     else if (!strcmp(name, "debug_thr")) ix->debug_thr = (float)value;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
@@ -360,14 +361,15 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
     XS_TRY(ix->eps.ensure((size_t)nq * sizeof(float)));
     XS_TRY(ix->ncand.ensure(sizeof(int)));
     CU_TRY(cudaMemsetAsync(ix->ncand.p, 0, sizeof(int), ix->cur));
-    CU_TRY(cudaEventRecord(ix->ev[0], ix->cur));
-    ix->ev_valid = true;
+    const bool timing = ix->timing != 0;            // CUDA events around the coarse kernel / the call (off: nothing between the launches)
+    if (timing) CU_TRY(cudaEventRecord(ix->ev[0], ix->cur));
+    ix->ev_valid = timing;
 
     if (a.path == PATH_EXACT) {
         XS_TRY(prepare_queries(ix, a, nullptr, &launches));
-        CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
+        if (timing) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
         XS_TRY(run_exact(ix, a.q32, nq, k, a.self_base, a.out_idx, a.out_score, a.status, &launches));
-        CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
+        if (timing) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
     } else if (a.path == PATH_SCAN) {
         XS_TRY(prepare_queries(ix, a, nullptr, &launches));
         const int P = (int)((ix->n + SLICE_ROWS - 1) / SLICE_ROWS);
@@ -382,10 +384,10 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
             const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
             CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
+            if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
             launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
             launches += (c + 1) / 2;
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
+            if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), false, ix->pool_items.as<uint64_t>(),
                                    ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->cur);
             FinaliseArgs fa{};
@@ -443,12 +445,12 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 CU_TRY(cudaStreamSynchronize(ix->cur));
                 thr0 = ix->thr0.as<float>();
             }
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
+            if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
             cudaError_t e = launch_gemm_topk(*ta, plan.pair ? ix->tmap_db_a : ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                              (int)row0, thr0, ix->cur);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));
-            if (q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
+            if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
             fa.P = plan.splits; fa.cap = plan.cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad;
@@ -462,7 +464,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             launches += 1 + finalise_launches(fa, c);
         }
     }
-    CU_TRY(cudaEventRecord(ix->ev[3], ix->cur));
+    if (timing) CU_TRY(cudaEventRecord(ix->ev[3], ix->cur));
     CU_TRY(cudaGetLastError());
     ix->stats.gpu_launches = launches;
     return XS_OK;

@@ -165,6 +165,9 @@ XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const voi
  *   "scan_max_q"   int    largest batch served by the batch-1 HBM scan kernel      (1)
  *   "force_path"   int    0 = auto, 1 = scan, 2 = tcgen05 GEMM, 3 = exact fp32      (0)
  *   "gemm_splits"  int    database splits per query tile, 0 = auto                 (0)
+ *   "timing"       int    1 = record CUDA events so xs_index_stats reports ms_coarse/ms_total (0)
+ *   "pair_mode"    int    1 = CTA-pair (cta_group::2) GEMM shape for batches > 128 queries   (1)
+ *   "sample_pass"  int    1 = threshold bootstrap pass before the GEMM                    (1)
  */
 XS_API int xs_set_param(xs_index* index, const char* name, double value);
 
