@@ -28,6 +28,7 @@ status = torch.zeros((max(Q, 70),), dtype=torch.int32, device=dev)
 def run(label, nq, reps=10, **params):
     for k_, v_ in params.items():
         ix.set_param(k_, v_)
+    ix.set_param("timing", 1)
     coarse, total = [], []
     for i in range(reps + 2):
         ix.search_device(queries.data_ptr(), nq, K, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
@@ -35,6 +36,7 @@ def run(label, nq, reps=10, **params):
         if i >= 2:
             coarse.append(st["ms_coarse"]); total.append(st["ms_total"])
     torch.cuda.synchronize()
+    ix.set_param("timing", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -64,9 +66,11 @@ if len(sys.argv) > 3:
         ib = torch.empty((nq_big, K), dtype=torch.int64, device=dev)
         sb = torch.empty((nq_big, K), dtype=torch.float32, device=dev)
         stb = torch.zeros((nq_big,), dtype=torch.int32, device=dev)
+        ix.set_param("timing", 1)
         for _ in range(2):
             ix.search_device(qb.data_ptr(), nq_big, K, ib.data_ptr(), sb.data_ptr(), status_ptr=stb.data_ptr())
         st = ix.stats()
+        ix.set_param("timing", 0)
         tf = 2.0 * N * 2048 * nq_big / (st["ms_coarse"] * 1e-3) / 1e12
         print(f"gemm nq={nq_big}: coarse {st['ms_coarse']:.3f} ms = {tf:.0f} TFLOP/s (bf16 dense), call {st['ms_total']:.3f} ms, "
               f"uncert {int(stb.sum())}, launches {st['gpu_launches']}", flush=True)
