@@ -22,8 +22,14 @@ ix = pkg.ExactIndex.from_device(rows.data_ptr(), N, 2048, 0)
 ids = torch.empty((70, 100), dtype=torch.int64, device=dev)
 sims = torch.empty((70, 100), dtype=torch.float32, device=dev)
 status = torch.zeros((70,), dtype=torch.int32, device=dev)
-for nq in (70, 1):
+big = bench.synth_rows_device(torch, 1024, 2048, dev, 2)
+ids_b = torch.empty((1024, 100), dtype=torch.int64, device=dev)
+sims_b = torch.empty((1024, 100), dtype=torch.float32, device=dev)
+status_b = torch.zeros((1024,), dtype=torch.int32, device=dev)
+ix.set_param("timing", 1)
+for nq in (70, 1, 1024):                      # GEMM path (HBM-bound), scan path, CTA-pair GEMM (tensor-bound)
+    q, i, s, st = (big, ids_b, sims_b, status_b) if nq == 1024 else (queries, ids, sims, status)
     for _ in range(steps):
-        ix.search_device(queries.data_ptr(), nq, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+        ix.search_device(q.data_ptr(), nq, 100, i.data_ptr(), s.data_ptr(), status_ptr=st.data_ptr())
     torch.cuda.synchronize()
-    print(nq, ix.stats(), int(status[:nq].sum()))
+    print(nq, ix.stats(), int(st[:nq].sum()))
