@@ -71,7 +71,7 @@ struct xs_index {
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0; float debug_thr = 0.f;
     // workspace
-    Buf fin_work, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     cudaStream_t stream = nullptr;                // the index's own stream (host API, build)
     cudaStream_t cur = nullptr;                   // stream of the call in progress (the caller's for *_dev entry points)
@@ -155,7 +155,7 @@ static void index_free(xs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->fin_work, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
@@ -336,6 +336,15 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
     return XS_OK;
 }
 
+// Completion counters of the split finalise: zeroed when (re)allocated, the kernel resets them after use.
+static int ensure_tickets(xs_index* ix, int64_t nq) {
+    const size_t need = (size_t)nq * sizeof(int);
+    if (need <= ix->fin_ticket.cap) return XS_OK;
+    XS_TRY(ix->fin_ticket.ensure(need));
+    CU_TRY(cudaMemsetAsync(ix->fin_ticket.p, 0, ix->fin_ticket.cap, ix->cur));
+    return XS_OK;
+}
+
 // Query preparation: one fused kernel when the raw layout allows it, else layout -> (zero pad) -> prep.
 static int prepare_queries(xs_index* ix, const CoreArgs& a, __nv_bfloat16* q16, int* launches) {
     if (!a.prep) return XS_OK;
@@ -397,7 +406,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
-            fa.work = ix->fin_work.p;
+            XS_TRY(ensure_tickets(ix, c));
+            fa.work = ix->fin_work.p; fa.ticket = ix->fin_ticket.as<int>();
             launch_finalise(fa, c, ix->cur);
             launches += 1 + finalise_launches(fa, c);
         }
@@ -459,7 +469,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
             fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
-            fa.work = ix->fin_work.p;
+            XS_TRY(ensure_tickets(ix, c));
+            fa.work = ix->fin_work.p; fa.ticket = ix->fin_ticket.as<int>();
             launch_finalise(fa, c, ix->cur);
             launches += 1 + finalise_launches(fa, c);
         }

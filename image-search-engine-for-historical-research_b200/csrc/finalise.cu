@@ -343,16 +343,19 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
 }
 
 // ---- split pipeline: rescore on every SM, then sort + emit ---------------------------------------------
-constexpr int RS_SPLIT = 8;                  // CTAs per query in the rescoring kernel
+constexpr int RS_SPLIT = 16;                 // CTAs per query in the rescoring kernel
 constexpr int RS_WARPS = 8;
 
 // grid (nq, RS_SPLIT): warp w of CTA (q, j) rescores candidates j*RS_WARPS + w, + RS_SPLIT*RS_WARPS, ...
 // The row is staged with cp.async (16 B per lane and step, all steps issued back to back) so the whole
 // 8 KB row is in flight at once -- with register loads ptxas interleaves each load with its use and a
 // warp never has more than ~3 outstanding.  24 resident warps per SM -> ~190 KB in flight per SM.
+// The LAST of a query's RS_SPLIT CTAs to finish (atomic ticket) sorts the rescored candidates, applies
+// the self-first rule and emits the first k -- no separate launch.
 __global__ void __launch_bounds__(RS_WARPS * 32)
-finalise_rescore_kernel(FinaliseArgs a, int cand_max) {
-    extern __shared__ float rs_rows[];                  // [RS_WARPS][d_pad]
+finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
+    extern __shared__ float rs_rows[];                  // [RS_WARPS][d_pad] row staging; reused as [cand_max] items by the emitter
+    __shared__ uint32_t sh_selfkey, sh_last;
     pdl_wait();
     const int64_t q = blockIdx.x;
     const int ncand = a.w_ncand[q];
@@ -380,41 +383,43 @@ finalise_rescore_kernel(FinaliseArgs a, int cand_max) {
         if (lane == 0) cand[c] = make_item((float)acc, row);
         __syncwarp();
     }
-}
-
-// grid nq: sort the rescored candidates, apply the self-first rule, emit the first k
-__global__ void __launch_bounds__(256)
-finalise_emit_kernel(FinaliseArgs a, int cand_max) {
-    extern __shared__ uint64_t emit_cand[];             // [cand_max]
-    __shared__ uint32_t sh_selfkey;
-    pdl_wait();
-    const int64_t q = blockIdx.x;
-    const int ncand = a.w_ncand[q];
-    const uint64_t* src = a.w_cand + q * cand_max;
+    // ---- completion ticket ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(&a.w_ticket[q], 1);
+        sh_last = (t == RS_SPLIT - 1) ? 1u : 0u;
+        if (sh_last) a.w_ticket[q] = 0;                 // ready for the next call
+        sh_selfkey = 0;
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    // ---- sort + emit (this CTA only) ----
+    uint64_t* items = reinterpret_cast<uint64_t*>(rs_rows);
     int m = 1;
     while (m < ncand) m <<= 1;
     if (m < 2) m = 2;
-    for (int c = threadIdx.x; c < m; c += blockDim.x) emit_cand[c] = (c < ncand) ? src[c] : 0ull;
-    if (threadIdx.x == 0) sh_selfkey = 0;
+    for (int c = threadIdx.x; c < m; c += blockDim.x) items[c] = (c < ncand) ? __ldcg(cand + c) : 0ull;
     __syncthreads();
     if (a.self_base >= 0) {
         const uint32_t self_row = (uint32_t)(a.self_base + q);
         for (int c = threadIdx.x; c < ncand; c += blockDim.x)
-            if (item_row(emit_cand[c]) == self_row)
-                emit_cand[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
+            if (item_row(items[c]) == self_row)
+                items[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
         if (threadIdx.x < 32) {
             const float* vrow = a.db32 + (int64_t)self_row * a.d_pad;
-            const double s = exact_dot1(vrow, a.q32 + q * a.d_pad, a.d_pad);
+            const double s = exact_dot1(vrow, qrow, a.d_pad);
             if (threadIdx.x == 0) sh_selfkey = score_key((float)s);
         }
     }
-    block_sort_desc(emit_cand, m);
+    block_sort_desc(items, m);
     const int kout = min(a.k, ncand);
     for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
         int64_t id = -1;
         float sc = -INFINITY;
         if (r < kout) {
-            const uint64_t it = emit_cand[r];
+            const uint64_t it = items[r];
             uint32_t key = item_key(it);
             if (a.self_base >= 0 && key == 0xFFFFFFFFu) key = sh_selfkey;
             id = (int64_t)item_row(it) + a.id_offset;
@@ -434,17 +439,18 @@ int finalise_cand_max(int k) {
     while (m < 2 * k) m <<= 1;
     return m;
 }
-size_t finalise_work_bytes(int64_t nq, int k) { return (size_t)nq * finalise_cand_max(k) * sizeof(uint64_t) + (size_t)nq * 2 * sizeof(int); }
+size_t finalise_work_bytes(int64_t nq, int k) { return (size_t)nq * finalise_cand_max(k) * sizeof(uint64_t) + (size_t)nq * 3 * sizeof(int); }
 
 void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
     FinaliseArgs a = a_in;
     const int cand_max = finalise_cand_max(a.k);
-    const bool split = !a.exact && a.work && nq <= FIN_SPLIT_MAX_Q;
+    const bool split = !a.exact && a.work && a.ticket && nq <= FIN_SPLIT_MAX_Q;
     if (split) {
         a.w_cand = static_cast<uint64_t*>(a.work);
         a.w_ncand = reinterpret_cast<int*>(a.w_cand + (size_t)nq * cand_max);
         a.w_flag = a.w_ncand + nq;
+        a.w_ticket = a.ticket;                       // zero-initialised once by the owner, self-resetting
     }
     const size_t offs_bytes = ((a.P <= FIN_MAX_LISTS) ? (size_t)((a.P + 4) & ~3) : 4) * sizeof(int);
     const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float) + 4096 * sizeof(uint32_t);
@@ -459,18 +465,16 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     if (split) {
         cudaFuncSetAttribute(finalise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<true>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
-        const size_t rsm = (size_t)RS_WARPS * a.d_pad * sizeof(float);
-        if (rsm > 48 * 1024) cudaFuncSetAttribute(finalise_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-        launch_pdl(finalise_rescore_kernel, dim3((unsigned)nq, RS_SPLIT), dim3(RS_WARPS * 32), rsm, st, a, cand_max);
-        const size_t esm = (size_t)cand_max * sizeof(uint64_t);
-        if (esm > 48 * 1024) cudaFuncSetAttribute(finalise_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm);
-        launch_pdl(finalise_emit_kernel, dim3((unsigned)nq), dim3(256), esm, st, a, cand_max);
+        size_t rsm = (size_t)RS_WARPS * a.d_pad * sizeof(float);
+        if (rsm < (size_t)cand_max * sizeof(uint64_t)) rsm = (size_t)cand_max * sizeof(uint64_t);
+        if (rsm > 48 * 1024) cudaFuncSetAttribute(finalise_rescore_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+        launch_pdl(finalise_rescore_emit_kernel, dim3((unsigned)nq, RS_SPLIT), dim3(RS_WARPS * 32), rsm, st, a, cand_max);
     } else {
         cudaFuncSetAttribute(finalise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<false>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
     }
 }
-int finalise_launches(const FinaliseArgs& a, int64_t nq) { return (!a.exact && a.work && nq <= FIN_SPLIT_MAX_Q) ? 3 : 1; }
+int finalise_launches(const FinaliseArgs& a, int64_t nq) { return (!a.exact && a.work && a.ticket && nq <= FIN_SPLIT_MAX_Q) ? 2 : 1; }
 
 // ---- threshold bootstrap ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)

@@ -95,7 +95,8 @@ struct FinaliseArgs {
     int64_t* out_idx; float* out_score; int* status; int* n_cand;
     int64_t out_pitch;          // elements between consecutive queries in out_idx / out_score
     void* work;                 // optional: finalise_work_bytes(nq, k) of scratch -> enables the 3-kernel split for small batches
-    uint64_t* w_cand; int* w_ncand; int* w_flag;   // carved out of `work` by launch_finalise
+    int* ticket;                // [nq] zero-initialised completion counters (self-resetting), required for the split
+    uint64_t* w_cand; int* w_ncand; int* w_flag; int* w_ticket;   // carved out by launch_finalise
 };
 int  finalise_cand_max(int k);
 size_t finalise_work_bytes(int64_t nq, int k);
