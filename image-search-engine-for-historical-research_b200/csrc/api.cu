@@ -752,3 +752,24 @@ extern "C" int xs_merge_candidates_strided(int device, const void* in_idx, const
     CU_TRY(cudaGetLastError());
     return XS_OK;
 }
+
+extern "C" int xs_mutual_knn(int device, const int64_t* ids, int64_t n, int kd, uint8_t* out_mutual) {
+    if (!ids || !out_mutual) return fail(XS_ERR_ARG, "null pointer");
+    if (n <= 0 || kd <= 0 || n > 0x7FFFFFFF) return fail(XS_ERR_ARG, "bad sizes (n=%lld, kd=%d)", (long long)n, kd);
+    CU_TRY(cudaSetDevice(device));
+    const size_t count = (size_t)n * kd;
+    void *d64 = nullptr, *d32 = nullptr, *dm = nullptr;
+    cudaError_t e = cudaMalloc(&d64, count * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d32, count * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dm, count);
+    if (e == cudaSuccess) e = cudaMemcpy(d64, ids, count * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_mutual_knn(static_cast<const int64_t*>(d64), static_cast<int32_t*>(d32), n, kd, static_cast<uint8_t*>(dm), nullptr);
+        e = cudaMemcpy(out_mutual, dm, count, cudaMemcpyDeviceToHost);
+    }
+    if (d64) cudaFree(d64);
+    if (d32) cudaFree(d32);
+    if (dm) cudaFree(dm);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "xs_mutual_knn: %s", cudaGetErrorString(e)); }
+    return XS_OK;
+}

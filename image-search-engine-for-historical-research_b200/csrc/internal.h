@@ -115,4 +115,8 @@ size_t rank_all_work_bytes(int c, int64_t n);
 void launch_rank_all(const float* scores, int64_t pitch, int c, int64_t n, int q0, int nq_total, int64_t id_offset,
                      void* work, int64_t* out_ranks, float* out_scores, cudaStream_t st);
 
+// ---- graph.cu -----------------------------------------------------------------------------------
+// mutual[i][j] = 1 iff j >= 1 and i is among the kd neighbours of ids[i][j]  (diffusion.py:107-108)
+void launch_mutual_knn(const int64_t* ids64, int32_t* ids32_scratch, int64_t n, int kd, uint8_t* mutual, cudaStream_t st);
+
 }  // namespace xs

@@ -160,6 +160,14 @@ XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const voi
                                        int64_t* out_idx, float* out_score, void* stream);
 
 /*
+ * Mutual-kNN test of the diffusion affinity graph.
+ *   replaces: the per-row loop `np.isin(ids[ids[i]], i).any(axis=1)` of get_affinity   src/utils/diffusion.py:106-108
+ * ids: HOST [n, kd] int64, the kNN lists of every row (slot 0 = the row itself, as xs_self_knn returns them).
+ * out_mutual: HOST [n, kd] bytes, 1 where slot j >= 1 is a mutual neighbour, 0 elsewhere (slot 0 always 0).
+ */
+XS_API int xs_mutual_knn(int device, const int64_t* ids, int64_t n, int kd, uint8_t* out_mutual);
+
+/*
  * Tunables (set before searching; all have safe defaults):
  *   "eps_sigmas"   float  width of the bf16 error band in standard deviations      (8.0)
  *   "scan_max_q"   int    largest batch served by the batch-1 HBM scan kernel      (1)

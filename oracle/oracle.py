@@ -220,6 +220,32 @@ def protocol_maps(ranks, gnd, kappas=(1, 5, 10)):
 
 
 # --------------------------------------------------------------------------------------
+# 8f-2 -- mutual-kNN affinity of the diffusion graph          src/utils/diffusion.py:101-116
+# --------------------------------------------------------------------------------------
+def mutual_mask(ids):
+    """``ismutual`` of diffusion.py:107-108 for every row: slot j of row i is mutual when i occurs in
+    the neighbour list of ``ids[i, j]``; slot 0 (the row itself) is cleared."""
+    ids = np.asarray(ids)
+    out = np.zeros(ids.shape, dtype=bool)
+    for i in range(ids.shape[0]):
+        m = np.isin(ids[ids[i]], i).any(axis=1)
+        m[0] = False
+        out[i] = m
+    return out
+
+
+def affinity_dense(sims, ids, gamma=3):
+    """Dense restatement of ``get_affinity`` (diffusion.py:101-116) for small N."""
+    sims = np.where(sims < 0, 0, sims).astype(np.float32) ** gamma
+    n = sims.shape[0]
+    a = np.zeros((n, n), dtype=np.float32)
+    m = mutual_mask(ids)
+    for i in range(n):
+        a[i, np.asarray(ids)[i, m[i]]] = sims[i, m[i]]
+    return a
+
+
+# --------------------------------------------------------------------------------------
 # comparator used by every parity test
 # --------------------------------------------------------------------------------------
 def compare_topk(ids, ref_ids, score_of, rtol=1e-6, atol=1e-7):

@@ -108,6 +108,30 @@ def main():
     out["E_sorted_scores"] = np.take_along_axis(ns["scores"], ns["ranks"], axis=0)
     out["E_ranks"] = ns["ranks"]
 
+    # --- case F: diffusion graph -- Diffusion.get_affinity / get_laplacian lifted from the class body ---
+    import scipy.sparse as sparse
+    dsrc = open(f"{REF}/src/utils/diffusion.py").read()
+    cls = [n for n in ast.parse(dsrc).body if isinstance(n, ast.ClassDef) and n.name == "Diffusion"][0]
+    ns = {"np": np, "sparse": sparse}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in ("get_affinity", "get_laplacian"):
+            fn.decorator_list = []
+            code = ast.get_source_segment(dsrc, fn)
+            exec(compile(textwrap.dedent(code), f"diffusion.py:{fn.name}", "exec"), ns)
+
+    class _Self:
+        get_affinity = lambda self, sims, ids, gamma=3: ns["get_affinity"](self, sims, ids, gamma)
+    v, _ = synth.clustered(400, 1, d=64, n_clusters=12, noise=0.9)[:2]
+    oracle = importlib.import_module("oracle.oracle")
+    sims, ids = oracle.knn_search(v.T, v.T, 12, "cosine")
+    assert (ids[:, 0] == np.arange(400)).all()
+    aff = ns["get_affinity"](_Self(), sims.copy(), ids)
+    lap = ns["get_laplacian"](_Self(), sims.copy(), ids)
+    out["F_knn_ids"] = ids.astype(np.int32)
+    out["F_knn_sims"] = sims
+    out["F_affinity"] = aff.toarray()
+    out["F_laplacian"] = np.asarray(lap.toarray(), dtype=np.float32)
+
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     for k, a in out.items():
         print(f"{k:28s} {str(a.dtype):8s} {a.shape}")

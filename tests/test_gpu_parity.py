@@ -342,3 +342,20 @@ def test_argument_errors_and_dtypes(pkg, synth, oracle):
             ix.search(q.T, 5)                                      # closed index
     with pytest.raises(ValueError):
         pkg.matching_L2(600, v.T, q.T)                             # K > N
+
+
+def test_diffusion_graph(pkg, synth, oracle, golden):
+    """Mutual-kNN affinity + Laplacian (diffusion.py:87-116) from the GPU kNN lists vs the reference's own output."""
+    ids, sims = golden["F_knn_ids"].astype(np.int64), golden["F_knn_sims"]
+    np.testing.assert_array_equal(pkg.diffusion.mutual_mask(ids), oracle.mutual_mask(ids))
+    aff = pkg.diffusion.get_affinity(sims.copy(), ids)
+    np.testing.assert_array_equal(aff.toarray(), golden["F_affinity"])
+    lap = pkg.diffusion.get_laplacian(sims.copy(), ids)
+    np.testing.assert_allclose(np.asarray(lap.toarray(), dtype=np.float32), golden["F_laplacian"], rtol=1e-6, atol=1e-7)
+    # end to end: the kNN lists themselves from the GPU self search
+    v, _ = synth.clustered(400, 1, d=64, n_clusters=12, noise=0.9)[:2]
+    s2, i2, lap2 = pkg.diffusion.knn_graph(v.T, n_trunc=12, kd=12)
+    assert (i2[:, 0] == np.arange(400)).all()
+    s64 = oracle.scores_f64(v, v)
+    _check_lists(oracle, i2, ids, s64, "knn_graph ids")
+    assert lap2.shape == (400, 400)

@@ -103,3 +103,9 @@ def test_compare_topk(oracle):
     assert oracle.compare_topk([0, 1, 2], [0, 2, 1], f)[0]
     assert not oracle.compare_topk([0, 1, 3], [0, 1, 2], f)[0]
     assert not oracle.compare_topk([0, 1, 1], [0, 1, 2], f)[0]
+
+
+def test_diffusion_affinity(oracle, golden):
+    ids, sims = golden["F_knn_ids"].astype(np.int64), golden["F_knn_sims"]
+    np.testing.assert_array_equal(oracle.affinity_dense(sims.copy(), ids), golden["F_affinity"])
+    assert golden["F_affinity"].any() and (golden["F_affinity"] != golden["F_affinity"].T).any() is not None
