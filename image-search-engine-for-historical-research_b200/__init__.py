@@ -14,7 +14,7 @@ from .knn import KNN, BaseKNN
 from .nnsearch import matching, matching_L2, cached_index, clear_index_cache
 from .ranking import rank_ip
 from .reranking import feature_enhancement, qge1
-from . import diffusion
+from . import diffusion, store
 
 __all__ = ["ExactIndex", "KNN", "BaseKNN", "matching", "matching_L2", "rank_ip",
-           "cached_index", "clear_index_cache", "feature_enhancement", "qge1", "diffusion"]
+           "cached_index", "clear_index_cache", "feature_enhancement", "qge1", "diffusion", "store"]

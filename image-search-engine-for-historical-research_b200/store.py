@@ -1,0 +1,66 @@
+"""Feature store: a memory-mappable on-disk form of the descriptor matrix.
+
+The reference persists descriptors as a pickle ``{'path': [...], 'feature': ndarray (D, N)}``
+(``save_path_feature`` / ``load_path_features``, src/utils/general.py:67-92) and as a torch file
+for the R1M distractors (src/extract_1m.py:98, src/test_rOP1m.py:137); at start-up ``online.py``
+unpickles, concatenates into a float64 array and transposes views of it on every request
+(src/online.py:93-102, 133).  The store keeps ROW-major fp32 ``(N, D)`` in a plain ``.npy`` (so
+``np.load(mmap_mode='r')`` maps it without reading) next to the path list; building the device
+index from it is then a straight staged copy -- no unpickle, no concatenate, no transpose, no
+accidental float64.
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+
+import numpy as np
+
+ROWS_FILE = "rows.npy"
+PATHS_FILE = "paths.json"
+
+
+def save_store(directory: str, vecs, paths=None, chunk: int = 65536) -> str:
+    """Write ``vecs`` -- the reference's ``(D, N)`` array -- as a row-major fp32 store."""
+    vecs = np.asarray(vecs)
+    d, n = vecs.shape
+    os.makedirs(directory, exist_ok=True)
+    out = np.lib.format.open_memmap(os.path.join(directory, ROWS_FILE), mode="w+", dtype=np.float32, shape=(n, d))
+    for lo in range(0, n, chunk):                      # transposed in blocks: no second full-size copy
+        hi = min(n, lo + chunk)
+        out[lo:hi] = vecs[:, lo:hi].T
+    out.flush()
+    del out
+    with open(os.path.join(directory, PATHS_FILE), "w") as f:
+        json.dump(list(paths) if paths is not None else [], f)
+    return directory
+
+
+def open_store(directory: str):
+    """``(rows, paths)``: ``rows`` is a read-only memory map ``(N, D)`` fp32; ``rows.T`` is the
+    reference's ``vecs`` view."""
+    rows = np.load(os.path.join(directory, ROWS_FILE), mmap_mode="r")
+    with open(os.path.join(directory, PATHS_FILE)) as f:
+        paths = json.load(f)
+    return rows, paths
+
+
+def load_path_features(pickle_path: str):
+    """Reader for the reference's own pickle (general.py:84-92): ``(vecs (D, N), img_r_path)``."""
+    with open(pickle_path, "rb") as f:
+        pf = pickle.load(f)
+    return pf["feature"], pf["path"]
+
+
+def convert_pickle(pickle_path: str, directory: str) -> str:
+    """One-off conversion of a reference feature pickle into a store."""
+    vecs, paths = load_path_features(pickle_path)
+    return save_store(directory, vecs, paths)
+
+
+def index_from_store(directory: str, renormalise: bool = False, device: int = 0):
+    """Device index straight from the mapped rows (uploaded in 8k-row tiles by xs_index_create)."""
+    from .index import ExactIndex
+    rows, paths = open_store(directory)
+    return ExactIndex(rows, renormalise=renormalise, device=device), paths
