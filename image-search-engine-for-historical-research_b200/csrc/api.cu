@@ -436,12 +436,12 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const float* thr0 = nullptr;
             XS_TRY(ix->thr0.ensure((size_t)c * sizeof(float)));
             GemmPlan sp = plan_gemm_sample(plan, ix->num_sms, k);
-            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 4 * k) {
+            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 3 * k) {
                 const int64_t sslots = (int64_t)sp.m_tiles * sp.splits * GEMM_BM;
                 XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));
                 XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
                 XS_TRY(ix->pool_thr.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
-                cudaError_t es = launch_gemm_topk(*ta, ix->tmap_db_b, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+                cudaError_t es = launch_gemm_topk(*ta, ix->tmap_db_a, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                                   ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                                   (int)row0, nullptr, ix->cur);
                 if (es != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk (sample) launch failed: %s", cudaGetErrorString(es));

@@ -30,14 +30,20 @@ namespace xs {
 //                 traffic per flop and deepens the ring: large query batches, tensor-pipe-bound.
 constexpr int MAX_STAGES = 6;
 constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB
-template <bool PAIR> struct Shape {
-    static constexpr int STAGES = PAIR ? 6 : 4;
-    static constexpr int B_ROWS = PAIR ? GEMM_BN / 2 : GEMM_BN;
+//   HALF          one CTA per 128 x 128 tile (cta_group::1), 6 stages x 32 KB: the per-CTA staging of PAIR without
+//                 the pairing.  Used by the threshold-bootstrap pass, which is one tile per CTA and purely
+//                 latency-bound: a deeper ring of smaller stages finishes the 32 K-steps sooner.
+enum { MODE_FULL = 0, MODE_PAIR = 1, MODE_HALF = 2 };
+template <int MODE> struct Shape {
+    static constexpr bool PAIR = MODE == MODE_PAIR;
+    static constexpr int STAGES = MODE == MODE_FULL ? 4 : 6;
+    static constexpr int B_ROWS = MODE == MODE_FULL ? GEMM_BN : GEMM_BN / 2;     // database rows this CTA stages per step
+    static constexpr int TILE_N = MODE == MODE_HALF ? GEMM_BN / 2 : GEMM_BN;     // database rows per tile (UMMA N)
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int UMMA_M = PAIR ? 256 : 128;
-    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128|256
-    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GEMM_BN >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N = TILE_N, M = 128 | 256
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
 };
 constexpr int GEMM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
@@ -52,7 +58,7 @@ struct __align__(8) GemmBarriers {
 };
 // both shapes stage 192 KB of operands
 constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t);
-static_assert(Shape<true>::STAGES * Shape<true>::STAGE_BYTES == Shape<false>::STAGES * Shape<false>::STAGE_BYTES, "ring sizes differ");
+static_assert(Shape<MODE_PAIR>::STAGES * Shape<MODE_PAIR>::STAGE_BYTES == Shape<MODE_FULL>::STAGES * Shape<MODE_FULL>::STAGE_BYTES, "ring sizes differ");
 size_t gemm_smem_bytes() { return GEMM_SMEM; }
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in the pair's leader CTA
 
@@ -141,7 +147,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-template <bool PAIR>
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
@@ -149,8 +155,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    using S = Shape<PAIR>;
-    constexpr int STAGES = S::STAGES, B_BYTES = S::B_BYTES, STAGE_BYTES = S::STAGE_BYTES;
+    using S = Shape<MODE>;
+    constexpr bool PAIR = S::PAIR;
+    constexpr int STAGES = S::STAGES, B_BYTES = S::B_BYTES, STAGE_BYTES = S::STAGE_BYTES, TILE_N = S::TILE_N;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + STAGES * STAGE_BYTES);
@@ -210,11 +217,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             else mbar_arrive_remote(full, 0);
                             tma_load_2d_pair(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
                             tma_load_2d_pair(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK,
-                                             t * tile_stride * GEMM_BN + (int)cta_rank * S::B_ROWS, HINT_EVICT_LAST);
+                                             t * tile_stride * TILE_N + (int)cta_rank * S::B_ROWS, HINT_EVICT_LAST);
                         } else {
                             mbar_expect_tx(full, STAGE_BYTES);
                             tma_load_2d(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
-                            tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * tile_stride * GEMM_BN, HINT_EVICT_FIRST);
+                            tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * tile_stride * TILE_N, HINT_EVICT_FIRST);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -292,11 +299,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
 #pragma unroll 1
-                    for (int c = 0; c < GEMM_BN / 32; ++c) {
+                    for (int c = 0; c < TILE_N / 32; ++c) {
                         uint32_t v[32];
                         tc_ld32(taddr + c * 32, v);
                         tc_ld_wait();
-                        const int64_t lim = n_valid - ((int64_t)t * tile_stride * GEMM_BN + c * 32);
+                        const int64_t lim = n_valid - ((int64_t)t * tile_stride * TILE_N + c * 32);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             float s = __uint_as_float(v[i]);
@@ -322,11 +329,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
 #pragma unroll 1
-                for (int c = 0; c < GEMM_BN / 32; ++c) {
+                for (int c = 0; c < TILE_N / 32; ++c) {
                     uint32_t v[32];
                     tc_ld32(taddr + c * 32, v);
                     tc_ld_wait();
-                    const int64_t row_base = (int64_t)t * tile_stride * GEMM_BN + c * 32;
+                    const int64_t row_base = (int64_t)t * tile_stride * TILE_N + c * 32;
                     const int64_t lim = n_valid - row_base;                 // rows >= n_valid are zero padding
                     if (lim >= 32) {
 #pragma unroll
@@ -419,6 +426,7 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
     p.grid = p.pair ? 2 * used : used;
     p.tile_stride = 1;
     p.sample_mode = 0;
+    p.half = 0;
     return p;
 }
 
@@ -426,11 +434,12 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
 // The k-th best score of that sample is a valid lower bound of the k-th best of the whole database.
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
     GemmPlan p = main_plan;
-    p.pair = 0;                                      // the bootstrap pass always runs one CTA per tile
-    const int all_tiles = main_plan.n_tiles;
-    int s = (num_sms / 2) / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
-    if (s < 16) s = 16;
-    if (s < (3 * k + 3) / 4) s = (3 * k + 3) / 4;      // 8 scores per tile: the union must hold well over k of them
+    p.pair = 0;
+    p.half = 1;                                      // 128-row tiles, 6-stage ring: one tile per CTA, latency-bound
+    const int all_tiles = main_plan.n_tiles * 2;     // in 128-row tiles
+    int s = num_sms / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
+    if (s < 32) s = 32;
+    if (s < (3 * k + 3) / 4) s = (3 * k + 3) / 4;    // 8 scores per tile: the union must hold well over k of them
     if (s > all_tiles) s = all_tiles;
     p.n_tiles = s;
     p.tile_stride = all_tiles / s;
@@ -445,7 +454,7 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
                              const float* thr0, cudaStream_t st) {
-    auto kern = plan.pair ? gemm_topk_kernel<true> : gemm_topk_kernel<false>;
+    auto kern = plan.pair ? gemm_topk_kernel<MODE_PAIR> : (plan.half ? gemm_topk_kernel<MODE_HALF> : gemm_topk_kernel<MODE_FULL>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};

@@ -70,6 +70,7 @@ struct GemmPlan {
     int k_keep;       // items kept by a mid-job trim
     int cap;          // capacity of one partial list (>= 2 * k_keep)
     int grid;         // CTAs launched
+    int half;         // 1: 128-row database tiles, one CTA each, 6-stage ring (bootstrap pass; needs the box-128 database map)
     int pair;         // 1: cta_group::2 kernel, clusters of two CTAs, 256 x 256 tiles (needs the box-128 database map)
     int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)
     int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
