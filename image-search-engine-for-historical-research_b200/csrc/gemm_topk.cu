@@ -356,7 +356,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         uint64_t* l = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(list), src));
                         const int c_src = __shfl_sync(0xffffffffu, cnt, src);
                         uint32_t T;
-                        const int c_new = warp_prune(l, c_src, k_keep, true, 0.f, my_hist, T);
+                        const int c_new = warp_prune_edge(l, c_src, k_keep, -1.f, cap, 64, my_hist, T);
                         if (lane == src) { cnt = c_new; thr = fmaxf(thr, key_score(T)); thr_rec = max(thr_rec, T); }
                     }
                 }
@@ -374,7 +374,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int c_src = __shfl_sync(0xffffffffu, cnt, src);
                 const float b_src = __shfl_sync(0xffffffffu, band, src);
                 uint32_t T;
-                const int c_new = warp_prune(l, c_src, k, false, b_src, my_hist, T);
+                const int c_new = warp_prune_edge(l, c_src, k, b_src, cap, 0, my_hist, T);
                 if (lane == src) cnt = c_new;
             }
             pool_count[slot] = cnt;
@@ -437,9 +437,14 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
     p.pair = 0;
     p.half = 1;                                      // 128-row tiles, 6-stage ring: one tile per CTA, latency-bound
     const int all_tiles = main_plan.n_tiles * 2;     // in 128-row tiles
-    int s = num_sms / (main_plan.m_tiles > 0 ? main_plan.m_tiles : 1);
-    if (s < 32) s = 32;
-    if (s < (3 * k + 3) / 4) s = (3 * k + 3) / 4;    // 8 scores per tile: the union must hold well over k of them
+    // tiles per query tile: at least 32 and 1.25 k (8 scores per tile: the union must hold well over k), then
+    // rounded UP to fill whole waves of one-tile jobs
+    const int mt = main_plan.m_tiles > 0 ? main_plan.m_tiles : 1;
+    int s0 = (5 * k + 3) / 4;
+    if (s0 < 32) s0 = 32;
+    const int64_t rounds = ((int64_t)mt * s0 + num_sms - 1) / num_sms;
+    int s = (int)(rounds * num_sms / mt);
+    if (s < s0) s = s0;
     if (s > all_tiles) s = all_tiles;
     p.n_tiles = s;
     p.tile_stride = all_tiles / s;

@@ -127,4 +127,53 @@ __device__ __forceinline__ int warp_prune(uint64_t* list, int cnt, int keep, boo
     return out;
 }
 
+// Cheaper trim for the common case: min/max of the keys, ONE pass into 256 bins spread over [min, max],
+// keep everything from the bin that holds the `keep`-th largest key upwards.  The kept count is >= keep
+// and exceeds it by at most that bin's population; when that would leave fewer than `slack` free slots
+// (heavy ties) the exact radix trim above takes over.  `band` < 0: trim by count at the bin edge;
+// `band` >= 0: keep every item whose score is >= key_score(edge) - band.  thr_key = the edge (<= the
+// true keep-th largest key), i.e. nothing at or above it was dropped.
+__device__ __forceinline__ int warp_prune_edge(uint64_t* list, int cnt, int keep, float band, int cap, int slack,
+                                               uint32_t* whist, uint32_t& thr_key) {
+    const uint32_t lane = lane_id();
+    __syncwarp();
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+    for (int i = lane; i < cnt; i += 32) { const uint32_t key = item_key(list[i]); kmin = min(kmin, key); kmax = max(kmax, key); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    const uint32_t range = kmax - kmin;
+    const int shift = (range >> 8) ? (32 - __clz(range) - 8) : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) whist[lane * 8 + j] = 0;
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) atomicAdd(&whist[(item_key(list[i]) - kmin) >> shift], 1u);
+    __syncwarp();
+    uint32_t dg, kr;
+    warp_pick_digit(whist, (uint32_t)keep, dg, kr);
+    // population at or above the edge = keep - kr + whist[dg]
+    const uint32_t kept = (uint32_t)keep - kr + whist[dg];
+    __syncwarp();
+    if (band < 0.f && kept + (uint32_t)slack > (uint32_t)cap)
+        return warp_prune(list, cnt, keep, true, 0.f, whist, thr_key);      // ties: exact trim by count
+    const uint32_t edge = kmin + (dg << shift);
+    thr_key = edge;
+    const uint32_t cut_key = (band >= 0.f) ? score_key(key_score(edge) - band) : edge;
+    int out = 0;
+    for (int b = 0; b < cnt; b += 32) {
+        const int i = b + lane;
+        const uint64_t it = (i < cnt) ? list[i] : 0ull;
+        const bool take = (i < cnt) && item_key(it) >= cut_key;
+        const uint32_t tm = __ballot_sync(0xffffffffu, take);
+        const int pos = out + __popc(tm & lanemask_lt());
+        __syncwarp();
+        if (take) list[pos] = it;
+        out += __popc(tm);
+    }
+    __syncwarp();
+    return out;
+}
+
 }  // namespace xs
