@@ -293,10 +293,11 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16 coarse scoring (tcgen05, fp32 accumulate) + fp32 operands / fp64-accumulated exact rescoring", "data": "synthetic",
+        "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2: 1,007,000 x 2048 DB (unit-norm Gaussian, seed 0), 70-query batch, exact top-100",
                    "rows_per_gpu": shard_rows, "sharding": "none" if world == 1 else f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel",
                    "l2": "inputs larger than L2 (4.1 GB bf16 database per pass vs 126 MB L2)",
+                   "arithmetic": "bf16 operands / fp32 accumulate (tcgen05) for the coarse pass, then fp32 operands / fp64 accumulate exact rescoring of ~120 candidates per query",
                    "path": {1: "scan", 2: "tcgen05 GEMM + fused top-K", 3: "exact"}.get(stats["path"], "?"),
                    "uncertified_queries_last_step": int(uncert), "parity_spot_check": parity_ok},
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": N_QUERIES * DIM * 4,
