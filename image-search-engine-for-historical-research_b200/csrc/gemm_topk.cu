@@ -79,16 +79,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap, not hang the device.  Waiters back off with nanosleep: in the
-// HBM-bound regime the 128 epilogue threads wait ~20 us per tile, and spinning at full rate costs power
-// that the (power-capped) part takes back from the SM clock.
+// Bounded wait: a protocol bug must trap, not hang the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    unsigned ns = 32;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(ns);
-        if (ns < 256) ns <<= 1;
         if (clock64() - t0 > 8000000000ll) { printf("xs gemm_topk: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
