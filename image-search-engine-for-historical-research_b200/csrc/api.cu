@@ -644,6 +644,9 @@ extern "C" int xs_aqe_search(xs_index* ix, const int64_t* top_ids, int64_t nq, i
     return finish_to_host(ix, a.q32, nq, k, -1, a.out_idx, a.out_score, a.status, a.path != PATH_EXACT, out_idx, out_score);
 }
 
+// Self-kNN runs as a two-deep software pipeline: while the GPU works on batch b, the host drains batch
+// b-1 (certificate bits, the rare exact re-runs, copy into the caller's arrays) from the other half of
+// a double-buffered pinned landing zone.
 extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, int64_t* out_idx, float* out_score) {
     if (!ix) return fail(XS_ERR_ARG, "null index");
     if (q_begin < 0 || q_end > ix->n || q_begin >= q_end) return fail(XS_ERR_ARG, "bad row range [%lld, %lld)", (long long)q_begin, (long long)q_end);
@@ -653,26 +656,80 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
     CU_TRY(cudaSetDevice(ix->device));
     ix->cur = ix->stream;
     const int64_t batch = 8192;
+    const size_t nb_i = (size_t)batch * k * sizeof(int64_t), nb_s = (size_t)batch * k * sizeof(float), nb_st = (size_t)(batch + 1) * sizeof(int);
     XS_TRY(ix->status.ensure((size_t)batch * sizeof(int)));
-    XS_TRY(ix->out_idx.ensure((size_t)batch * k * sizeof(int64_t)));
-    XS_TRY(ix->out_score.ensure((size_t)batch * k * sizeof(float)));
+    XS_TRY(ix->out_idx.ensure(nb_i));
+    XS_TRY(ix->out_score.ensure(nb_s));
+    XS_TRY(ix->h_idx.ensure(2 * nb_i));
+    XS_TRY(ix->h_score.ensure(2 * nb_s));
+    XS_TRY(ix->h_status.ensure(2 * nb_st));
+    cudaEvent_t done[2];
+    CU_TRY(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     xs_stats total{};
-    for (int64_t r0 = q_begin; r0 < q_end; r0 += batch) {
+    int rc = XS_OK;
+
+    // drain batch `pb` (rows [pr0, pr0+pc)) that was copied into landing-zone half `ph`
+    auto drain = [&](int ph, int64_t pr0, int64_t pc, bool coarse) -> int {
+        CU_TRY(cudaEventSynchronize(done[ph]));
+        int64_t* hi = reinterpret_cast<int64_t*>(static_cast<char*>(ix->h_idx.p) + ph * nb_i);
+        float* hs = reinterpret_cast<float*>(static_cast<char*>(ix->h_score.p) + ph * nb_s);
+        int* hst = reinterpret_cast<int*>(static_cast<char*>(ix->h_status.p) + ph * nb_st);
+        if (coarse) {
+            total.n_candidates += hst[0];
+            for (int64_t q = 0; q < pc;) {
+                if (!(hst[1 + q] & ST_UNCERTIFIED)) { ++q; continue; }
+                int64_t e = q + 1;
+                while (e < pc && e - q < 16 && (hst[1 + e] & ST_UNCERTIFIED)) ++e;
+                // rare: exact re-run after everything in flight has finished (the device result buffers are shared)
+                CU_TRY(cudaStreamSynchronize(ix->stream));
+                int launches = 0;
+                XS_TRY(run_exact(ix, ix->db32 + (size_t)(pr0 + q) * ix->d_pad, e - q, k, pr0 + q, ix->out_idx.as<int64_t>(),
+                                 ix->out_score.as<float>(), nullptr, &launches));
+                CU_TRY(cudaMemcpyAsync(hi + q * k, ix->out_idx.p, (size_t)(e - q) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+                CU_TRY(cudaMemcpyAsync(hs + q * k, ix->out_score.p, (size_t)(e - q) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+                CU_TRY(cudaStreamSynchronize(ix->stream));
+                total.n_exact_rerun += e - q; total.gpu_launches += launches;
+                q = e;
+            }
+        }
+        memcpy(out_idx + (pr0 - q_begin) * k, hi, (size_t)pc * k * sizeof(int64_t));
+        if (out_score) memcpy(out_score + (pr0 - q_begin) * k, hs, (size_t)pc * k * sizeof(float));
+        return XS_OK;
+    };
+
+    int64_t prev_r0 = -1, prev_c = 0; int prev_h = 0; bool prev_coarse = false; bool have_prev = false;
+    int b = 0;
+    for (int64_t r0 = q_begin; r0 < q_end && rc == XS_OK; r0 += batch, ++b) {
         const int64_t c = (q_end - r0 < batch) ? q_end - r0 : batch;
+        const int h = b & 1;
         CoreArgs a{};
         a.q32 = ix->db32 + (size_t)r0 * ix->d_pad; a.nq = c; a.k = k; a.prep = true; a.prep_renorm = false;   // rows are used as stored
         a.path = choose_path(ix, c, k);
         a.tmap_a = (a.path == PATH_GEMM) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
         a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
-        XS_TRY(search_core(ix, a));
-        XS_TRY(finish_to_host(ix, a.q32, c, k, r0, a.out_idx, a.out_score, a.status, a.path != PATH_EXACT,
-                              out_idx + (r0 - q_begin) * k, out_score ? out_score + (r0 - q_begin) * k : nullptr));
-        total.n_queries += ix->stats.n_queries; total.n_exact_rerun += ix->stats.n_exact_rerun;
-        total.n_candidates += ix->stats.n_candidates; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;
+        rc = search_core(ix, a);
+        if (rc != XS_OK) break;
+        total.n_queries += c; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;
+        char* hi = static_cast<char*>(ix->h_idx.p) + h * nb_i;
+        char* hs = static_cast<char*>(ix->h_score.p) + h * nb_s;
+        int* hst = reinterpret_cast<int*>(static_cast<char*>(ix->h_status.p) + h * nb_st);
+        cudaError_t e = cudaMemcpyAsync(hi, a.out_idx, (size_t)c * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hs, a.out_score, (size_t)c * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hst + 1, a.status, (size_t)c * sizeof(int), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hst, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[h], ix->stream);
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "xs_self_knn: %s", cudaGetErrorString(e)); break; }
+        if (have_prev) rc = drain(prev_h, prev_r0, prev_c, prev_coarse);
+        prev_r0 = r0; prev_c = c; prev_h = h; prev_coarse = a.path != PATH_EXACT; have_prev = true;
     }
+    if (rc == XS_OK && have_prev) rc = drain(prev_h, prev_r0, prev_c, prev_coarse);
+    cudaStreamSynchronize(ix->stream);
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
     ix->stats = total;
     ix->ev_valid = false;
-    return XS_OK;
+    return rc;
 }
 
 extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, int64_t stride_row, int64_t stride_col,

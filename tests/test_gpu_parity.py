@@ -359,3 +359,30 @@ def test_diffusion_graph(pkg, synth, oracle, golden):
     s64 = oracle.scores_f64(v, v)
     _check_lists(oracle, i2, ids, s64, "knn_graph ids")
     assert lap2.shape == (400, 400)
+
+
+def test_self_knn_pipelined_batches_and_reruns(pkg, synth, oracle):
+    """More rows than one 8192-row batch (two-deep pipeline) and duplicated rows (certificate fails ->
+    exact re-run inside the pipeline): every row still gets its own id first and exact neighbours."""
+    v, _ = synth.gaussian(20000, 1, d=64)
+    ix = pkg.ExactIndex(v.T)
+    sims, ids = ix.self_knn(10)
+    assert (ids[:, 0] == np.arange(20000)).all()
+    pick = np.array([0, 1, 8191, 8192, 8193, 16383, 16384, 19999])
+    rs, ri = oracle.knn_search(v.T, v.T[pick], 10, "cosine")
+    s64 = oracle.scores_f64(v, v[:, pick])
+    _check_lists(oracle, ids[pick], ri, s64, "self-kNN pipelined")
+    sub_s, sub_i = ix.self_knn(10, 9000, 9100)              # a row range
+    np.testing.assert_array_equal(sub_i, ids[9000:9100])
+    ix.close()
+    vt, _ = synth.ties(9000, 1, d=64, n_distinct=300)       # every row has 29 exact duplicates
+    ix = pkg.ExactIndex(vt.T)
+    sims, ids = ix.self_knn(8)
+    st = ix.stats()
+    assert (ids[:, 0] == np.arange(9000)).all()
+    # the 7 other neighbours are duplicates of the row (score 1), lowest ids first
+    for r in (0, 299, 300, 4567, 8999):
+        dup = np.arange(r % 300, 9000, 300)
+        expect = [r] + [d for d in dup if d != r][:7]
+        assert ids[r].tolist() == expect, (r, ids[r], expect)
+    ix.close()
