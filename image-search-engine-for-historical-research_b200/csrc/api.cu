@@ -436,7 +436,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const float* thr0 = nullptr;
             XS_TRY(ix->thr0.ensure((size_t)c * sizeof(float)));
             GemmPlan sp = plan_gemm_sample(plan, ix->num_sms, k);
-            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 3 * k) {
+            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 3 * k && (size_t)sp.splits * 64 <= 200 * 1024) {
                 const int64_t sslots = (int64_t)sp.m_tiles * sp.splits * GEMM_BM;
                 XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));
                 XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));

@@ -518,7 +518,9 @@ sample_threshold_kernel(const uint64_t* __restrict__ pool_items, const int* __re
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
-    launch_pdl(sample_threshold_kernel, dim3((unsigned)nq), dim3(1024), (size_t)8 * P * sizeof(uint64_t), st, pool_items, pool_count, P, cap, k, eps, thr0);
+    const size_t smem = (size_t)8 * P * sizeof(uint64_t);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_pdl(sample_threshold_kernel, dim3((unsigned)nq), dim3(1024), smem, st, pool_items, pool_count, P, cap, k, eps, thr0);
 }
 
 // ---- multi-GPU merge -------------------------------------------------------------------------------
