@@ -68,6 +68,17 @@ def test_full_size_properties(pkg, family):
         ids2, sims2 = ix.search(q_np, K)
         np.testing.assert_array_equal(ids2, ids)
         np.testing.assert_array_equal(sims2, sims)
+        # large k at full size: the bootstrap pass sizes its sample to k; coarse paths vs exact path
+        if family == "G":
+            for kk in (1000, 2048):
+                ix.set_param("force_path", 2)
+                gi, gs = ix.search(q_np[:3], kk)
+                assert ix.stats()["path"] == 2
+                ix.set_param("force_path", 3)
+                ei, es = ix.search(q_np[:3], kk)
+                np.testing.assert_array_equal(gi, ei)
+                np.testing.assert_array_equal(gs, es)
+            ix.set_param("force_path", 0)
         # batch-1 dispatch takes the scan path and agrees
         i1, s1 = ix.search(q_np[5:6], K)
         assert ix.stats()["path"] == 1
