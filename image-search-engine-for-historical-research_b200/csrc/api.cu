@@ -69,7 +69,7 @@ struct xs_index {
     __nv_bfloat16* db16 = nullptr; float* db32 = nullptr; DevStats* dstats = nullptr;
     CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
     // tunables
-    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0; float debug_thr = 0.f;
+    float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
     // workspace
     Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
@@ -256,7 +256,6 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "sample_pass")) ix->sample_pass = (int)value;
     else if (!strcmp(name, "pair_mode")) ix->pair_mode = (int)value;
     else if (!strcmp(name, "timing")) ix->timing = (int)value;
-    else if (!strcmp(name, "debug_thr")) ix->debug_thr = (float)value;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
 }
@@ -449,11 +448,6 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                                         ix->eps.as<float>() + q0, ix->thr0.as<float>(), c, ix->cur);
                 thr0 = ix->thr0.as<float>();
                 launches += 2;
-            } else if (ix->debug_thr != 0.f) {
-                std::vector<float> h((size_t)c, ix->debug_thr);
-                CU_TRY(cudaMemcpyAsync(ix->thr0.p, h.data(), (size_t)c * sizeof(float), cudaMemcpyHostToDevice, ix->cur));
-                CU_TRY(cudaStreamSynchronize(ix->cur));
-                thr0 = ix->thr0.as<float>();
             }
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
             cudaError_t e = launch_gemm_topk(*ta, plan.pair ? ix->tmap_db_a : ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,

@@ -59,7 +59,6 @@ struct __align__(8) GemmBarriers {
 // both shapes stage 192 KB of operands
 constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t);
 static_assert(Shape<MODE_PAIR>::STAGES * Shape<MODE_PAIR>::STAGE_BYTES == Shape<MODE_FULL>::STAGES * Shape<MODE_FULL>::STAGE_BYTES, "ring sizes differ");
-size_t gemm_smem_bytes() { return GEMM_SMEM; }
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in the pair's leader CTA
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------

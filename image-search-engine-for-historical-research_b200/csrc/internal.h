@@ -77,7 +77,6 @@ struct GemmPlan {
 };
 GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits, bool allow_pair);
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k);
-size_t   gemm_smem_bytes();
 // tmap_q: [nq_pad128][d_pad] bf16, box {64,128};  tmap_db: [n_pad][d_pad] bf16, box {64,256} (box {64,128} when plan.pair)
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,

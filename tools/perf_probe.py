@@ -52,7 +52,6 @@ def run(label, nq, reps=10, **params):
 
 run("gemm default (sample pass on)", Q, force_path=2)
 run("gemm, no sample pass", Q, force_path=2, sample_pass=0)
-run("gemm, no sample, thr=+10 (pure streaming)", Q, force_path=2, sample_pass=0, debug_thr=10.0)
 run("gemm default nq=1", 1, force_path=2)
 run("gemm default nq=16", 16, force_path=2)
 run("scan nq=1", 1, force_path=1)
