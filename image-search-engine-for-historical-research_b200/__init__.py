@@ -12,9 +12,9 @@ backed by hand-written sm_100a CUDA behind the C ABI in ``include/xs_b200.h``.  
 from .index import ExactIndex
 from .knn import KNN, BaseKNN
 from .nnsearch import matching, matching_L2, cached_index, clear_index_cache
-from .ranking import rank_ip
+from .ranking import rank_ip, rank_ip_torch
 from .reranking import feature_enhancement, qge1
 from . import diffusion, store
 
-__all__ = ["ExactIndex", "KNN", "BaseKNN", "matching", "matching_L2", "rank_ip",
+__all__ = ["ExactIndex", "KNN", "BaseKNN", "matching", "matching_L2", "rank_ip", "rank_ip_torch",
            "cached_index", "clear_index_cache", "feature_enhancement", "qge1", "diffusion", "store"]

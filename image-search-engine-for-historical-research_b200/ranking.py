@@ -30,3 +30,35 @@ def rank_ip(vecs, qvecs, K=None, return_scores=False, index=None):
     ids, sims = ix.search(q, K)
     ranks = np.ascontiguousarray(ids.T)
     return (ranks, np.ascontiguousarray(sims.T)) if return_scores else ranks
+
+
+def rank_ip_torch(vecs, qvecs, K, index=None):
+    """The same ranking for torch CUDA tensors without leaving the device -- the shape of the
+    reference's other dense score+sort sites, e.g. hard-negative mining
+    ``scores = torch.mm(poolvecs.t(), qvecs); scores, ranks = torch.sort(scores, dim=0, descending=True)``
+    (src/datasets/traindataset.py:221-222, 468-469), which only reads the leading ranks.
+
+    ``vecs`` is ``(D, N)``, ``qvecs`` ``(D, Q)`` (float tensors on one CUDA device); returns
+    ``(scores f32 (K, Q), ranks int64 (K, Q))`` tensors on that device, best first.  Pass ``index`` (an
+    ``ExactIndex``) to reuse a database already resident in the matcher's layout.
+    """
+    import torch
+    from .index import ExactIndex
+    if not (vecs.is_cuda and qvecs.is_cuda):
+        raise ValueError("rank_ip_torch takes CUDA tensors; use rank_ip for numpy arrays")
+    dev = vecs.device.index if vecs.device.index is not None else torch.cuda.current_device()
+    own = index is None
+    if own:
+        rows = vecs.t().contiguous().float()
+        torch.cuda.current_stream(dev).synchronize()
+        index = ExactIndex.from_device(rows.data_ptr(), rows.shape[0], rows.shape[1], dev)
+    q = qvecs.t().contiguous().float()
+    nq = int(q.shape[0])
+    ids = torch.empty((nq, int(K)), dtype=torch.int64, device=q.device)
+    sims = torch.empty((nq, int(K)), dtype=torch.float32, device=q.device)
+    index.search_device(q.data_ptr(), nq, int(K), ids.data_ptr(), sims.data_ptr(),
+                        stream=torch.cuda.current_stream(dev).cuda_stream)
+    if own:
+        torch.cuda.current_stream(dev).synchronize()
+        index.close()
+    return sims.t().contiguous(), ids.t().contiguous()

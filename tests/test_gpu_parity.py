@@ -386,3 +386,18 @@ def test_self_knn_pipelined_batches_and_reruns(pkg, synth, oracle):
         expect = [r] + [d for d in dup if d != r][:7]
         assert ids[r].tolist() == expect, (r, ids[r], expect)
     ix.close()
+
+
+def test_rank_ip_torch_device_tensors(pkg, synth, oracle):
+    """Device-resident variant for the torch.mm + torch.sort call sites (traindataset.py:221-222)."""
+    import torch
+    v, q = synth.gaussian(5000, 40, d=256)
+    tv, tq = torch.from_numpy(v).cuda(), torch.from_numpy(q).cuda()
+    scores, ranks = pkg.rank_ip_torch(tv, tq, 25)
+    assert ranks.shape == (25, 40) and ranks.is_cuda and scores.dtype == torch.float32
+    ref_scores, ref_ranks = torch.sort(torch.mm(tv.t(), tq), dim=0, descending=True)
+    s64 = oracle.scores_f64(v, q)
+    _check_lists(oracle, ranks.t().cpu().numpy(), ref_ranks[:25].t().cpu().numpy(), s64, "rank_ip_torch")
+    torch.testing.assert_close(scores, ref_scores[:25], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        pkg.rank_ip_torch(tv.cpu(), tq.cpu(), 5)
