@@ -231,17 +231,27 @@ def run_ours(args):
     # ---- end to end through the host-buffer call (`e2e`) ----------------------------------------------
     q_host = queries.cpu().pin_memory()
     q_np = q_host.numpy()
+    if world > 1:       # pinned landing buffers for the sharded path (the host-buffer C-ABI call has its own)
+        qd = torch.empty_like(queries)
+        ids_pin = torch.empty((N_QUERIES, TOPK), dtype=torch.int64).pin_memory()
+        sims_pin = torch.empty((N_QUERIES, TOPK), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        if world == 1:
+            return index.search(q_np, TOPK)                       # pinned host queries in, ids + scores back on the host
+        qd.copy_(q_host, non_blocking=True)
+        i_d, s_d = searcher.search(qd, TOPK)
+        ids_pin.copy_(i_d, non_blocking=True)
+        sims_pin.copy_(s_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return ids_pin, sims_pin
+
     for _ in range(3):
-        ids_h, sims_h = index.search(q_np, TOPK)
+        ids_h, sims_h = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        if world == 1:
-            ids_h, sims_h = index.search(q_np, TOPK)
-        else:
-            qd = q_host.to(dev, non_blocking=True)
-            i_d, s_d = searcher.search(qd, TOPK)
-            ids_h, sims_h = i_d.cpu(), s_d.cpu()
+        ids_h, sims_h = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
