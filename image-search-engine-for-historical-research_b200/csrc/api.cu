@@ -67,7 +67,9 @@ struct xs_index {
     int64_t n = 0, n_pad = 0, id_offset = 0;
     int d = 0, d_pad = 0;
     __nv_bfloat16* db16 = nullptr; float* db32 = nullptr; DevStats* dstats = nullptr;
+    __nv_bfloat16* db16t = nullptr;              // tiled twin of db16 for the GEMM's database operand (optional)
     CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
+    CUtensorMap tmap_dbt_b, tmap_dbt_h;          // tiled twin: boxes of 256 / 128 rows, each one contiguous run
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
     // workspace
@@ -104,8 +106,10 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d_pad
     cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
     cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("XS_EXP_L2PROMO")) promo = (CUtensorMapL2promotion)atoi(e);      // experiment knob
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(XS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return XS_OK;
@@ -159,12 +163,40 @@ static void index_free(xs_index* ix) {
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
     if (ix->db16) cudaFree(ix->db16);
+    if (ix->db16t) cudaFree(ix->db16t);
     if (ix->db32) cudaFree(ix->db32);
     if (ix->dstats) cudaFree(ix->dstats);
     for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     cudaGetLastError();
     delete ix;
+}
+
+// 2-D map over the tiled twin viewed as [n_pad * KB rows][64 columns] (stride 128 B): box {64, box_rows}.
+static int make_tmap_tiled(CUtensorMap* map, const void* base, int64_t n_pad, int d_pad, int box_rows) {
+    XS_TRY(get_encoder());
+    cuuint64_t dims[2] = {(cuuint64_t)GEMM_BK, (cuuint64_t)n_pad * (cuuint64_t)(d_pad / GEMM_BK)};
+    cuuint64_t strides[1] = {(cuuint64_t)GEMM_BK * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(XS_ERR_CUDA, "cuTensorMapEncodeTiled (tiled twin) failed with CUresult %d", (int)r);
+    return XS_OK;
+}
+
+// After all rows are in place: the tiled twin of the bf16 copy (skipped with XS_NO_TILED=1 or when memory is short).
+static int build_tiled_twin(xs_index* ix) {
+    if (const char* e = getenv("XS_NO_TILED")) if (atoi(e)) return XS_OK;
+    const size_t b16 = (size_t)ix->n_pad * ix->d_pad * 2;
+    if (cudaMalloc(&ix->db16t, b16) != cudaSuccess) { cudaGetLastError(); ix->db16t = nullptr; return XS_OK; }   // optional: fall back to the row-major maps
+    launch_tile_db16(ix->db16, ix->db16t, ix->n_pad, ix->d_pad, ix->stream);
+    CU_TRY(cudaStreamSynchronize(ix->stream));
+    XS_TRY(make_tmap_tiled(&ix->tmap_dbt_b, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BN));
+    XS_TRY(make_tmap_tiled(&ix->tmap_dbt_h, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BM));
+    ix->bytes += (int64_t)b16;
+    return XS_OK;
 }
 
 // Copies `rows` rows starting at r0 of a strided host matrix into a dense device tile.
@@ -213,6 +245,7 @@ extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int6
         if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e));
     }
     ix->stage.release();
+    if (rc == XS_OK) rc = build_tiled_twin(ix);
     if (rc != XS_OK) { index_free(ix); return rc; }
     *out = ix;
     return XS_OK;
@@ -231,6 +264,8 @@ extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int de
     }
     cudaError_t e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); index_free(ix); return rc; }
+    rc = build_tiled_twin(ix);
+    if (rc != XS_OK) { index_free(ix); return rc; }
     *out = ix;
     return XS_OK;
 }
@@ -440,7 +475,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));
                 XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
                 XS_TRY(ix->pool_thr.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
-                cudaError_t es = launch_gemm_topk(*ta, ix->tmap_db_a, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+                sp.db_tiled = ix->db16t ? 1 : 0;
+                cudaError_t es = launch_gemm_topk(*ta, ix->db16t ? ix->tmap_dbt_h : ix->tmap_db_a, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                                   ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                                   (int)row0, nullptr, ix->cur);
                 if (es != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk (sample) launch failed: %s", cudaGetErrorString(es));
@@ -450,7 +486,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 launches += 2;
             }
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
-            cudaError_t e = launch_gemm_topk(*ta, plan.pair ? ix->tmap_db_a : ix->tmap_db_b, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+            plan.db_tiled = ix->db16t ? 1 : 0;
+            cudaError_t e = launch_gemm_topk(*ta, ix->db16t ? (plan.pair ? ix->tmap_dbt_h : ix->tmap_dbt_b) : (plan.pair ? ix->tmap_db_a : ix->tmap_db_b), plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                              (int)row0, thr0, ix->cur);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));

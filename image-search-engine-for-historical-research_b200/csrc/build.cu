@@ -213,6 +213,25 @@ bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16,
     return true;
 }
 
+// ---- tiled bf16 copy ---------------------------------------------------------------------------------
+__global__ void tile_db16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n_pad, int d_pad) {
+    // one thread per 16-byte chunk: row r, k-block kb, chunk c (8 chunks of 8 bf16 per 128-byte k-block row)
+    const int chunks_per_row = d_pad >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * chunks_per_row) return;
+    const int64_t r = i / chunks_per_row;
+    const int cc = (int)(i - r * chunks_per_row);
+    const int kb = cc >> 3, c = cc & 7;
+    const int KB = d_pad >> 6;
+    const int64_t out = ((((r >> 8) * KB + kb) << 8) + (r & 255)) * 8 + c;
+    dst[out] = src[i];
+}
+
+void launch_tile_db16(const __nv_bfloat16* db16, __nv_bfloat16* db16t, int64_t n_pad, int d_pad, cudaStream_t st) {
+    const int64_t total = n_pad * (d_pad >> 3);
+    tile_db16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(db16), reinterpret_cast<uint4*>(db16t), n_pad, d_pad);
+}
+
 // ---- AQE query construction ------------------------------------------------------------------------
 // feature_enhancement of src/utils/Reranking.py:195-208 / :288-301 up to the re-score: for every query
 // take its kq best database rows, weight them ((kq-j)/kq)^w (j = 0 best), sum, divide by (norm + 1e-6).

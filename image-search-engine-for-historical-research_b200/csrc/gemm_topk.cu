@@ -16,6 +16,7 @@
 //   warps 2..5  epilogue       tcgen05.ld 32x32b.x32 -> filter -> lists; overlap the next tile's MMA
 // A job is (query tile, database split); jobs are dealt round-robin to the CTAs.
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "select.cuh"
 #include "internal.h"
@@ -150,7 +151,7 @@ template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
-                 int k, int k_keep, int cap, int sample_mode, const float* __restrict__ eps, const float* __restrict__ thr0,
+                 int k, int k_keep, int cap, int sample_mode, int db_tiled, uint64_t hint_db, const float* __restrict__ eps, const float* __restrict__ thr0,
                  uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -211,16 +212,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
                         const uint32_t full = smem_u32(&bars->full[stage]);
+                        // database operand coordinates: row-major [n_pad][d_pad] -> (k, row); tiled
+                        // [n_pad/256][d_pad/64][256][64] (every box one contiguous 16/32 KB run) -> (0, ((row/256)*KB + kb)*256 + row%256)
+                        const int brow = t * tile_stride * TILE_N + (PAIR ? (int)cta_rank * S::B_ROWS : 0);
+                        const int bc0 = db_tiled ? 0 : kb * GEMM_BK;
+                        const int bc1 = db_tiled ? (((brow >> 8) * k_blocks + kb) << 8) + (brow & 255) : brow;
                         if constexpr (PAIR) {
                             if (cta_rank == 0) mbar_expect_tx(full, 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
                             else mbar_arrive_remote(full, 0);
                             tma_load_2d_pair(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
-                            tma_load_2d_pair(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK,
-                                             t * tile_stride * TILE_N + (int)cta_rank * S::B_ROWS, HINT_EVICT_LAST);
+                            tma_load_2d_pair(smem_u32(sB + stage * B_BYTES), &tmap_db, full, bc0, bc1, HINT_EVICT_LAST);
                         } else {
                             mbar_expect_tx(full, STAGE_BYTES);
                             tma_load_2d(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
-                            tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, kb * GEMM_BK, t * tile_stride * TILE_N, HINT_EVICT_FIRST);
+                            tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, bc0, bc1, hint_db);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -476,8 +481,10 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     const int k_blocks = d_pad / GEMM_BK;
+    uint64_t hint_db = HINT_EVICT_FIRST;
+    if (const char* e = getenv("XS_EXP_HINT")) hint_db = (atoi(e) == 0) ? 0x1000000000000000ull : (atoi(e) == 2 ? HINT_EVICT_LAST : HINT_EVICT_FIRST);   // experiment knob
     return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, k_blocks,
-                              a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, eps, thr0,
+                              a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, plan.db_tiled, hint_db, eps, thr0,
                               pool_items, pool_count, pool_thr);
 }
 

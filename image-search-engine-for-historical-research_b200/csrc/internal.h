@@ -47,6 +47,10 @@ bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16,
 void launch_aqe_queries(const float* db32, const int64_t* top_ids, int64_t nq, int kq, double w, int64_t n, int d_pad,
                         float* q_out, cudaStream_t st);
 
+// Tiled copy of the bf16 database for the GEMM's B operand: [n_pad/256][d_pad/64][256][64], so that every TMA box
+// (128 or 256 rows x 64 columns) is one contiguous 16/32 KB run in HBM instead of 128-byte pieces 4 KB apart.
+void launch_tile_db16(const __nv_bfloat16* db16, __nv_bfloat16* db16t, int64_t n_pad, int d_pad, cudaStream_t st);
+
 // ---- scan.cu ------------------------------------------------------------------------------------
 // Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  Both scoring kernels also
 // add every score to ghist[q][score_key >> HIST_SHIFT] (zeroed by the caller).
@@ -70,6 +74,7 @@ struct GemmPlan {
     int k_keep;       // items kept by a mid-job trim
     int cap;          // capacity of one partial list (>= 2 * k_keep)
     int grid;         // CTAs launched
+    int db_tiled;     // 1: the database tensor map is over the tiled copy [n_pad/256][d_pad/64][256][64]
     int half;         // 1: 128-row database tiles, one CTA each, 6-stage ring (bootstrap pass; needs the box-128 database map)
     int pair;         // 1: cta_group::2 kernel, clusters of two CTAs, 256 x 256 tiles (needs the box-128 database map)
     int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)

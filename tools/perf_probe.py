@@ -50,7 +50,9 @@ def run(label, nq, reps=10, **params):
         ix.set_param(k_, {"sample_pass": 1}.get(k_, 0))
 
 
-run("gemm default (sample pass on)", Q, force_path=2)
+run("gemm default (sample pass on)", Q, reps=40, force_path=2)
+if len(sys.argv) > 3 and sys.argv[3] == "only_first":
+    sys.exit(0)
 run("gemm, no sample pass", Q, force_path=2, sample_pass=0)
 run("gemm default nq=1", 1, force_path=2)
 run("gemm default nq=16", 16, force_path=2)
