@@ -343,14 +343,13 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
 }
 
 // ---- split pipeline: rescore on every SM, then sort + emit ---------------------------------------------
-constexpr int RS_SPLIT = 16;                 // CTAs per query in the rescoring kernel
 constexpr int RS_WARPS = 8;
 
-// grid (nq, RS_SPLIT): warp w of CTA (q, j) rescores candidates j*RS_WARPS + w, + RS_SPLIT*RS_WARPS, ...
+// grid (nq, rs_split): warp w of CTA (q, j) rescores candidates j*RS_WARPS + w, + rs_split*RS_WARPS, ...
 // The row is staged with cp.async (16 B per lane and step, all steps issued back to back) so the whole
 // 8 KB row is in flight at once -- with register loads ptxas interleaves each load with its use and a
 // warp never has more than ~3 outstanding.  24 resident warps per SM -> ~190 KB in flight per SM.
-// The LAST of a query's RS_SPLIT CTAs to finish (atomic ticket) sorts the rescored candidates, applies
+// The LAST of a query's rs_split CTAs to finish (atomic ticket) sorts the rescored candidates, applies
 // the self-first rule and emits the first k -- no separate launch.
 __global__ void __launch_bounds__(RS_WARPS * 32)
 finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
@@ -364,7 +363,8 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
     const int warp = threadIdx.x >> 5, lane = lane_id();
     float* buf = rs_rows + (size_t)warp * a.d_pad;
     const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
-    for (int c = blockIdx.y * RS_WARPS + warp; c < ncand; c += RS_SPLIT * RS_WARPS) {
+    const int rs_split = gridDim.y;                     // CTAs per query: 16 for small batches (latency), 4 for large ones (launch count)
+    for (int c = blockIdx.y * RS_WARPS + warp; c < ncand; c += rs_split * RS_WARPS) {
         const uint32_t row = item_row(cand[c]);
         const float* v = a.db32 + (int64_t)row * a.d_pad;
         for (int i = lane * 4; i < a.d_pad; i += 128)
@@ -388,7 +388,7 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const int t = atomicAdd(&a.w_ticket[q], 1);
-        sh_last = (t == RS_SPLIT - 1) ? 1u : 0u;
+        sh_last = (t == rs_split - 1) ? 1u : 0u;
         if (sh_last) a.w_ticket[q] = 0;                 // ready for the next call
         sh_selfkey = 0;
     }
@@ -468,7 +468,8 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
         size_t rsm = (size_t)RS_WARPS * a.d_pad * sizeof(float);
         if (rsm < (size_t)cand_max * sizeof(uint64_t)) rsm = (size_t)cand_max * sizeof(uint64_t);
         if (rsm > 48 * 1024) cudaFuncSetAttribute(finalise_rescore_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-        launch_pdl(finalise_rescore_emit_kernel, dim3((unsigned)nq, RS_SPLIT), dim3(RS_WARPS * 32), rsm, st, a, cand_max);
+        const unsigned rs_split = nq <= 128 ? 16u : (nq <= 512 ? 8u : 4u);
+        launch_pdl(finalise_rescore_emit_kernel, dim3((unsigned)nq, rs_split), dim3(RS_WARPS * 32), rsm, st, a, cand_max);
     } else {
         cudaFuncSetAttribute(finalise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<false>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
