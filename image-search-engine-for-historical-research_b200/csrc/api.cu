@@ -233,8 +233,8 @@ extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int6
     int rc = index_alloc(ix, n, d, device, id_offset);
     if (rc != XS_OK) { index_free(ix); return rc; }
     const size_t es = dtype == XS_F64 ? 8 : 4;
-    const int64_t chunk = 8192;
-    rc = ix->stage.ensure((size_t)chunk * d * es);
+    const int64_t chunk = 32768;                       // rows per staged tile: 128 KB runs per column of an F-order fp32 source
+    rc = ix->stage.ensure((size_t)(n < chunk ? n : chunk) * d * es);
     for (int64_t r0 = 0; rc == XS_OK && r0 < n; r0 += chunk) {
         const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         rc = stage_host_rows(db, dtype, colmajor, colmajor ? stride_col : stride_row, r0, rows, d, ix->stage.p, ix->stream);
