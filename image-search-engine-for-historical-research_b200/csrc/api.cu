@@ -325,6 +325,7 @@ struct CoreArgs {
     int64_t a_row0;
     int64_t self_base;          // -1 or first database row of the queries
     int64_t* out_idx; float* out_score; int* status;   // device; pitch = k
+    int* ncand;                 // device counter of rescored candidates (nullptr: the index's own)
     int path;                   // PATH_*
 };
 
@@ -403,7 +404,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
     ix->stats.n_queries = nq; ix->stats.path = a.path;
     XS_TRY(ix->eps.ensure((size_t)nq * sizeof(float)));
     XS_TRY(ix->ncand.ensure(sizeof(int)));
-    CU_TRY(cudaMemsetAsync(ix->ncand.p, 0, sizeof(int), ix->cur));
+    int* const ncand = a.ncand ? a.ncand : ix->ncand.as<int>();
+    CU_TRY(cudaMemsetAsync(ncand, 0, sizeof(int), ix->cur));
     const bool timing = ix->timing != 0;            // CUDA events around the coarse kernel / the call (off: nothing between the launches)
     if (timing) CU_TRY(cudaEventRecord(ix->ev[0], ix->cur));
     ix->ev_valid = timing;
@@ -438,7 +440,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.P = P; fa.cap = cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad; fa.eps = ix->eps.as<float>() + q0;
             fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset; fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
-            fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
+            fa.status = a.status + q0; fa.n_cand = ncand; fa.out_pitch = k;
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
             XS_TRY(ensure_tickets(ix, c));
             fa.work = ix->fin_work.p; fa.ticket = ix->fin_ticket.as<int>();
@@ -498,7 +500,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.eps = ix->eps.as<float>() + q0; fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset;
             fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
             fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
-            fa.status = a.status + q0; fa.n_cand = ix->ncand.as<int>(); fa.out_pitch = k;
+            fa.status = a.status + q0; fa.n_cand = ncand; fa.out_pitch = k;
             XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
             XS_TRY(ensure_tickets(ix, c));
             fa.work = ix->fin_work.p; fa.ticket = ix->fin_ticket.as<int>();
@@ -547,22 +549,50 @@ static int rerun_uncertified(xs_index* ix, float* q32, int64_t nq, int k, int64_
 // Host-API epilogue: results + certificate bits land in pinned memory with ONE synchronisation;
 // uncertified queries (rare) are re-run on the exact path and re-copied; then a plain memcpy to the
 // caller's (possibly pageable) buffers.
+// One device buffer for everything a host call returns, so that ONE copy brings it back:
+//   [ids int64 nq*k | scores f32 nq*k | certificate bits int32 nq | candidate counter int32 (+ pad)]
+struct OutPack {
+    size_t off_score, off_status, off_ncand, bytes;
+    OutPack(int64_t nq, int k) {
+        off_score = (size_t)nq * k * sizeof(int64_t);
+        off_status = off_score + (size_t)nq * k * sizeof(float);
+        off_ncand = off_status + (size_t)nq * sizeof(int);
+        bytes = (off_ncand + sizeof(int) + 15) & ~(size_t)15;
+    }
+};
+
 static int finish_to_host(xs_index* ix, float* q32, int64_t nq, int k, int64_t self_base, int64_t* dev_idx, float* dev_score,
                           int* dev_status, bool coarse, int64_t* out_idx, float* out_score) {
     const size_t nb_i = (size_t)nq * k * sizeof(int64_t), nb_s = (size_t)nq * k * sizeof(float);
-    XS_TRY(ix->h_idx.ensure(nb_i));
+    const OutPack pk(nq, k);
+    // the caller laid its device results out as an OutPack starting at dev_idx (xs_search / xs_aqe_search do)
+    const bool packed = reinterpret_cast<char*>(dev_score) == reinterpret_cast<char*>(dev_idx) + pk.off_score &&
+                        reinterpret_cast<char*>(dev_status) == reinterpret_cast<char*>(dev_idx) + pk.off_status;
+    XS_TRY(ix->h_idx.ensure(packed ? pk.bytes : nb_i));
     XS_TRY(ix->h_score.ensure(nb_s));
     XS_TRY(ix->h_status.ensure((size_t)(nq + 1) * sizeof(int)));
-    CU_TRY(cudaMemcpyAsync(ix->h_idx.p, dev_idx, nb_i, cudaMemcpyDeviceToHost, ix->stream));
-    if (out_score) CU_TRY(cudaMemcpyAsync(ix->h_score.p, dev_score, nb_s, cudaMemcpyDeviceToHost, ix->stream));
-    if (coarse) {
-        CU_TRY(cudaMemcpyAsync(ix->h_status.as<int>() + 1, dev_status, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
-        CU_TRY(cudaMemcpyAsync(ix->h_status.p, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    int64_t* h_idx = ix->h_idx.as<int64_t>();
+    float* h_score = ix->h_score.as<float>();
+    int* h_status = ix->h_status.as<int>() + 1;
+    int* h_ncand = ix->h_status.as<int>();
+    if (packed) {
+        CU_TRY(cudaMemcpyAsync(ix->h_idx.p, dev_idx, pk.bytes, cudaMemcpyDeviceToHost, ix->stream));
+        char* base = static_cast<char*>(ix->h_idx.p);
+        h_score = reinterpret_cast<float*>(base + pk.off_score);
+        h_status = reinterpret_cast<int*>(base + pk.off_status);
+        h_ncand = reinterpret_cast<int*>(base + pk.off_ncand);
+    } else {
+        CU_TRY(cudaMemcpyAsync(h_idx, dev_idx, nb_i, cudaMemcpyDeviceToHost, ix->stream));
+        if (out_score) CU_TRY(cudaMemcpyAsync(h_score, dev_score, nb_s, cudaMemcpyDeviceToHost, ix->stream));
+        if (coarse) {
+            CU_TRY(cudaMemcpyAsync(h_status, dev_status, (size_t)nq * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+            CU_TRY(cudaMemcpyAsync(h_ncand, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+        }
     }
     CU_TRY(cudaStreamSynchronize(ix->stream));
     if (coarse) {
-        const int* st = ix->h_status.as<int>() + 1;
-        ix->stats.n_candidates = ix->h_status.as<int>()[0];
+        const int* st = h_status;
+        ix->stats.n_candidates = *h_ncand;
         int launches = 0;
         int64_t reruns = 0;
         for (int64_t q = 0; q < nq;) {
@@ -571,8 +601,8 @@ static int finish_to_host(xs_index* ix, float* q32, int64_t nq, int k, int64_t s
             while (e < nq && e - q < 16 && (st[e] & ST_UNCERTIFIED)) ++e;
             XS_TRY(run_exact(ix, q32 + q * ix->d_pad, e - q, k, self_base >= 0 ? self_base + q : -1, dev_idx + q * k,
                              dev_score + q * k, nullptr, &launches));
-            CU_TRY(cudaMemcpyAsync(ix->h_idx.as<int64_t>() + q * k, dev_idx + q * k, (size_t)(e - q) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
-            if (out_score) CU_TRY(cudaMemcpyAsync(ix->h_score.as<float>() + q * k, dev_score + q * k, (size_t)(e - q) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+            CU_TRY(cudaMemcpyAsync(h_idx + q * k, dev_idx + q * k, (size_t)(e - q) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+            if (out_score) CU_TRY(cudaMemcpyAsync(h_score + q * k, dev_score + q * k, (size_t)(e - q) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
             reruns += e - q;
             q = e;
         }
@@ -580,8 +610,8 @@ static int finish_to_host(xs_index* ix, float* q32, int64_t nq, int k, int64_t s
         ix->stats.n_exact_rerun = reruns;
         ix->stats.gpu_launches += launches;
     }
-    memcpy(out_idx, ix->h_idx.p, nb_i);
-    if (out_score) memcpy(out_score, ix->h_score.p, nb_s);
+    memcpy(out_idx, h_idx, nb_i);
+    if (out_score) memcpy(out_score, h_score, nb_s);
     return XS_OK;
 }
 
@@ -628,16 +658,17 @@ extern "C" int xs_search(xs_index* ix, const void* q, int dtype, int64_t nq, int
     const size_t es = dtype == XS_F64 ? 8 : 4;
     XS_TRY(ix->q_raw.ensure((size_t)nq * ix->d * es));
     XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
-    XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
-    XS_TRY(ix->out_idx.ensure((size_t)nq * k * sizeof(int64_t)));
-    XS_TRY(ix->out_score.ensure((size_t)nq * k * sizeof(float)));
+    const OutPack pk(nq, k);
+    XS_TRY(ix->out_idx.ensure(pk.bytes));                 // ids | scores | certificate bits | counter, copied back in one go
     XS_TRY(stage_host_rows(q, dtype, colmajor, colmajor ? stride_col : stride_row, 0, nq, ix->d, ix->q_raw.p, ix->stream));
     CoreArgs a{};
     int extra_launches = 0;
     if (dtype == XS_F32 && !colmajor) a.raw = ix->q_raw.as<float>();          // dense fp32 rows: prepared in one fused kernel
     else { launch_layout_rows(ix->q_raw.p, dtype, colmajor, colmajor ? nq : ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream); extra_launches = 1; }
     a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
-    a.self_base = -1; a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
+    char* const pack = static_cast<char*>(ix->out_idx.p);
+    a.self_base = -1; a.out_idx = reinterpret_cast<int64_t*>(pack); a.out_score = reinterpret_cast<float*>(pack + pk.off_score);
+    a.status = reinterpret_cast<int*>(pack + pk.off_status); a.ncand = reinterpret_cast<int*>(pack + pk.off_ncand);
     a.path = choose_path(ix, nq, k);
     XS_TRY(search_core(ix, a));
     ix->stats.gpu_launches += extra_launches;
