@@ -64,19 +64,44 @@ class ShardedSearcher:
         self.local_search = local_search
         self.merge = merge
         self._gathered = {}
+        # callbacks may take a result-slot argument (the CUDA shard does: two result buffers alternate)
+        import inspect
+        self._ls_slot = "slot" in inspect.signature(local_search).parameters
+        self._mg_slot = "slot" in inspect.signature(merge).parameters
 
     def search(self, queries, k: int):
+        """Blocking form: local exact top-k, one all-gather, merge.  Every rank returns the full answer."""
+        return self.search_async(queries, k).result()
+
+    def search_async(self, queries, k: int):
+        """Throughput form: enqueue the local search and START the all-gather, return a handle.  The
+        collective runs on NCCL's own stream, so the next batch's scan overlaps it; ``handle.result()``
+        makes the current stream wait for the gather and enqueues the merge.  Two result slots alternate,
+        so at most two searches may be in flight per searcher."""
         import torch
         nq = int(queries.shape[0])
-        packed = self.local_search(queries, k)
+        slot = self._slot = (getattr(self, "_slot", 1) + 1) & 1
+        packed = self.local_search(queries, k, slot) if self._ls_slot else self.local_search(queries, k)
         if self.world == 1:
-            return unpack(packed, nq, k)
-        key = (nq, k, packed.device)
+            return _Pending(self, None, packed, nq, k, slot)
+        key = (nq, k, packed.device, slot)
         if key not in self._gathered:
             self._gathered[key] = torch.empty((self.world * packed.numel(),), dtype=torch.uint8, device=packed.device)
         packed_all = self._gathered[key]
-        self.dist.all_gather_into_tensor(packed_all, packed, group=self.group)
-        return self.merge(packed_all, self.world, nq, k)
+        work = self.dist.all_gather_into_tensor(packed_all, packed, group=self.group, async_op=True)
+        return _Pending(self, work, packed_all, nq, k, slot)
+
+
+class _Pending:
+    def __init__(self, owner, work, buf, nq, k, slot):
+        self.owner, self.work, self.buf, self.nq, self.k, self.slot = owner, work, buf, nq, k, slot
+
+    def result(self):
+        if self.work is None:
+            return unpack(self.buf, self.nq, self.k)
+        self.work.wait()                                    # stream-level wait, the host does not block
+        o = self.owner
+        return o.merge(self.buf, o.world, self.nq, self.k, self.slot) if o._mg_slot else o.merge(self.buf, o.world, self.nq, self.k)
 
 
 def packed_bytes(nq: int, k: int) -> int:
@@ -103,9 +128,9 @@ class CudaShard:
         self.lib = nat.load()
         self._out = {}
 
-    def _buffers(self, nq, k):
+    def _buffers(self, nq, k, slot=0):
         torch = self.torch
-        key = (nq, k)
+        key = (nq, k, slot)
         if key not in self._out:
             dev = torch.device("cuda", self.device)
             packed = torch.empty((packed_bytes(nq, k),), dtype=torch.uint8, device=dev)
@@ -113,23 +138,24 @@ class CudaShard:
             self._out[key] = (ids, sims, torch.zeros((nq,), dtype=torch.int32, device=dev), packed)
         return self._out[key]
 
-    def local_search(self, queries, k):
-        """``queries``: fp32 row-major torch tensor on this rank's device.  Returns the packed result."""
+    def local_search(self, queries, k, slot=0):
+        """``queries``: fp32 row-major torch tensor on this rank's device.  Returns the packed result
+        (written into result slot ``slot``; two slots alternate while an all-gather is in flight)."""
         torch = self.torch
         nq = int(queries.shape[0])
-        ids, sims, status, packed = self._buffers(nq, k)
+        ids, sims, status, packed = self._buffers(nq, k, slot)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.index.search_device(queries.data_ptr(), nq, k, ids.data_ptr(), sims.data_ptr(),
                                  status_ptr=status.data_ptr(), stream=stream)
         return packed
 
     def uncertified(self, nq, k) -> int:
-        """Number of queries of the last local_search(nq, k) the bf16 pass could not certify."""
-        return int(self._buffers(nq, k)[2].sum().item())
+        """Number of queries of the last local searches (both slots) the bf16 pass could not certify."""
+        return int(self._buffers(nq, k, 0)[2].sum().item()) + int(self._buffers(nq, k, 1)[2].sum().item())
 
-    def merge(self, packed_all, world, nq, k):
+    def merge(self, packed_all, world, nq, k, slot=0):
         torch = self.torch
-        key = ("m", nq, k)
+        key = ("m", nq, k, slot)
         if key not in self._out:
             self._out[key] = (torch.empty((nq, k), dtype=torch.int64, device=packed_all.device),
                               torch.empty((nq, k), dtype=torch.float32, device=packed_all.device))
