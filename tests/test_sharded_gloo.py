@@ -49,7 +49,15 @@ def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
         return torch.from_numpy(i), torch.from_numpy(s)
 
     searcher = sharded.ShardedSearcher(local_search, merge)
-    ids, sims = searcher.search(torch.from_numpy(np.ascontiguousarray(qvecs.T)), k)
+    qt = torch.from_numpy(np.ascontiguousarray(qvecs.T))
+    # two searches in flight (the throughput form): the second one, on the reversed queries, must not disturb the first
+    h1 = searcher.search_async(qt, k)
+    h2 = searcher.search_async(torch.flip(qt, dims=[0]).contiguous(), k)
+    ids, sims = h1.result()
+    ids2, sims2 = h2.result()
+    assert torch.equal(torch.flip(ids2, dims=[0]), ids) and torch.equal(torch.flip(sims2, dims=[0]), sims)
+    ids_b, sims_b = searcher.search(qt, k)                # blocking form agrees
+    assert torch.equal(ids_b, ids) and torch.equal(sims_b, sims)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=ids.numpy(), sims=sims.numpy())
     dist.destroy_process_group()
 
