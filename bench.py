@@ -133,7 +133,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_rows = 125_875                               # 1/8 of the database per step (~1 GB fp32)
+    sample_rows = int(os.environ.get("XS_BENCH_REF_ROWS", "125875"))     # 1/8 of the database per step (~1 GB fp32)
     rng = np.random.default_rng(0)
     db = rng.standard_normal((sample_rows, DIM), dtype=np.float32)
     db /= np.linalg.norm(db, axis=1, keepdims=True)
