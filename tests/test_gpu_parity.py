@@ -401,3 +401,26 @@ def test_rank_ip_torch_device_tensors(pkg, synth, oracle):
     torch.testing.assert_close(scores, ref_scores[:25], rtol=1e-5, atol=1e-6)
     with pytest.raises(ValueError):
         pkg.rank_ip_torch(tv.cpu(), tq.cpu(), 5)
+
+
+def test_rank_all_many_queries_column_blocks(pkg, synth, oracle):
+    """More than 128 queries: xs_rank_all streams the [N, nq] result back in column blocks."""
+    v, q = synth.gaussian(700, 150, d=64)
+    with pkg.ExactIndex(v.T) as ix:
+        ranks, sc = ix.rank_all(q.T, return_scores=True)
+    assert ranks.shape == (700, 150)
+    _, ref = oracle.rank_ip(v, q)
+    s64 = oracle.scores_f64(v, q)
+    _check_lists(oracle, ranks.T, ref.T, s64, "rank_all 150 queries")
+    assert (np.diff(sc, axis=0) <= 0).all()
+
+
+def test_device_api_reruns_uncertified_itself(pkg, synth, oracle):
+    """xs_search_dev without a status buffer: duplicated rows defeat the certificate, the call re-runs
+    those queries exactly before returning (one stream synchronisation)."""
+    import torch
+    v, q = synth.ties(4096, 6, d=64, n_distinct=64)
+    scores, ranks = pkg.rank_ip_torch(torch.from_numpy(v).cuda(), torch.from_numpy(q).cuda(), 70)
+    rid, rs = oracle.topk_ip(v, q, 70)
+    np.testing.assert_array_equal(ranks.t().cpu().numpy(), rid)
+    np.testing.assert_allclose(scores.t().cpu().numpy(), rs, rtol=1e-5, atol=1e-7)
