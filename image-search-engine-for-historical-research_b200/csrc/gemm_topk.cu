@@ -481,8 +481,8 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     const int k_blocks = d_pad / GEMM_BK;
-    uint64_t hint_db = HINT_EVICT_FIRST;
-    if (const char* e = getenv("XS_EXP_HINT")) hint_db = (atoi(e) == 0) ? 0x1000000000000000ull : (atoi(e) == 2 ? HINT_EVICT_LAST : HINT_EVICT_FIRST);   // experiment knob
+    // streamed-once database tiles: evict-first measured 0.603 ms per pass against 0.642 ms with evict-normal / evict-last
+    const uint64_t hint_db = HINT_EVICT_FIRST;
     return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, k_blocks,
                               a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, plan.db_tiled, hint_db, eps, thr0,
                               pool_items, pool_count, pool_thr);
