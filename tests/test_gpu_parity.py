@@ -424,3 +424,32 @@ def test_device_api_reruns_uncertified_itself(pkg, synth, oracle):
     rid, rs = oracle.topk_ip(v, q, 70)
     np.testing.assert_array_equal(ranks.t().cpu().numpy(), rid)
     np.testing.assert_allclose(scores.t().cpu().numpy(), rs, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,nq,d,k", [(1, 1, 8, 1), (5, 3, 1, 5), (255, 2, 7, 3), (257, 130, 65, 9), (600, 4, 3000, 10)])
+def test_extreme_shapes(pkg, oracle, n, nq, d, k):
+    """Degenerate and awkward sizes: a single row, d = 1, sizes straddling the 256-row / 64-column padding,
+    descriptors longer than the 2048-wide fast paths."""
+    rng = np.random.default_rng(n * 1000 + d)
+    v = rng.standard_normal((d, n)).astype(np.float32)
+    q = rng.standard_normal((d, nq)).astype(np.float32)
+    rid, rs = oracle.topk_ip(v, q, k)
+    s64 = oracle.scores_f64(v, q)
+    with pkg.ExactIndex(v.T) as ix:
+        for path in (0, 1, 2, 3):
+            ix.set_param("force_path", path)
+            ids, sims = ix.search(q.T, k)
+            _check_lists(oracle, ids, rid, s64, f"shape {(n, nq, d, k)} path {path}")
+            np.testing.assert_allclose(sims, rs, rtol=2e-5, atol=1e-6)
+
+
+def test_many_queries_multiple_batches(pkg, synth, oracle):
+    """More queries than one internal batch (8192) through the host call."""
+    v, q = synth.gaussian(3000, 9000, d=64)
+    with pkg.ExactIndex(v.T) as ix:
+        ids, sims = ix.search(q.T, 5)
+    pick = np.array([0, 127, 128, 8191, 8192, 8999])
+    rid, rs = oracle.topk_ip(v, q[:, pick], 5)
+    s64 = oracle.scores_f64(v, q[:, pick])
+    _check_lists(oracle, ids[pick], rid, s64, "9000 queries")
+    np.testing.assert_allclose(sims[pick], rs, rtol=1e-5, atol=1e-7)
