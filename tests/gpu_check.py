@@ -1,6 +1,7 @@
-"""Diagnostic run on a GPU box: every path against the oracle on cfg1-sized inputs, verbose.
+"""Diagnostic run on a GPU box (lives under tests/ because it uses the oracle as its checker): every path
+against the oracle on cfg1-sized inputs, verbose.
 
-    python tools/gpu_check.py [scan|exact|gemm|all] [N] [Q] [D] [K]
+    python tests/gpu_check.py [scan|exact|gemm|all] [N] [Q] [D] [K]
 """
 import importlib
 import os
