@@ -8,8 +8,8 @@ kernel (xs_merge_candidates).  Rescoring needs no communication: a shard holds t
 its own candidates.
 
 The local searcher and the merge are injectable so that the sharding / id-offset / gather logic
-is covered by world_size-2 gloo tests on CPU, where the test passes the oracle in; the default
-is the CUDA path, and there is no automatic fallback.
+is covered by world_size-2 gloo tests on CPU, where the test passes the oracle's searcher and merge
+in; the product wiring (`CudaShard`) is CUDA only and there is no automatic fallback.
 """
 from __future__ import annotations
 
@@ -27,25 +27,6 @@ def shard_bounds(n_rows: int, world: int):
     for g in range(world):
         b.append(b[-1] + base + (1 if g < rem else 0))
     return b
-
-
-def merge_parts_host(ids_parts: np.ndarray, sims_parts: np.ndarray, k: int):
-    """Reference semantics of the merge kernel (descending score, ties by ascending id), used by
-    the CPU tests to check the CUDA merge: ``[G, nq, k] -> [nq, k]``."""
-    g, nq, kk = ids_parts.shape
-    ids = np.empty((nq, k), dtype=np.int64)
-    sims = np.empty((nq, k), dtype=np.float32)
-    for j in range(nq):
-        i = ids_parts[:, j, :].reshape(-1)
-        s = sims_parts[:, j, :].reshape(-1)
-        keep = i >= 0
-        i, s = i[keep], s[keep]
-        order = np.lexsort((i, -s.astype(np.float64)))[:k]
-        ids[j, :len(order)] = i[order]
-        sims[j, :len(order)] = s[order]
-        ids[j, len(order):] = -1
-        sims[j, len(order):] = -np.inf
-    return ids, sims
 
 
 class ShardedSearcher:

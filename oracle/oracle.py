@@ -246,6 +246,28 @@ def affinity_dense(sims, ids, gamma=3):
 
 
 # --------------------------------------------------------------------------------------
+# 8e -- merge of per-shard top-k lists (no reference counterpart: the reference is single-process)
+# --------------------------------------------------------------------------------------
+def merge_parts(ids_parts, sims_parts, k):
+    """Semantics the CUDA merge kernel must have: ``[G, nq, k] -> [nq, k]``, descending score, ties by
+    ascending id, entries with id < 0 (a shard with fewer than k rows) ignored."""
+    g, nq, kk = ids_parts.shape
+    ids = np.empty((nq, k), dtype=np.int64)
+    sims = np.empty((nq, k), dtype=np.float32)
+    for j in range(nq):
+        i = ids_parts[:, j, :].reshape(-1)
+        s = sims_parts[:, j, :].reshape(-1)
+        keep = i >= 0
+        i, s = i[keep], s[keep]
+        order = np.lexsort((i, -s.astype(np.float64)))[:k]
+        ids[j, :len(order)] = i[order]
+        sims[j, :len(order)] = s[order]
+        ids[j, len(order):] = -1
+        sims[j, len(order):] = -np.inf
+    return ids, sims
+
+
+# --------------------------------------------------------------------------------------
 # comparator used by every parity test
 # --------------------------------------------------------------------------------------
 def compare_topk(ids, ref_ids, score_of, rtol=1e-6, atol=1e-7):

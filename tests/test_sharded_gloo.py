@@ -45,7 +45,7 @@ def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
     def merge(packed_all, world_, nq_, kk):
         parts = [sharded.unpack(packed_all[g * sharded.packed_bytes(nq_, kk):(g + 1) * sharded.packed_bytes(nq_, kk)], nq_, kk)
                  for g in range(world_)]
-        i, s = sharded.merge_parts_host(np.stack([p[0].numpy() for p in parts]), np.stack([p[1].numpy() for p in parts]), kk)
+        i, s = oracle.merge_parts(np.stack([p[0].numpy() for p in parts]), np.stack([p[1].numpy() for p in parts]), kk)
         return torch.from_numpy(i), torch.from_numpy(s)
 
     searcher = sharded.ShardedSearcher(local_search, merge)
