@@ -21,7 +21,7 @@ PATH_AUTO, PATH_SCAN, PATH_GEMM, PATH_EXACT = 0, 1, 2, 3
 ABI_SYMBOLS = (
     "xs_last_error", "xs_abi_version", "xs_device_count", "xs_index_create", "xs_index_create_dev",
     "xs_index_destroy", "xs_index_info", "xs_index_stats", "xs_search", "xs_search_dev", "xs_self_knn",
-    "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn",
+    "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
 )
 
 
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
         lib.xs_merge_candidates.argtypes = [i32, p, p, i32, i64, i32, p, p, p]
         lib.xs_merge_candidates_strided.argtypes = [i32, p, p, i64, i64, i32, i64, i32, p, p, p]
         lib.xs_mutual_knn.argtypes = [i32, p, i64, i32, p]
+        lib.xs_diffusion_cg.argtypes = [i32, p, p, p, i64, p, i64, i32, i32, C.c_double, p]
         lib.xs_set_param.argtypes = [p, C.c_char_p, C.c_double]
         for name in ABI_SYMBOLS:
             if name != "xs_last_error":

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libxs_b200.so")
-SOURCES = ["api.cu", "build.cu", "scan.cu", "gemm_topk.cu", "finalise.cu", "sort.cu", "graph.cu"]
+SOURCES = ["api.cu", "build.cu", "scan.cu", "gemm_topk.cu", "finalise.cu", "sort.cu", "graph.cu", "diffusion.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

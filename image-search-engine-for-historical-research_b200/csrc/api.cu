@@ -5,6 +5,7 @@
 // (query copies, score rows, candidate pools, results).  One search = prep_queries -> coarse
 // kernel (batch-1 scan | tcgen05 GEMM with fused top-K) -> finalise (exact rescoring + sort),
 // all on one stream; uncertified queries are re-run on the exact fp32 path.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -869,6 +870,68 @@ extern "C" int xs_merge_candidates_strided(int device, const void* in_idx, const
     CU_TRY(cudaSetDevice(device));
     launch_merge_parts(in_idx, in_score, idx_part_stride, score_part_stride, n_parts, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream));
     CU_TRY(cudaGetLastError());
+    return XS_OK;
+}
+
+namespace {
+struct DevMem {                                   // scope-bound cudaMalloc for the one-shot entry points
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+}  // namespace
+
+extern "C" int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* indices, const float* values, int64_t n,
+                               const int64_t* trunc_ids, int64_t rows, int n_trunc, int maxiter, double tol,
+                               float* out_scores) {
+    if (!indptr || !indices || !values || !trunc_ids || !out_scores) return fail(XS_ERR_ARG, "null pointer");
+    if (n <= 0 || n > 0x7FFFFFFF || rows <= 0) return fail(XS_ERR_ARG, "bad sizes (n=%lld, rows=%lld)", (long long)n, (long long)rows);
+    if (n_trunc < 1 || n_trunc > 4096 || n_trunc > n) return fail(XS_ERR_ARG, "n_trunc must be in [1, min(n, 4096)] (got %d)", n_trunc);
+    if (maxiter < 0 || !(tol >= 0.0)) return fail(XS_ERR_ARG, "bad maxiter/tol");
+    if (indptr[0] != 0) return fail(XS_ERR_ARG, "indptr[0] must be 0");
+    int64_t maxdeg = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t d = indptr[i + 1] - indptr[i];
+        if (d < 0) return fail(XS_ERR_ARG, "indptr must be non-decreasing");
+        if (d > maxdeg) maxdeg = d;
+    }
+    const int64_t nnz = indptr[n];
+    const int T = n_trunc;
+    const int stride = (int)std::max<int64_t>(1, std::min<int64_t>(maxdeg, T));
+    CU_TRY(cudaSetDevice(device));
+    int grid = 0;
+    CU_TRY(diffusion_cg_grid(T, &grid));
+    const int64_t chunk = std::min<int64_t>(rows, 32768);
+    if ((int64_t)grid > chunk) grid = (int)chunk;
+    DevMem d_ptr, d_ind, d_val, d_ids64, d_ids32, d_out, d_cols, d_vals, d_bad;
+    cudaError_t e = d_ptr.alloc((size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = d_ind.alloc((size_t)nnz * 4);
+    if (e == cudaSuccess) e = d_val.alloc((size_t)nnz * 4);
+    if (e == cudaSuccess) e = d_ids64.alloc((size_t)chunk * T * 8);
+    if (e == cudaSuccess) e = d_ids32.alloc((size_t)chunk * T * 4);
+    if (e == cudaSuccess) e = d_out.alloc((size_t)chunk * T * 4);
+    if (e == cudaSuccess) e = d_cols.alloc((size_t)grid * T * stride * 2);
+    if (e == cudaSuccess) e = d_vals.alloc((size_t)grid * T * stride * 4);
+    if (e == cudaSuccess) e = d_bad.alloc(4);
+    if (e == cudaSuccess) e = cudaMemset(d_bad.p, 0, 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ptr.p, indptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(d_ind.p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(d_val.p, values, (size_t)nnz * 4, cudaMemcpyHostToDevice);
+    for (int64_t r0 = 0; e == cudaSuccess && r0 < rows; r0 += chunk) {
+        const int64_t rc = std::min<int64_t>(chunk, rows - r0);
+        e = cudaMemcpy(d_ids64.p, trunc_ids + r0 * T, (size_t)rc * T * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        launch_ids_to_i32(d_ids64.as<int64_t>(), d_ids32.as<int32_t>(), rc * T, nullptr);
+        e = launch_diffusion_cg(d_ptr.as<int64_t>(), d_ind.as<int32_t>(), d_val.as<float>(), n, d_ids32.as<int32_t>(), rc, T,
+                                stride, maxiter, tol, d_cols.as<uint16_t>(), d_vals.as<float>(), grid, d_out.as<float>(),
+                                d_bad.as<int>(), nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(out_scores + r0 * T, d_out.p, (size_t)rc * T * 4, cudaMemcpyDeviceToHost);
+    }
+    int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "xs_diffusion_cg: %s", cudaGetErrorString(e)); }
+    if (bad) return fail(XS_ERR_ARG, "trunc_ids holds an id outside [0, n)");
     return XS_OK;
 }
 

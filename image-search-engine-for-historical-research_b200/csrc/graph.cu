@@ -30,6 +30,10 @@ mutual_knn_kernel(const int32_t* __restrict__ ids, int64_t n, int kd, uint8_t* _
     }
 }
 
+void launch_ids_to_i32(const int64_t* ids64, int32_t* ids32, int64_t count, cudaStream_t st) {
+    ids_to_i32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(ids64, ids32, count);
+}
+
 void launch_mutual_knn(const int64_t* ids64, int32_t* ids32, int64_t n, int kd, uint8_t* mutual, cudaStream_t st) {
     const int64_t count = n * kd;
     ids_to_i32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(ids64, ids32, count);

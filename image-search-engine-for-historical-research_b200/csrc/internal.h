@@ -123,5 +123,12 @@ void launch_rank_all(const float* scores, int64_t pitch, int c, int64_t n, int q
 // ---- graph.cu -----------------------------------------------------------------------------------
 // mutual[i][j] = 1 iff j >= 1 and i is among the kd neighbours of ids[i][j]  (diffusion.py:107-108)
 void launch_mutual_knn(const int64_t* ids64, int32_t* ids32_scratch, int64_t n, int kd, uint8_t* mutual, cudaStream_t st);
+void launch_ids_to_i32(const int64_t* ids64, int32_t* ids32, int64_t count, cudaStream_t st);
+
+// diffusion.cu -- truncated CG solves (one CTA per database row)
+cudaError_t diffusion_cg_grid(int T, int* grid_out);
+cudaError_t launch_diffusion_cg(const int64_t* indptr, const int32_t* indices, const float* values, int64_t n,
+                                const int32_t* trunc_ids, int64_t rows, int T, int stride, int maxiter, double atol,
+                                uint16_t* s_cols, float* s_vals, int grid, float* out, int* bad, cudaStream_t st);
 
 }  // namespace xs

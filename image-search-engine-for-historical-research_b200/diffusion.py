@@ -5,7 +5,8 @@ src/utils/diffusion.py:67) and then decides mutual neighbourhood row by row in P
 (``get_affinity``, :101-116).  Here the kNN lists come from ``KNN.self_search`` (tcgen05 GEMM + fused
 top-K, a row's own id first) and the mutual test runs as one CUDA kernel (xs_mutual_knn); the sparse
 assembly and the normalised Laplacian keep the reference's scipy formulation (:87-98).  The per-row
-conjugate-gradient solves (:15-19, 74-76) are outside the exact-matching path and are not rebuilt.
+truncated conjugate-gradient solves (:15-19, 74-76) run on the GPU as well, one CTA per database row
+(xs_diffusion_cg); ``Diffusion`` strings the three together like the reference class does.
 """
 from __future__ import annotations
 
@@ -60,3 +61,84 @@ def knn_graph(features, n_trunc: int, kd: int = 50, device: int = 0):
     sims, ids = knn.self_search(n_trunc)
     lap = get_laplacian(sims[:, :kd].copy(), ids[:, :kd], device=device)
     return sims, ids, lap
+
+
+def offline_cg(lap, trunc_ids, tol: float = 1e-6, maxiter: int = 20, device: int = 0) -> np.ndarray:
+    """All rows of ``get_offline_result`` (diffusion.py:15-19) at once: for every row ``i`` solve
+    ``lap[ids][:, ids] x = e_0`` with ``ids = trunc_ids[i]`` by at most ``maxiter`` CG steps
+    (``linalg.cg(trunc_lap, trunc_init, tol=1e-6, maxiter=20)``).  Returns float32 ``(rows, n_trunc)``."""
+    import scipy.sparse as sparse
+    lap = sparse.csr_matrix(lap)
+    lap.sum_duplicates()
+    if lap.shape[0] != lap.shape[1]:
+        raise ValueError("the Laplacian must be square")
+    trunc_ids = np.ascontiguousarray(trunc_ids, dtype=np.int64)
+    if trunc_ids.ndim != 2:
+        raise ValueError("trunc_ids must be (rows, n_trunc)")
+    rows, n_trunc = trunc_ids.shape
+    indptr = np.ascontiguousarray(lap.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(lap.indices, dtype=np.int32)
+    values = np.ascontiguousarray(lap.data, dtype=np.float32)
+    out = np.empty((rows, n_trunc), dtype=np.float32)
+    nat.check(nat.load().xs_diffusion_cg(int(device), indptr.ctypes.data, indices.ctypes.data, values.ctypes.data,
+                                         lap.shape[0], trunc_ids.ctypes.data, rows, n_trunc, int(maxiter), float(tol),
+                                         out.ctypes.data), "xs_diffusion_cg")
+    return out
+
+
+class Diffusion(object):
+    """Mirror of ``src/utils/diffusion.py:42-116`` (exact-kNN branch; the ANN branch for N >= 110 000 exists in
+    the reference only because the exhaustive search was too slow -- here the exhaustive one is used at
+    every size).  ``features`` is ``(N, D)``; ``cache_dir`` may be None (no joblib cache)."""
+
+    def __init__(self, features, cache_dir=None, device: int = 0):
+        from .knn import KNN
+        self.features = np.asarray(features)
+        self.N = len(self.features)
+        self.cache_dir = cache_dir
+        self.device = device
+        self.knn = KNN(self.features, method="cosine", device=device)
+
+    def get_offline_results(self, n_trunc, kd=50):
+        """diffusion.py:52-85: self-kNN truncated at ``n_trunc``, Laplacian of the first ``kd`` neighbours,
+        one truncated CG per row, merged into an ``(N, N)`` float32 ``csr_matrix``."""
+        import os
+        import scipy.sparse as sparse
+        path = os.path.join(self.cache_dir, "offline.jbl") if self.cache_dir else None
+        if path and os.path.exists(path):
+            import joblib
+            return joblib.load(path)
+        sims, ids = self.knn.self_search(n_trunc)
+        lap_alpha = self.get_laplacian(sims[:, :kd].copy(), ids[:, :kd])
+        all_scores = offline_cg(lap_alpha, ids, device=self.device)
+        rows = np.repeat(np.arange(self.N), n_trunc)
+        offline = sparse.csr_matrix((all_scores.reshape(-1), (rows, ids.reshape(-1))), shape=(self.N, self.N),
+                                    dtype=np.float32)
+        if path:
+            import joblib
+            joblib.dump(offline, path)
+        return offline
+
+    def get_laplacian(self, sims, ids, alpha=0.99):
+        return get_laplacian(sims, ids, alpha=alpha, device=self.device)
+
+    def get_affinity(self, sims, ids, gamma=3):
+        return get_affinity(sims, ids, gamma=gamma, device=self.device)
+
+
+def search_offline(offline, sims, idx, n_trunc: int):
+    """The query side of the diffusion re-ranking (Reranking.py:243-256): per query, the ``sims ** 3``-weighted
+    sum of the offline rows of its ``k_query`` nearest database items, then the ``n_trunc`` best columns.
+    ``sims``/``idx`` are what ``diffusion.knn.search(qvecs.T, k_query)`` returned.  Returns
+    ``(truncation_scores f32 (Q, n_trunc), truncation_ranks int64 (Q, n_trunc))``; the caller transposes the
+    ranks like the reference (:258).  Host-side: 3 sparse rows per query."""
+    sims = np.asarray(sims) ** 3
+    nq = idx.shape[0]
+    out_s = np.empty((nq, n_trunc), dtype=np.float32)
+    out_r = np.empty((nq, n_trunc), dtype=np.int64)
+    for i in range(nq):
+        scores = np.asarray(sims[i] @ offline[idx[i]]).reshape(-1)
+        order = np.lexsort((np.arange(scores.size), -scores))[:n_trunc]
+        out_s[i] = scores[order]
+        out_r[i] = order
+    return out_s, out_r

@@ -168,6 +168,21 @@ XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const voi
 XS_API int xs_mutual_knn(int device, const int64_t* ids, int64_t n, int kd, uint8_t* out_mutual);
 
 /*
+ * Gallery-side diffusion: one truncated conjugate-gradient solve per database row.
+ *   replaces: get_offline_result (`lap_alpha[ids][:, ids]`, `linalg.cg(trunc_lap, trunc_init, tol=1e-6, maxiter=20)`)
+ *             src/utils/diffusion.py:15-19 and the joblib loop over all rows :74-76
+ * indptr/indices/values: HOST CSR of the n x n Laplacian (int64 / int32 / float32; canonical: no repeated
+ *   columns inside a row).  trunc_ids: HOST [rows, n_trunc] int64, each row's truncation set (distinct ids in
+ *   [0, n); slot 0 carries the right-hand side e_0 -- the row itself in the reference).  n_trunc <= 4096.
+ * Solves  L[ids][:, ids] x = e_0  from x0 = 0 with plain CG in fp64: stops before a step once
+ * ||r|| < tol (||b|| = 1), else returns the iterate after `maxiter` steps.  out_scores: HOST [rows, n_trunc]
+ * float32 (the dtype the reference stores them in, diffusion.py:81-83).
+ */
+XS_API int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* indices, const float* values, int64_t n,
+                           const int64_t* trunc_ids, int64_t rows, int n_trunc, int maxiter, double tol,
+                           float* out_scores);
+
+/*
  * Tunables (set before searching; all have safe defaults):
  *   "eps_sigmas"   float  width of the bf16 error band in standard deviations      (8.0)
  *   "scan_max_q"   int    largest batch served by the batch-1 HBM scan kernel      (1)

@@ -245,6 +245,43 @@ def affinity_dense(sims, ids, gamma=3):
     return a
 
 
+def cg_plain(a, b, tol=1e-6, maxiter=20):
+    """The solver behind ``linalg.cg(trunc_lap, trunc_init, tol=1e-6, maxiter=20)`` (diffusion.py:18; scipy is a
+    third-party dependency, ``scipy==1.9.0`` in requirements.txt:19): un-preconditioned conjugate gradients
+    from x0 = 0, fp64, stop before a step when ``||r|| < tol * ||b||``, else return the iterate after
+    ``maxiter`` steps.  tests/test_oracle_golden.py pins it against the scipy installed here."""
+    b = np.asarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    r = b.copy()
+    atol = tol * float(np.linalg.norm(b))
+    p = None
+    rho_prev = 1.0
+    for it in range(maxiter):
+        if np.linalg.norm(r) < atol:
+            break
+        rho = float(r @ r)
+        p = r.copy() if it == 0 else r + (rho / rho_prev) * p
+        q = a @ p
+        alpha = rho / float(p @ q)
+        x += alpha * p
+        r -= alpha * q
+        rho_prev = rho
+    return x
+
+
+def offline_scores(lap, trunc_ids, tol=1e-6, maxiter=20):
+    """``get_offline_result`` for every row (diffusion.py:15-19, 74-76): ``lap[ids][:, ids]`` then CG on e_0."""
+    lap = lap.tocsr()
+    trunc_ids = np.asarray(trunc_ids)
+    out = np.empty(trunc_ids.shape, dtype=np.float64)
+    e0 = np.zeros(trunc_ids.shape[1])
+    e0[0] = 1
+    for i in range(trunc_ids.shape[0]):
+        ids = trunc_ids[i]
+        out[i] = cg_plain(lap[ids][:, ids], e0, tol, maxiter)
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # 8e -- merge of per-shard top-k lists (no reference counterpart: the reference is single-process)
 # --------------------------------------------------------------------------------------

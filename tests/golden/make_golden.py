@@ -132,6 +132,28 @@ def main():
     out["F_affinity"] = aff.toarray()
     out["F_laplacian"] = np.asarray(lap.toarray(), dtype=np.float32)
 
+    # --- case G: gallery-side diffusion -- get_offline_result (diffusion.py:15-19) lifted as is.  The one
+    # adaptation: the reference pins scipy 1.9 whose cg takes `tol=`; the scipy installed here (>= 1.14)
+    # renamed it `rtol`, so the `linalg` name the lifted body sees forwards tol -> rtol (same criterion,
+    # ||r|| <= tol * ||b||). ---
+    import scipy.sparse.linalg as sp_linalg
+
+    class _Linalg:
+        @staticmethod
+        def cg(a, b, tol=1e-5, maxiter=None):
+            return sp_linalg.cg(a, b, rtol=tol, atol=0.0, maxiter=maxiter)
+    n_trunc, kd = 40, 12
+    sims40, ids40 = oracle.knn_search(v.T, v.T, n_trunc, "cosine")
+    lap_g = ns["get_laplacian"](_Self(), sims40[:, :kd].copy(), ids40[:, :kd])
+    trunc_init = np.zeros(n_trunc)
+    trunc_init[0] = 1
+    gns = {"np": np, "linalg": _Linalg, "trunc_ids": ids40, "trunc_init": trunc_init, "lap_alpha": lap_g}
+    gfn = [n for n in ast.parse(dsrc).body if isinstance(n, ast.FunctionDef) and n.name == "get_offline_result"][0]
+    exec(compile(ast.get_source_segment(dsrc, gfn), "diffusion.py:get_offline_result", "exec"), gns)
+    out["G_trunc_ids"] = ids40.astype(np.int32)
+    out["G_trunc_sims"] = sims40
+    out["G_offline"] = np.stack([gns["get_offline_result"](i) for i in range(400)])
+
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     for k, a in out.items():
         print(f"{k:28s} {str(a.dtype):8s} {a.shape}")

@@ -361,6 +361,48 @@ def test_diffusion_graph(pkg, synth, oracle, golden):
     assert lap2.shape == (400, 400)
 
 
+def test_diffusion_offline_cg(pkg, synth, oracle, golden):
+    """Gallery-side truncated CG (diffusion.py:15-19, 74-76): the CUDA solver vs the reference's own output
+    (case G), vs the oracle on a second graph, and the Diffusion class end to end."""
+    import scipy.sparse as sparse
+    lap = sparse.csr_matrix(golden["F_laplacian"])
+    ids = golden["G_trunc_ids"].astype(np.int64)
+    got = pkg.diffusion.offline_cg(lap, ids)
+    assert got.dtype == np.float32 and got.shape == ids.shape
+    np.testing.assert_allclose(got, golden["G_offline"], rtol=2e-6, atol=1e-8)
+    # fewer steps / early stop / a subset of rows in another order
+    np.testing.assert_allclose(pkg.diffusion.offline_cg(lap, ids[::-7], maxiter=3),
+                               oracle.offline_scores(lap, ids[::-7], maxiter=3), rtol=2e-6, atol=1e-8)
+    np.testing.assert_allclose(pkg.diffusion.offline_cg(lap, ids[:50], tol=1e-2),
+                               oracle.offline_scores(lap, ids[:50], tol=1e-2), rtol=2e-6, atol=1e-8)
+    np.testing.assert_array_equal(pkg.diffusion.offline_cg(lap, ids[:5], maxiter=0), np.zeros((5, 40), np.float32))
+    # a denser, larger problem: truncation sets of 300 out of 3000 rows, 30 neighbours in the graph
+    v, _ = synth.clustered(3000, 1, d=64, n_clusters=40, noise=0.8)[:2]
+    d = pkg.diffusion.Diffusion(v.T, None)
+    sims, tids = d.knn.self_search(300)
+    lap2 = d.get_laplacian(sims[:, :30].copy(), tids[:, :30])
+    pick = np.arange(0, 3000, 97)
+    np.testing.assert_allclose(pkg.diffusion.offline_cg(lap2, tids[pick]), oracle.offline_scores(lap2, tids[pick]),
+                               rtol=5e-6, atol=1e-8)
+    offline = d.get_offline_results(300, 30)
+    assert offline.shape == (3000, 3000) and offline.dtype == np.float32
+    np.testing.assert_allclose(np.asarray(offline[pick[3]].todense()).reshape(-1)[tids[pick[3]]],
+                               oracle.offline_scores(lap2, tids[pick[3:4]])[0], rtol=5e-6, atol=1e-8)
+    qs, qi = d.knn.search(v.T[:4], 3)
+    ts, tr = pkg.diffusion.search_offline(offline, qs, qi, 300)
+    for i in range(4):                                         # Reranking.py:251-255 on a dense row
+        dense = (qs[i].astype(np.float32) ** 3) @ offline[qi[i]].toarray()
+        np.testing.assert_allclose(ts[i], np.sort(dense)[::-1][:300], rtol=1e-6)
+        np.testing.assert_allclose(dense[tr[i]], ts[i], rtol=1e-6)
+        assert len(set(tr[i].tolist())) == 300
+    with pytest.raises(ValueError):
+        bad = ids[:3].copy()
+        bad[1, 5] = 400
+        pkg.diffusion.offline_cg(lap, bad)
+    with pytest.raises(ValueError):
+        pkg.diffusion.offline_cg(lap, np.zeros((2, 5000), np.int64))
+
+
 def test_self_knn_pipelined_batches_and_reruns(pkg, synth, oracle):
     """More rows than one 8192-row batch (two-deep pipeline) and duplicated rows (certificate fails ->
     exact re-run inside the pipeline): every row still gets its own id first and exact neighbours."""

@@ -109,3 +109,30 @@ def test_diffusion_affinity(oracle, golden):
     ids, sims = golden["F_knn_ids"].astype(np.int64), golden["F_knn_sims"]
     np.testing.assert_array_equal(oracle.affinity_dense(sims.copy(), ids), golden["F_affinity"])
     assert golden["F_affinity"].any() and (golden["F_affinity"] != golden["F_affinity"].T).any() is not None
+
+
+def test_offline_cg_matches_reference(oracle, golden):
+    """Case G: the truncated CG restatement against get_offline_result (diffusion.py:15-19) run on scipy."""
+    import scipy.sparse as sparse
+    lap = sparse.csr_matrix(golden["F_laplacian"])
+    ids = golden["G_trunc_ids"].astype(np.int64)
+    np.testing.assert_array_equal(ids[:, :12], golden["F_knn_ids"])        # the Laplacian's lists are the prefix
+    got = oracle.offline_scores(lap, ids)
+    np.testing.assert_allclose(got, golden["G_offline"], rtol=1e-9, atol=1e-12)
+    assert (golden["G_offline"][:, 0] > 0.5).all()                          # the row's own score dominates
+
+
+def test_cg_plain_early_stop_matches_scipy(oracle):
+    """Well-conditioned system: the stopping rule fires before maxiter, same iterate as scipy's cg."""
+    import scipy.sparse.linalg as linalg
+    rng = np.random.default_rng(3)
+    m = rng.standard_normal((30, 30))
+    a = np.eye(30) + 0.01 * (m @ m.T)
+    b = np.zeros(30)
+    b[0] = 1
+    want, info = linalg.cg(a, b, rtol=1e-6, atol=0.0, maxiter=20)
+    assert info == 0
+    np.testing.assert_allclose(oracle.cg_plain(a, b, 1e-6, 20), want, rtol=1e-12, atol=1e-15)
+    want2, info2 = linalg.cg(a, b, rtol=1e-6, atol=0.0, maxiter=2)          # cut short
+    assert info2 == 2
+    np.testing.assert_allclose(oracle.cg_plain(a, b, 1e-6, 2), want2, rtol=1e-12, atol=1e-15)
