@@ -13,3 +13,7 @@ if _root not in _sys.path:
 _pkg = _importlib.import_module("image-search-engine-for-historical-research_b200")
 globals().update({name: getattr(_pkg, name) for name in _pkg.__all__})
 __all__ = list(_pkg.__all__)
+# `from xs_b200.diffusion import Diffusion` etc.: alias the already-loaded submodules (no second copy is imported)
+for _name, _mod in list(_sys.modules.items()):
+    if _name.startswith(_pkg.__name__ + "."):
+        _sys.modules[__name__ + _name[len(_pkg.__name__):]] = _mod
