@@ -13,8 +13,10 @@ from .index import ExactIndex
 from .knn import KNN, BaseKNN
 from .nnsearch import matching, matching_L2, cached_index, clear_index_cache
 from .ranking import rank_ip, rank_ip_torch
-from .reranking import feature_enhancement, qge1
+from .reranking import (feature_enhancement, qge1, average_query_expansion, database_augmentation,
+                        initial_rank)
 from . import diffusion, store
 
 __all__ = ["ExactIndex", "KNN", "BaseKNN", "matching", "matching_L2", "rank_ip", "rank_ip_torch",
-           "cached_index", "clear_index_cache", "feature_enhancement", "qge1", "diffusion", "store"]
+           "cached_index", "clear_index_cache", "feature_enhancement", "qge1", "average_query_expansion",
+           "database_augmentation", "initial_rank", "diffusion", "store"]

@@ -245,6 +245,48 @@ def affinity_dense(sims, ids, gamma=3):
     return a
 
 
+# --------------------------------------------------------------------------------------
+# 8f-4 -- average query expansion / database augmentation     src/utils/Reranking.py:314-365, 375-440
+# --------------------------------------------------------------------------------------
+def _db_postprocess(query_vecs, reference_vecs):
+    """``postprocess`` (Reranking.py:326-332 / :387-398): move the origin to the mean of all rows of both
+    sets, then L2-normalise each set (left untouched when it holds a zero row, :322-324)."""
+    center = np.mean(np.concatenate([query_vecs, reference_vecs], axis=0), axis=0)
+    out = []
+    for v in (query_vecs - center, reference_vecs - center):
+        norm = np.expand_dims(np.linalg.norm(v, axis=1), axis=1)
+        out.append(v if np.any(norm == 0) else v / norm)
+    return out[0], out[1]
+
+
+def _db_sim_order(query_vecs, reference_vecs):
+    """``calculate_sim_matrix`` + ``np.argsort(sim_mat, axis=1)`` (Reranking.py:334-345)."""
+    q, r = _db_postprocess(query_vecs, reference_vecs)
+    return np.argsort(2 - 2 * np.dot(q, r.T), axis=1)
+
+
+def average_query_expansion(qvecs, vecs, K, top_k=3):
+    """Reranking.py:339-358 without the printing: returns ``(ranks (K, Q), vecs_aug (N, 2D), qvecs_aug (Q, 2D))``."""
+    indices = _db_sim_order(qvecs.T, vecs.T)
+    q_aug = np.concatenate([qvecs.T, np.mean(vecs.T[indices[:, :top_k], :], axis=1)], axis=1)
+    indices = _db_sim_order(vecs.T, vecs.T)
+    v_aug = np.concatenate([vecs.T, np.mean(vecs.T[indices[:, 1:top_k + 1], :], axis=1)], axis=1)
+    idx, _ = matching_L2(K, v_aug, q_aug)
+    return idx.T, v_aug, q_aug
+
+
+def database_augmentation(qvecs, vecs, K, top_k=3):
+    """Reranking.py:404-431 without the printing: returns ``(ranks (K, Q), vecs_aug (N, D), qvecs_aug (Q, D))``."""
+    weights = np.logspace(0, -2., top_k + 1)
+    indices = _db_sim_order(qvecs.T, vecs.T)
+    top_k_ref = vecs.T[indices[:, :top_k], :]
+    q_aug = np.tensordot(weights, np.concatenate([np.expand_dims(qvecs.T, 1), top_k_ref], axis=1), axes=(0, 1))
+    indices = _db_sim_order(vecs.T, vecs.T)
+    v_aug = np.tensordot(weights, vecs.T[indices[:, :top_k + 1], :], axes=(0, 1))
+    idx, _ = matching_L2(K, v_aug, q_aug)
+    return idx.T, v_aug, q_aug
+
+
 def cg_plain(a, b, tol=1e-6, maxiter=20):
     """The solver behind ``linalg.cg(trunc_lap, trunc_init, tol=1e-6, maxiter=20)`` (diffusion.py:18; scipy is a
     third-party dependency, ``scipy==1.9.0`` in requirements.txt:19): un-preconditioned conjugate gradients

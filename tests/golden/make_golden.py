@@ -154,6 +154,18 @@ def main():
     out["G_trunc_sims"] = sims40
     out["G_offline"] = np.stack([gns["get_offline_result"](i) for i in range(400)])
 
+    # --- case H: average query expansion / database augmentation (Reranking.py:314-365, 375-440), lifted whole.
+    # They print their mAP instead of returning the ranks, so the `compute_map_and_print2` name they call is a
+    # recorder; `matching_L2` is the reference's own function lifted above. ---
+    v, q, _ = synth.clustered(600, 8, d=64, n_clusters=20, noise=1.2, spread=0.5)
+    for name in ("average_query_expansion", "database_augmentation"):
+        fn = lift_function(f"{REF}/src/utils/Reranking.py", name)
+        seen = {}
+        fn.__globals__.update(matching_L2=ref_matching_L2, print=lambda *a, **k: None,
+                              compute_map_and_print2=lambda dataset, ranks, gnd: seen.setdefault("ranks", ranks))
+        fn(q.copy(), v.copy(), 20, "synthetic", None)
+        out[f"H_{name}_ranks"] = seen["ranks"].astype(np.int32)
+
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     for k, a in out.items():
         print(f"{k:28s} {str(a.dtype):8s} {a.shape}")

@@ -403,6 +403,28 @@ def test_diffusion_offline_cg(pkg, synth, oracle, golden):
         pkg.diffusion.offline_cg(lap, np.zeros((2, 5000), np.int64))
 
 
+def test_query_expansion_and_database_augmentation(pkg, synth, oracle, golden):
+    """average_query_expansion / database_augmentation (Reranking.py:314-365, 375-440) through top-k searches
+    instead of N x N argsorts, vs the reference's own ranks (case H); initial_rank = batch_torch_topk (:487-511)."""
+    v, q, _ = synth.clustered(600, 8, d=64, n_clusters=20, noise=1.2, spread=0.5)
+    for name in ("average_query_expansion", "database_augmentation"):
+        got = getattr(pkg, name)(q, v, 20, "synthetic", None)
+        assert got.shape == (20, 8) and got.dtype == np.int64
+        _, v_aug, q_aug = getattr(oracle, name)(q, v, 20)
+        s64 = oracle.scores_f64((v_aug / np.linalg.norm(v_aug, axis=1, keepdims=True)).T,
+                                (q_aug / np.linalg.norm(q_aug, axis=1, keepdims=True)).T)
+        _check_lists(oracle, got.T, golden[f"H_{name}_ranks"].T.astype(np.int64), s64, name)
+    feat = np.ascontiguousarray(np.concatenate([q, v], axis=1).T)
+    got = pkg.initial_rank(feat, 7)
+    dist = 2 - 2 * feat.astype(np.float64) @ feat.astype(np.float64).T
+    dist = (dist / dist.max(axis=0)).T                                    # the reference's per-row rescale
+    want = np.argsort(dist, axis=1, kind="stable")[:, :7]
+    assert (got[:, 0] == np.arange(608)).all()
+    _check_lists(oracle, got[:, 1:], want[:, 1:], -dist.T, "initial_rank")
+    import torch
+    np.testing.assert_array_equal(pkg.initial_rank(torch.from_numpy(feat), 7), got)
+
+
 def test_self_knn_pipelined_batches_and_reruns(pkg, synth, oracle):
     """More rows than one 8192-row batch (two-deep pipeline) and duplicated rows (certificate fails ->
     exact re-run inside the pipeline): every row still gets its own id first and exact neighbours."""

@@ -136,3 +136,12 @@ def test_cg_plain_early_stop_matches_scipy(oracle):
     want2, info2 = linalg.cg(a, b, rtol=1e-6, atol=0.0, maxiter=2)          # cut short
     assert info2 == 2
     np.testing.assert_allclose(oracle.cg_plain(a, b, 1e-6, 2), want2, rtol=1e-12, atol=1e-15)
+
+
+def test_query_expansion_and_database_augmentation(oracle, synth, golden):
+    """Case H: the N x N argsort re-rankers (Reranking.py:314-365, 375-440) restated vs the lifted originals."""
+    v, q, _ = synth.clustered(600, 8, d=64, n_clusters=20, noise=1.2, spread=0.5)
+    for name in ("average_query_expansion", "database_augmentation"):
+        ranks, v_aug, q_aug = getattr(oracle, name)(q, v, 20)
+        np.testing.assert_array_equal(ranks, golden[f"H_{name}_ranks"])
+        assert v_aug.shape == (600, 128 if name.startswith("average") else 64) and q_aug.shape[0] == 8
