@@ -22,6 +22,7 @@ ABI_SYMBOLS = (
     "xs_last_error", "xs_abi_version", "xs_device_count", "xs_index_create", "xs_index_create_dev",
     "xs_index_destroy", "xs_index_info", "xs_index_stats", "xs_search", "xs_search_dev", "xs_self_knn",
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
+    "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
 )
 
 
@@ -66,6 +67,11 @@ def load() -> C.CDLL:
         lib.xs_mutual_knn.argtypes = [i32, p, i64, i32, p]
         lib.xs_diffusion_cg.argtypes = [i32, p, p, p, i64, p, i64, i32, i32, C.c_double, p]
         lib.xs_set_param.argtypes = [p, C.c_char_p, C.c_double]
+        lib.xs_exchange_create.argtypes = [i32, i32, i32, i64, C.POINTER(p), p]
+        lib.xs_exchange_connect.argtypes = [p, p]
+        lib.xs_exchange_push.argtypes = [p, p, i64, i32, p]
+        lib.xs_exchange_merge.argtypes = [p, i32, i64, i32, p, p, p]
+        lib.xs_exchange_destroy.argtypes = [p]
         for name in ABI_SYMBOLS:
             if name != "xs_last_error":
                 getattr(lib, name).restype = i32

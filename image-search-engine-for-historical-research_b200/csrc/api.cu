@@ -873,6 +873,112 @@ extern "C" int xs_merge_candidates_strided(int device, const void* in_idx, const
     return XS_OK;
 }
 
+// ---- peer exchange: per-shard result lists pushed into every rank's mailbox over NVLink peer mappings --------
+struct xs_exchange {
+    int device = 0, world = 1, rank = 0;
+    int64_t part_bytes = 0;                       // mailbox bytes per (slot, sender), multiple of 16
+    char* local = nullptr;                        // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
+    char* peer[XCHG_MAX_WORLD] = {};              // every rank's mailbox as mapped here (peer[rank] == local)
+    bool connected = false;
+    uint32_t push_epoch[2] = {0, 0}, merge_epoch[2] = {0, 0};
+    static constexpr size_t FLAGS_OFF = 0, ACKS_OFF = 2 * XCHG_MAX_WORLD * 4, TICKET_OFF = 4 * XCHG_MAX_WORLD * 4, DATA_OFF = 512;
+    size_t total() const { return DATA_OFF + (size_t)2 * world * part_bytes; }
+};
+
+extern "C" int xs_exchange_create(int device, int world, int rank, int64_t part_bytes, xs_exchange** out, unsigned char* handle_out) {
+    if (!out || !handle_out) return fail(XS_ERR_ARG, "null pointer");
+    if (world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return fail(XS_ERR_ARG, "bad world/rank (%d/%d, at most %d ranks)", rank, world, XCHG_MAX_WORLD);
+    if (part_bytes <= 0 || part_bytes % 16) return fail(XS_ERR_ARG, "part_bytes must be a positive multiple of 16");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    CU_TRY(cudaSetDevice(device));
+    xs_exchange* ex = new xs_exchange();
+    ex->device = device; ex->world = world; ex->rank = rank; ex->part_bytes = part_bytes;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->local), ex->total());
+    if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->total());
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ex->local);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (ex->local) cudaFree(ex->local);
+        delete ex;
+        return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "xs_exchange_create: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    ex->peer[rank] = ex->local;
+    *out = ex;
+    return XS_OK;
+}
+
+extern "C" int xs_exchange_connect(xs_exchange* ex, const unsigned char* handles) {
+    if (!ex || !handles) return fail(XS_ERR_ARG, "null pointer");
+    if (ex->connected) return fail(XS_ERR_ARG, "already connected");
+    CU_TRY(cudaSetDevice(ex->device));
+    for (int g = 0; g < ex->world; ++g) {
+        if (g == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)g * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < g; ++j) if (j != ex->rank && ex->peer[j]) { cudaIpcCloseMemHandle(ex->peer[j]); ex->peer[j] = nullptr; }
+            return fail(XS_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+        }
+        ex->peer[g] = static_cast<char*>(p);
+    }
+    ex->connected = true;
+    return XS_OK;
+}
+
+extern "C" int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t bytes, int slot, void* stream) {
+    if (!ex || !packed_dev) return fail(XS_ERR_ARG, "null pointer");
+    if (!ex->connected && ex->world > 1) return fail(XS_ERR_ARG, "exchange not connected");
+    if (slot < 0 || slot > 1 || bytes <= 0 || bytes % 16 || bytes > ex->part_bytes) return fail(XS_ERR_ARG, "bad slot/bytes (%d, %lld of %lld)", slot, (long long)bytes, (long long)ex->part_bytes);
+    CU_TRY(cudaSetDevice(ex->device));
+    PushArgs a{};
+    for (int g = 0; g < ex->world; ++g) {
+        a.dst[g] = ex->peer[g] + xs_exchange::DATA_OFF + ((size_t)slot * ex->world + ex->rank) * ex->part_bytes;
+        a.flag[g] = reinterpret_cast<uint32_t*>(ex->peer[g] + xs_exchange::FLAGS_OFF) + slot * XCHG_MAX_WORLD + ex->rank;
+    }
+    a.my_acks = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD;
+    a.epoch = ++ex->push_epoch[slot];
+    launch_exchange_push(packed_dev, bytes, a, ex->world, static_cast<cudaStream_t>(stream));
+    CU_TRY(cudaGetLastError());
+    return XS_OK;
+}
+
+extern "C" int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64_t* out_idx, float* out_score, void* stream) {
+    if (!ex || !out_idx) return fail(XS_ERR_ARG, "null pointer");
+    if (slot < 0 || slot > 1 || nq <= 0 || k <= 0 || nq * k * 12 > ex->part_bytes) return fail(XS_ERR_ARG, "bad slot/sizes");
+    if ((int64_t)ex->world * k > 16384) return fail(XS_ERR_UNSUPPORTED, "world*k = %lld > 16384", (long long)ex->world * k);
+    if (ex->merge_epoch[slot] >= ex->push_epoch[slot]) return fail(XS_ERR_ARG, "merge of slot %d without a matching push", slot);
+    CU_TRY(cudaSetDevice(ex->device));
+    MergeSync ms{};
+    ms.flags = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::FLAGS_OFF) + slot * XCHG_MAX_WORLD;
+    ms.ticket = reinterpret_cast<uint32_t*>(ex->local + xs_exchange::TICKET_OFF) + slot;
+    for (int g = 0; g < ex->world; ++g)
+        ms.ack[g] = reinterpret_cast<uint32_t*>(ex->peer[g] + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD + ex->rank;
+    ms.epoch = ++ex->merge_epoch[slot];
+    const char* base = ex->local + xs_exchange::DATA_OFF + (size_t)slot * ex->world * ex->part_bytes;
+    launch_merge_parts(base, base + nq * k * 8, ex->part_bytes, ex->part_bytes, ex->world, nq, k, out_idx, out_score,
+                       static_cast<cudaStream_t>(stream), &ms);
+    CU_TRY(cudaGetLastError());
+    return XS_OK;
+}
+
+extern "C" int xs_exchange_destroy(xs_exchange* ex) {
+    if (!ex) return XS_OK;
+    cudaSetDevice(ex->device);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < ex->world; ++g)
+        if (g != ex->rank && ex->peer[g]) cudaIpcCloseMemHandle(ex->peer[g]);
+    if (ex->local) cudaFree(ex->local);
+    cudaGetLastError();
+    delete ex;
+    return XS_OK;
+}
+
 namespace {
 struct DevMem {                                   // scope-bound cudaMalloc for the one-shot entry points
     void* p = nullptr;

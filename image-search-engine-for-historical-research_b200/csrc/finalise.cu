@@ -5,6 +5,7 @@
 // (fp32 operands, fp64 accumulation in a fixed order, one rounding to fp32 -- the deterministic
 // stand-in for OpenBLAS' sgemm at src/main_retrieve.py:175), (4) sort by (score desc, id asc),
 // (5) emit the first k, plus a certificate bit when anything outside the band may have been lost.
+#include <cstdio>
 #include "common.cuh"
 #include "select.cuh"
 #include "internal.h"
@@ -525,14 +526,40 @@ void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, 
 }
 
 // ---- multi-GPU merge -------------------------------------------------------------------------------
+// ---- peer-exchange handshake words (system scope: written by kernels running on OTHER GPUs over NVLink) ----
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// Spin until *p >= want.  A peer that never arrives is a protocol error: trap after ~20 s instead of hanging the GPU.
+__device__ __forceinline__ void wait_word_sys(const uint32_t* p, uint32_t want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        __nanosleep(64);
+        if (clock64() - t0 > 40000000000ll) { printf("xs: peer exchange timed out (want %u, have %u)\n", want, ld_acquire_sys(p)); __trap(); }
+    }
+}
+
 // in: [parts][nq][k] (score desc, id asc inside every part; parts own increasing id ranges, so the
 // flat position p*k + r orders equal scores by ascending id).  One CTA per query.
+// With sync.flags set this is the receiving end of the peer exchange: part p was written into this GPU's
+// mailbox by rank p's push kernel, which then released flags[p] = epoch; the last CTA to finish reading
+// acknowledges the epoch to every peer (their next push into this mailbox slot waits for it).
 __global__ void __launch_bounds__(512)
-merge_parts_kernel(const char* __restrict__ in_idx, const char* __restrict__ in_score, int64_t idx_stride, int64_t score_stride, int parts,
-                   int64_t nq, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_score, int m) {
+merge_parts_kernel(const char* in_idx, const char* in_score, int64_t idx_stride, int64_t score_stride, int parts,
+                   int64_t nq, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_score, int m, const MergeSync sync) {
     extern __shared__ uint64_t cand[];                  // [m] power of two >= parts*k
+    __shared__ int s_last;
     const int64_t q = blockIdx.x;
     const int total = parts * k;
+    if (sync.flags) {
+        if ((int)threadIdx.x < parts) wait_word_sys(sync.flags + threadIdx.x, sync.epoch);
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         uint64_t it = 0ull;
         if (i < total) {
@@ -557,19 +584,51 @@ merge_parts_kernel(const char* __restrict__ in_idx, const char* __restrict__ in_
         out_idx[q * k + r] = id;
         if (out_score) out_score[q * k + r] = s;
     }
+    if (sync.flags) {
+        __syncthreads();                                // every read of the mailbox by this CTA has completed
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = (atomicAdd(sync.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            if (threadIdx.x == 0) *sync.ticket = 0;
+            if ((int)threadIdx.x < parts) st_release_sys(sync.ack[threadIdx.x], sync.epoch);
+        }
+    }
 }
 
 // part p's id list starts at in_idx + p*idx_stride BYTES, its score list at in_score + p*score_stride BYTES
 void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride, int64_t score_stride, int parts, int64_t nq, int k,
-                        int64_t* out_idx, float* out_score, cudaStream_t st) {
+                        int64_t* out_idx, float* out_score, cudaStream_t st, const MergeSync* sync) {
     if (nq <= 0) return;
     int m = 2;
     while (m < parts * k) m <<= 1;
     const size_t smem = (size_t)m * sizeof(uint64_t);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    MergeSync none{};
     merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(static_cast<const char*>(in_idx), static_cast<const char*>(in_score), idx_stride, score_stride,
-                                                      parts, nq, k, out_idx, out_score, m);
+                                                      parts, nq, k, out_idx, out_score, m, sync ? *sync : none);
+}
+
+// Sending end of the peer exchange: CTA g copies this rank's packed result into rank g's mailbox (plain stores
+// through the NVLink peer mapping; g == rank is a local copy) and then releases rank g's arrival flag.  Before
+// overwriting the slot it waits for rank g's acknowledgement of the slot's previous epoch.
+__global__ void __launch_bounds__(512)
+exchange_push_kernel(const uint4* __restrict__ src, int64_t n16, const PushArgs a) {
+    const int g = blockIdx.x;
+    if (threadIdx.x == 0 && a.epoch > 1) wait_word_sys(a.my_acks + g, a.epoch - 1);
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(a.dst[g]);
+    for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(a.flag[g], a.epoch);
+}
+
+void launch_exchange_push(const void* src, int64_t bytes, const PushArgs& a, int world, cudaStream_t st) {
+    exchange_push_kernel<<<world, 512, 0, st>>>(static_cast<const uint4*>(src), bytes / 16, a);
 }
 
 }  // namespace xs

@@ -111,8 +111,22 @@ void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st);
 // Multi-GPU merge of [parts][nq][k] lists.
+constexpr int XCHG_MAX_WORLD = 16;
+struct MergeSync {                       // receiving end of the peer exchange (all zero = plain merge)
+    const uint32_t* flags;               // local arrival flags of this slot, one per sending rank
+    uint32_t epoch;
+    uint32_t* ticket;                    // local CTA counter of this slot
+    uint32_t* ack[XCHG_MAX_WORLD];       // rank g's acknowledgement word for (slot, this rank)
+};
+struct PushArgs {                        // sending end
+    void* dst[XCHG_MAX_WORLD];           // rank g's mailbox part for (slot, this rank)
+    uint32_t* flag[XCHG_MAX_WORLD];      // rank g's arrival flag for (slot, this rank)
+    const uint32_t* my_acks;             // local acknowledgement words of this slot, one per receiving rank
+    uint32_t epoch;
+};
 void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride_bytes, int64_t score_stride_bytes, int parts, int64_t nq, int k,
-                        int64_t* out_idx, float* out_score, cudaStream_t st);
+                        int64_t* out_idx, float* out_score, cudaStream_t st, const MergeSync* sync = nullptr);
+void launch_exchange_push(const void* src, int64_t bytes, const PushArgs& a, int world, cudaStream_t st);
 // ---- sort.cu ------------------------------------------------------------------------------------
 // Full ranking (K == N): stable segmented radix sort of c exact score rows; writes columns q0..q0+c of
 // out_ranks [n][nq_total] int64 (+ id_offset) and, optionally, out_scores [n][nq_total] fp32.

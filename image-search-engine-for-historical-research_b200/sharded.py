@@ -7,6 +7,11 @@ local top-k with GLOBAL ids (``id_offset``); the only exchange step is one all-g
 kernel (xs_merge_candidates).  Rescoring needs no communication: a shard holds the fp32 rows of
 its own candidates.
 
+On NVLink boxes the collective library can be taken off the data path altogether: ``PeerExchange`` gives every
+rank a mailbox in its own HBM (CUDA IPC), a push kernel stores the packed list into all mailboxes and raises
+a flag, and the merge kernel itself waits for the world's flags (xs_exchange_*; ``ShardedSearcher(...,
+exchange=...)``).  torch.distributed then only carries the 64-byte handles and the set-up barriers.
+
 The local searcher and the merge are injectable so that the sharding / id-offset / gather logic
 is covered by world_size-2 gloo tests on CPU, where the test passes the oracle's searcher and merge
 in; the product wiring (`CudaShard`) is CUDA only and there is no automatic fallback.
@@ -37,13 +42,15 @@ class ShardedSearcher:
     is ONE all-gather; ``merge(packed_all, world, nq, k) -> (ids [nq,k], sims [nq,k])``.
     """
 
-    def __init__(self, local_search, merge, group=None):
+    def __init__(self, local_search, merge, group=None, exchange=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local_search = local_search
         self.merge = merge
+        self.exchange = exchange                    # PeerExchange: push + waiting merge instead of the all-gather
+        self._inflight = [None, None]
         self._gathered = {}
         # callbacks may take a result-slot argument (the CUDA shard does: two result buffers alternate)
         import inspect
@@ -62,7 +69,13 @@ class ShardedSearcher:
         import torch
         nq = int(queries.shape[0])
         slot = self._slot = (getattr(self, "_slot", 1) + 1) & 1
+        if self.exchange is not None and self._inflight[slot] is not None:
+            self._inflight[slot].result()           # the slot's previous merge must be enqueued before its next push
         packed = self.local_search(queries, k, slot) if self._ls_slot else self.local_search(queries, k)
+        if self.exchange is not None:
+            self.exchange.push(packed, slot)
+            self._inflight[slot] = _PendingPeer(self, nq, k, slot)
+            return self._inflight[slot]
         if self.world == 1:
             return _Pending(self, None, packed, nq, k, slot)
         key = (nq, k, packed.device, slot)
@@ -83,6 +96,88 @@ class _Pending:
         self.work.wait()                                    # stream-level wait, the host does not block
         o = self.owner
         return o.merge(self.buf, o.world, self.nq, self.k, self.slot) if o._mg_slot else o.merge(self.buf, o.world, self.nq, self.k)
+
+
+class _PendingPeer:
+    def __init__(self, owner, nq, k, slot):
+        self.owner, self.nq, self.k, self.slot, self.out = owner, nq, k, slot, None
+
+    def result(self):
+        if self.out is None:
+            self.out = self.owner.exchange.merge(self.nq, self.k, self.slot)
+            if self.owner._inflight[self.slot] is self:
+                self.owner._inflight[self.slot] = None
+        return self.out
+
+
+class PeerExchange:
+    """Mailboxes + handshake for the peer-memory exchange (xs_exchange_*).  ``part_bytes`` bounds one rank's
+    packed result (``packed_bytes(nq, k)`` of the largest search).  Collective: every rank of ``group``
+    constructs it at the same point.  CUDA only."""
+
+    def __init__(self, device: int, part_bytes: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.device = torch, dist, group, int(device)
+        self.lib = nat.load()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.part_bytes = (int(part_bytes) + 15) // 16 * 16
+        self._h = C.c_void_p()
+        self._out = {}
+        handle = (C.c_ubyte * 64)()
+        err = None
+        try:
+            nat.check(self.lib.xs_exchange_create(self.device, self.world, self.rank, self.part_bytes, C.byref(self._h), handle),
+                      "xs_exchange_create")
+        except Exception as e:                      # keep walking through the collectives below: peers are waiting in them
+            err = e
+        if self.world > 1:
+            dev = torch.device("cuda", self.device)
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            everyone = torch.empty((self.world * 64,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+            if err is None:
+                try:
+                    nat.check(self.lib.xs_exchange_connect(self._h, everyone.cpu().numpy().tobytes()), "xs_exchange_connect")
+                except Exception as e:
+                    err = e
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also the barrier: every mailbox zeroed and mapped
+            if int(ok.item()) == 0 and err is None:
+                err = RuntimeError("peer exchange could not be set up on another rank")
+        if err is not None:
+            if self._h:
+                self.lib.xs_exchange_destroy(self._h)
+                self._h = C.c_void_p()
+            raise RuntimeError(f"peer exchange unavailable: {err}") from err
+
+    def push(self, packed, slot: int):
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(self.lib.xs_exchange_push(self._h, C.c_void_p(packed.data_ptr()), int(packed.numel()), int(slot),
+                                            C.c_void_p(stream) if stream else None), "xs_exchange_push")
+
+    def merge(self, nq: int, k: int, slot: int):
+        torch = self.torch
+        key = (nq, k, slot)
+        if key not in self._out:
+            dev = torch.device("cuda", self.device)
+            self._out[key] = (torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev))
+        out_i, out_s = self._out[key]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        nat.check(self.lib.xs_exchange_merge(self._h, int(slot), int(nq), int(k), C.c_void_p(out_i.data_ptr()),
+                                             C.c_void_p(out_s.data_ptr()), C.c_void_p(stream) if stream else None),
+                  "xs_exchange_merge")
+        return out_i, out_s
+
+    def close(self):
+        """Collective: drains this rank's stream work, waits for every rank, then unmaps and frees."""
+        if self._h:
+            self.torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                self.dist.barrier(self.group)
+            self.lib.xs_exchange_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def packed_bytes(nq: int, k: int) -> int:

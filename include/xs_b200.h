@@ -160,6 +160,30 @@ XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const voi
                                        int64_t* out_idx, float* out_score, void* stream);
 
 /*
+ * Peer exchange: the all-gather + merge of the row-sharded search without a collective library on the data
+ * path.  Every rank owns a mailbox in its own HBM, exported through CUDA IPC; after its local search a rank
+ * PUSHES its packed result ([ids int64 nq*k | scores f32 nq*k], what xs_search_dev wrote) into every rank's
+ * mailbox with plain stores over the NVLink peer mappings and releases an arrival flag; the MERGE kernel of
+ * each rank waits for the world's flags, merges, and acknowledges the slot so that it can be overwritten.
+ * One process per GPU; the 64-byte handles travel through whatever channel the host processes share.
+ * (No reference counterpart: the reference is single-process.  Replaces ncclAllGather + xs_merge_candidates
+ * of SURVEY.md section 8e on the latency path.)
+ *
+ * Protocol: every rank calls push(slot) / merge(slot) in the same order; slots 0 and 1 alternate, and the
+ * merge of a slot must be enqueued before the next push into the same slot (at most two searches in flight).
+ * A peer that never arrives traps the waiting kernel after ~20 s instead of hanging the GPU.
+ * xs_exchange_destroy synchronises the device; the caller must barrier across ranks before calling it.
+ */
+typedef struct xs_exchange xs_exchange;
+XS_API int xs_exchange_create(int device, int world, int rank, int64_t part_bytes, xs_exchange** out,
+                              unsigned char* handle_out /* 64 bytes */);
+XS_API int xs_exchange_connect(xs_exchange* ex, const unsigned char* handles /* world x 64 bytes, by rank */);
+XS_API int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t bytes, int slot, void* stream);
+XS_API int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64_t* out_idx_dev, float* out_score_dev,
+                             void* stream);
+XS_API int xs_exchange_destroy(xs_exchange* ex);
+
+/*
  * Mutual-kNN test of the diffusion affinity graph.
  *   replaces: the per-row loop `np.isin(ids[ids[i]], i).any(axis=1)` of get_affinity   src/utils/diffusion.py:106-108
  * ids: HOST [n, kd] int64, the kNN lists of every row (slot 0 = the row itself, as xs_self_knn returns them).

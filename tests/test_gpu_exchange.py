@@ -1,0 +1,55 @@
+"""Peer-memory exchange (xs_exchange_*): the push kernel, the arrival flags the merge kernel waits on, the
+acknowledgements that free a mailbox slot.  World 1 in-process; world 2 under torchrun when two GPUs exist."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exchange_single_rank(pkg, synth, oracle):
+    import importlib
+    import torch
+    sharded = importlib.import_module(pkg.__name__ + ".sharded")
+    v, q = synth.gaussian(6000, 40, d=128)
+    index = pkg.ExactIndex(v.T, id_offset=1000)
+    shard = sharded.CudaShard(index, 0)
+    ex = sharded.PeerExchange(0, sharded.packed_bytes(40, 50))
+    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=ex)
+    qd = torch.from_numpy(np.ascontiguousarray(q.T)).cuda()
+    ref_i, ref_s = oracle.topk_ip(v, q, 50)
+    s64 = oracle.scores_f64(v, q)
+    for epoch in range(5):                                         # both slots, several epochs, varying sizes
+        nq, k = ((40, 50), (1, 50), (17, 3))[epoch % 3]
+        ids, sims = searcher.search(qd[:nq].contiguous(), k)
+        ids, sims = ids.cpu().numpy(), sims.cpu().numpy()
+        for j in range(nq):
+            ok, msg = oracle.compare_topk(ids[j] - 1000, ref_i[j, :k], lambda i, j=j: s64[i, j])
+            assert ok, f"epoch {epoch} query {j}: {msg}"
+        np.testing.assert_allclose(sims, ref_s[:nq, :k], rtol=1e-5, atol=1e-7)
+    a, b = searcher.search_async(qd, 50), searcher.search_async(qd, 50)
+    np.testing.assert_array_equal(a.result()[0].cpu().numpy(), b.result()[0].cpu().numpy())
+    with pytest.raises(ValueError):
+        ex.push(torch.empty(sharded.packed_bytes(40, 50) + 16, dtype=torch.uint8, device="cuda"), 0)   # larger than a mailbox part
+    with pytest.raises(ValueError):
+        ex.merge(40, 50, 1)                                         # a merge without its push
+    ex.close()
+    index.close()
+
+
+def test_exchange_two_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "exchange_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "exchange_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
