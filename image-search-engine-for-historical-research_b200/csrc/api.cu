@@ -881,7 +881,8 @@ struct xs_exchange {
     char* peer[XCHG_MAX_WORLD] = {};              // every rank's mailbox as mapped here (peer[rank] == local)
     bool connected = false;
     uint32_t push_epoch[2] = {0, 0}, merge_epoch[2] = {0, 0};
-    static constexpr size_t FLAGS_OFF = 0, ACKS_OFF = 2 * XCHG_MAX_WORLD * 4, TICKET_OFF = 4 * XCHG_MAX_WORLD * 4, DATA_OFF = 512;
+    static constexpr size_t FLAGS_OFF = 0, ACKS_OFF = 2 * XCHG_MAX_WORLD * 4, TICKET_OFF = 4 * XCHG_MAX_WORLD * 4,
+                            PUSH_TICKET_OFF = TICKET_OFF + 64, DATA_OFF = 1024;
     size_t total() const { return DATA_OFF + (size_t)2 * world * part_bytes; }
 };
 
@@ -942,6 +943,7 @@ extern "C" int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t
         a.flag[g] = reinterpret_cast<uint32_t*>(ex->peer[g] + xs_exchange::FLAGS_OFF) + slot * XCHG_MAX_WORLD + ex->rank;
     }
     a.my_acks = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD;
+    a.tickets = reinterpret_cast<uint32_t*>(ex->local + xs_exchange::PUSH_TICKET_OFF) + slot * XCHG_MAX_WORLD;
     a.epoch = ++ex->push_epoch[slot];
     launch_exchange_push(packed_dev, bytes, a, ex->world, static_cast<cudaStream_t>(stream));
     CU_TRY(cudaGetLastError());

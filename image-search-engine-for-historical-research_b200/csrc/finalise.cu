@@ -612,23 +612,48 @@ void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_st
                                                       parts, nq, k, out_idx, out_score, m, sync ? *sync : none);
 }
 
-// Sending end of the peer exchange: CTA g copies this rank's packed result into rank g's mailbox (plain stores
-// through the NVLink peer mapping; g == rank is a local copy) and then releases rank g's arrival flag.  Before
-// overwriting the slot it waits for rank g's acknowledgement of the slot's previous epoch.
-__global__ void __launch_bounds__(512)
+// Sending end of the peer exchange: the CTAs of column g copy this rank's packed result into rank g's mailbox
+// (plain 16-byte stores through the NVLink peer mapping, every load issued before the first store; g == rank is a
+// local copy) and the last of them releases rank g's arrival flag.  Before overwriting the slot they wait for
+// rank g's acknowledgement of the slot's previous epoch.
+constexpr int PUSH_THREADS = 1024, PUSH_UNROLL = 8;
+__global__ void __launch_bounds__(PUSH_THREADS)
 exchange_push_kernel(const uint4* __restrict__ src, int64_t n16, const PushArgs a) {
+    __shared__ int s_last;
     const int g = blockIdx.x;
     if (threadIdx.x == 0 && a.epoch > 1) wait_word_sys(a.my_acks + g, a.epoch - 1);
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(a.dst[g]);
-    for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    for (int64_t base = (int64_t)blockIdx.y * PUSH_THREADS * PUSH_UNROLL; base < n16; base += (int64_t)gridDim.y * PUSH_THREADS * PUSH_UNROLL) {
+        uint4 v[PUSH_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PUSH_UNROLL; ++u) {
+            const int64_t i = base + u * PUSH_THREADS + threadIdx.x;
+            if (i < n16) v[u] = src[i];
+        }
+#pragma unroll
+        for (int u = 0; u < PUSH_UNROLL; ++u) {
+            const int64_t i = base + u * PUSH_THREADS + threadIdx.x;
+            if (i < n16) dst[i] = v[u];
+        }
+    }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(a.flag[g], a.epoch);
+    if (threadIdx.x == 0) {
+        s_last = 1;
+        if (gridDim.y > 1) {
+            s_last = (atomicAdd(a.tickets + g, 1u) == gridDim.y - 1) ? 1 : 0;
+            if (s_last) { a.tickets[g] = 0; __threadfence_system(); }
+        }
+        if (s_last) st_release_sys(a.flag[g], a.epoch);
+    }
 }
 
 void launch_exchange_push(const void* src, int64_t bytes, const PushArgs& a, int world, cudaStream_t st) {
-    exchange_push_kernel<<<world, 512, 0, st>>>(static_cast<const uint4*>(src), bytes / 16, a);
+    const int64_t n16 = bytes / 16;
+    int64_t nblk = (n16 + (int64_t)PUSH_THREADS * PUSH_UNROLL - 1) / ((int64_t)PUSH_THREADS * PUSH_UNROLL);
+    nblk = nblk < 1 ? 1 : (nblk > 16 ? 16 : nblk);
+    exchange_push_kernel<<<dim3(world, (unsigned)nblk), PUSH_THREADS, 0, st>>>(static_cast<const uint4*>(src), n16, a);
 }
 
 }  // namespace xs

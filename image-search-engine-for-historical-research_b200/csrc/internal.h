@@ -122,6 +122,7 @@ struct PushArgs {                        // sending end
     void* dst[XCHG_MAX_WORLD];           // rank g's mailbox part for (slot, this rank)
     uint32_t* flag[XCHG_MAX_WORLD];      // rank g's arrival flag for (slot, this rank)
     const uint32_t* my_acks;             // local acknowledgement words of this slot, one per receiving rank
+    uint32_t* tickets;                   // local CTA counters of this slot, one per receiving rank (large payloads)
     uint32_t epoch;
 };
 void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride_bytes, int64_t score_stride_bytes, int parts, int64_t nq, int k,

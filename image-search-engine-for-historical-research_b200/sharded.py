@@ -59,9 +59,9 @@ class ShardedSearcher:
 
     def search(self, queries, k: int):
         """Blocking form: local exact top-k, one all-gather, merge.  Every rank returns the full answer."""
-        return self.search_async(queries, k).result()
+        return self.search_async(queries, k, blocking=True).result()
 
-    def search_async(self, queries, k: int):
+    def search_async(self, queries, k: int, blocking: bool = False):
         """Throughput form: enqueue the local search and START the all-gather, return a handle.  The
         collective runs on NCCL's own stream, so the next batch's scan overlaps it; ``handle.result()``
         makes the current stream wait for the gather and enqueues the merge.  Two result slots alternate,
@@ -69,11 +69,13 @@ class ShardedSearcher:
         import torch
         nq = int(queries.shape[0])
         slot = self._slot = (getattr(self, "_slot", 1) + 1) & 1
-        if self.exchange is not None and self._inflight[slot] is not None:
-            self._inflight[slot].result()           # the slot's previous merge must be enqueued before its next push
+        if self.exchange is not None:
+            if self._inflight[slot] is not None:
+                self._inflight[slot].result()       # the slot's previous merge must be enqueued before its next push
+            self.exchange.before_local_search(slot)
         packed = self.local_search(queries, k, slot) if self._ls_slot else self.local_search(queries, k)
         if self.exchange is not None:
-            self.exchange.push(packed, slot)
+            self.exchange.push(packed, slot, overlap=not blocking)
             self._inflight[slot] = _PendingPeer(self, nq, k, slot)
             return self._inflight[slot]
         if self.world == 1:
@@ -125,6 +127,7 @@ class PeerExchange:
         self.part_bytes = (int(part_bytes) + 15) // 16 * 16
         self._h = C.c_void_p()
         self._out = {}
+        self._side, self._pushed, self._busy = None, None, [False, False]
         handle = (C.c_ubyte * 64)()
         err = None
         try:
@@ -152,10 +155,31 @@ class PeerExchange:
                 self._h = C.c_void_p()
             raise RuntimeError(f"peer exchange unavailable: {err}") from err
 
-    def push(self, packed, slot: int):
-        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+    def push(self, packed, slot: int, overlap: bool = False):
+        """Enqueue the push of ``packed`` (this rank's result of the search just enqueued).  ``overlap``: run it
+        on a side stream behind an event, so that the caller's stream goes straight on to the next search --
+        nothing has to join it, the merge kernel waits for the arrival flags (this rank's own included)."""
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        if overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+                self._pushed = [torch.cuda.Event(), torch.cuda.Event()]
+            self._side.wait_stream(cur)
+            stream = self._side.cuda_stream
+        else:
+            stream = cur.cuda_stream
         nat.check(self.lib.xs_exchange_push(self._h, C.c_void_p(packed.data_ptr()), int(packed.numel()), int(slot),
                                             C.c_void_p(stream) if stream else None), "xs_exchange_push")
+        if overlap:
+            self._pushed[slot].record(self._side)
+            self._busy[slot] = True
+
+    def before_local_search(self, slot: int):
+        """The result buffer of ``slot`` is about to be overwritten: a side-stream push still reading it goes first."""
+        if self._busy[slot]:
+            self.torch.cuda.current_stream(self.device).wait_event(self._pushed[slot])
+            self._busy[slot] = False
 
     def merge(self, nq: int, k: int, slot: int):
         torch = self.torch

@@ -39,6 +39,17 @@ def test_exchange_single_rank(pkg, synth, oracle):
     with pytest.raises(ValueError):
         ex.merge(40, 50, 1)                                         # a merge without its push
     ex.close()
+    # a payload that takes several push CTAs per peer (2.3 MB): 3000 queries, k = 64
+    vq, _ = synth.gaussian(3000, 1, d=128)
+    big = sharded.PeerExchange(0, sharded.packed_bytes(3000, 64))
+    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=big)
+    qd = torch.from_numpy(np.ascontiguousarray(vq.T)).cuda()
+    want_i, want_s = index.search(vq.T, 64)
+    for _ in range(3):
+        ids, sims = searcher.search(qd, 64)
+        np.testing.assert_array_equal(ids.cpu().numpy(), want_i)
+        np.testing.assert_array_equal(sims.cpu().numpy(), want_s)
+    big.close()
     index.close()
 
 
