@@ -205,12 +205,12 @@ def run_ours(args):
     index = pkg.ExactIndex.from_device(rows.data_ptr(), hi - lo, DIM, local, renormalise=False, id_offset=lo)
     shard = sharded.CudaShard(index, local)
     exchange = None
-    if world > 1 and not replicas and args.exchange == "peer":
+    if world > 1 and not replicas and args.exchange in ("auto", "peer"):
         try:                                                   # collective set-up: succeeds or fails on every rank together
             exchange = sharded.PeerExchange(local, sharded.packed_bytes(N_QUERIES, TOPK))
         except RuntimeError as e:
             print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
-    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange)
+    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange, exchange_pipelined=args.exchange == "peer")
     if replicas:
         searcher.world = 1                                     # no exchange step at all
 
@@ -240,7 +240,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     uncert = shard.uncertified(N_QUERIES, TOPK)
-    launches_per_step = index.stats()["gpu_launches"] + ((2 if exchange is not None else 1) if (world > 1 and not replicas) else 0)
+    launches_per_step = index.stats()["gpu_launches"] + ((2 if (exchange is not None and args.exchange == "peer") else 1) if (world > 1 and not replicas) else 0)
 
     # ---- end to end through the host-buffer call (`e2e`) ----------------------------------------------
     q_host = queries.cpu().pin_memory()
@@ -328,7 +328,7 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2: 1,007,000 x 2048 DB (unit-norm Gaussian, seed 0), 70-query batch, exact top-100",
-                   "rows_per_gpu": shard_rows, "sharding": "none" if world == 1 else (f"{world} replicas of the whole database, one 70-query batch per GPU and step, no collective" if replicas else (f"row-sharded x{world}, per-shard top-100 pushed into every rank's mailbox over NVLink peer memory, merge kernel waits on arrival flags (no collective on the data path)" if exchange is not None else f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel")),
+                   "rows_per_gpu": shard_rows, "sharding": "none" if world == 1 else (f"{world} replicas of the whole database, one 70-query batch per GPU and step, no collective" if replicas else (f"row-sharded x{world}; e2e call: per-shard top-100 pushed into every rank's mailbox over NVLink peer memory, merge kernel waits on arrival flags; value loop: " + ("the same push on a side stream" if args.exchange == "peer" else "NCCL all-gather on its own stream + merge kernel") if exchange is not None else f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel")),
                    "l2": "inputs larger than L2 (4.1 GB bf16 database per pass vs 126 MB L2)",
                    "arithmetic": "bf16 operands / fp32 accumulate (tcgen05) for the coarse pass, then fp32 operands / fp64 accumulate exact rescoring of ~120 candidates per query",
                    "path": {1: "scan", 2: "tcgen05 GEMM + fused top-K", 3: "exact"}.get(stats["path"], "?"),
@@ -369,8 +369,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1, row sharding: how the per-shard lists meet -- peer-memory push + waiting merge kernel, or NCCL all-gather + merge")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1, row sharding: how the per-shard lists meet -- peer-memory push + flag-waiting merge kernel, or NCCL "
+                         "all-gather + merge; auto = push for the blocking (e2e) call, all-gather for the pipelined (value) loop")
     ap.add_argument("--sharding", default="rows", choices=["rows", "replicas"],
                     help="N > 1: 'rows' (default) = the database row-sharded over the GPUs + NCCL candidate merge (strong scaling, the "
                          "north-star layout); 'replicas' = every GPU holds the whole database and answers its own batches (weak scaling)")

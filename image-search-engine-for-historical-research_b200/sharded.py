@@ -42,7 +42,7 @@ class ShardedSearcher:
     is ONE all-gather; ``merge(packed_all, world, nq, k) -> (ids [nq,k], sims [nq,k])``.
     """
 
-    def __init__(self, local_search, merge, group=None, exchange=None):
+    def __init__(self, local_search, merge, group=None, exchange=None, exchange_pipelined=False):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -50,6 +50,9 @@ class ShardedSearcher:
         self.local_search = local_search
         self.merge = merge
         self.exchange = exchange                    # PeerExchange: push + waiting merge instead of the all-gather
+        # Measured on 8 B200s: the push wins on the blocking (latency) form, 0.231 vs 0.239 ms per 70-query search;
+        # the pipelined form is 2 % faster with NCCL's all-gather on its own stream -- so that is its default.
+        self.exchange_pipelined = bool(exchange_pipelined)
         self._inflight = [None, None]
         self._gathered = {}
         # callbacks may take a result-slot argument (the CUDA shard does: two result buffers alternate)
@@ -69,12 +72,13 @@ class ShardedSearcher:
         import torch
         nq = int(queries.shape[0])
         slot = self._slot = (getattr(self, "_slot", 1) + 1) & 1
+        use_peer = self.exchange is not None and (blocking or self.exchange_pipelined)
         if self.exchange is not None:
             if self._inflight[slot] is not None:
                 self._inflight[slot].result()       # the slot's previous merge must be enqueued before its next push
             self.exchange.before_local_search(slot)
         packed = self.local_search(queries, k, slot) if self._ls_slot else self.local_search(queries, k)
-        if self.exchange is not None:
+        if use_peer:
             self.exchange.push(packed, slot, overlap=not blocking)
             self._inflight[slot] = _PendingPeer(self, nq, k, slot)
             return self._inflight[slot]
