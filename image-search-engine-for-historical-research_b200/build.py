@@ -20,7 +20,8 @@ LIB = os.path.join(HERE, "libxs_b200.so")
 SOURCES = ["api.cu", "build.cu", "scan.cu", "gemm_topk.cu", "finalise.cu", "sort.cu", "graph.cu", "diffusion.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + \
+        os.environ.get("XS_NVCC_EXTRA", "").split()          # e.g. -DXS_PDL_EARLY=0 for an A/B build (use force)
 
 
 def _deps():
