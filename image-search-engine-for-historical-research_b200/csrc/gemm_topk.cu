@@ -290,6 +290,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             int cnt = 0;
             float thr = active ? (thr0 ? thr0[q] : -INFINITY) : INFINITY;
             uint32_t thr_rec = 0;
+            if (__ballot_sync(0xffffffffu, active) == 0u) {
+                // all 32 query rows of this warp are tile padding (e.g. rows 96..127 of a 70-query batch): nothing to
+                // read back -- only hand the accumulators over so that the MMA thread can go on
+                for (int t = t0; t < t1; ++t, ++it) {
+                    const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                    mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
+                    release_acc(acc);
+                }
+                pool_count[slot] = 0;
+                pool_thr[slot] = 0u;
+                continue;
+            }
             if (sample_mode) {
                 // Threshold bootstrap: only the 8 best scores of this lane's tile(s) are needed (the
                 // union of per-tile top-8 lists holds >= k items, and its k-th best is a valid lower
