@@ -37,3 +37,23 @@ def test_index_from_store(tmp_path, pkg, synth, oracle):
     np.testing.assert_array_equal(ids, rid)
     assert len(paths) == 2000
     ix.close()
+
+
+def test_search_offline_matches_reference_statements(pkg):
+    """Query side of the diffusion re-ranking (Reranking.py:243-256) -- host-only code, so it runs on CPU:
+    ``scores = sims[i] @ offline[idx[i]]`` then argpartition + argsort of the ``n_trunc`` best."""
+    import scipy.sparse as sparse
+    rng = np.random.default_rng(5)
+    n, n_trunc = 300, 40
+    offline = sparse.random(n, n, density=0.3, random_state=7, dtype=np.float32, format="csr")
+    sims = rng.random((6, 3)).astype(np.float32)
+    idx = rng.integers(0, n, size=(6, 3))
+    got_s, got_r = pkg.diffusion.search_offline(offline, sims, idx, n_trunc)
+    cubed = sims ** 3
+    for i in range(6):
+        scores = cubed[i] @ offline[idx[i]]                                   # the reference's statements
+        parts = np.argpartition(-scores, n_trunc)[:n_trunc]
+        ranks = np.argsort(-scores[parts])
+        np.testing.assert_allclose(got_s[i], scores[parts][ranks], rtol=1e-6)
+        np.testing.assert_allclose(scores[got_r[i]], got_s[i], rtol=1e-6)
+    assert got_r.dtype == np.int64 and got_s.dtype == np.float32
