@@ -881,6 +881,7 @@ struct xs_exchange {
     char* peer[XCHG_MAX_WORLD] = {};              // every rank's mailbox as mapped here (peer[rank] == local)
     bool connected = false;
     uint32_t push_epoch[2] = {0, 0}, merge_epoch[2] = {0, 0};
+    std::mutex mu;                                // epochs and launches of one exchange are serialised
     static constexpr size_t FLAGS_OFF = 0, ACKS_OFF = 2 * XCHG_MAX_WORLD * 4, TICKET_OFF = 4 * XCHG_MAX_WORLD * 4,
                             PUSH_TICKET_OFF = TICKET_OFF + 64, DATA_OFF = 1024;
     size_t total() const { return DATA_OFF + (size_t)2 * world * part_bytes; }
@@ -936,6 +937,8 @@ extern "C" int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t
     if (!ex || !packed_dev) return fail(XS_ERR_ARG, "null pointer");
     if (!ex->connected && ex->world > 1) return fail(XS_ERR_ARG, "exchange not connected");
     if (slot < 0 || slot > 1 || bytes <= 0 || bytes % 16 || bytes > ex->part_bytes) return fail(XS_ERR_ARG, "bad slot/bytes (%d, %lld of %lld)", slot, (long long)bytes, (long long)ex->part_bytes);
+    std::lock_guard<std::mutex> lock(ex->mu);
+    if (ex->push_epoch[slot] != ex->merge_epoch[slot]) return fail(XS_ERR_ARG, "push into slot %d before its previous result was merged", slot);
     CU_TRY(cudaSetDevice(ex->device));
     PushArgs a{};
     for (int g = 0; g < ex->world; ++g) {
@@ -954,6 +957,7 @@ extern "C" int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, i
     if (!ex || !out_idx) return fail(XS_ERR_ARG, "null pointer");
     if (slot < 0 || slot > 1 || nq <= 0 || k <= 0 || nq * k * 12 > ex->part_bytes) return fail(XS_ERR_ARG, "bad slot/sizes");
     if ((int64_t)ex->world * k > 16384) return fail(XS_ERR_UNSUPPORTED, "world*k = %lld > 16384", (long long)ex->world * k);
+    std::lock_guard<std::mutex> lock(ex->mu);
     if (ex->merge_epoch[slot] >= ex->push_epoch[slot]) return fail(XS_ERR_ARG, "merge of slot %d without a matching push", slot);
     CU_TRY(cudaSetDevice(ex->device));
     MergeSync ms{};

@@ -32,7 +32,7 @@ def main():
     shard = sharded.CudaShard(index, local)
     q_all = torch.from_numpy(np.ascontiguousarray(qvecs.T)).to(dev)
     exchange = sharded.PeerExchange(local, sharded.packed_bytes(70, 100))
-    peer = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange)
+    peer = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange, exchange_pipelined=True)
     nccl = sharded.ShardedSearcher(shard.local_search, shard.merge)
     s64 = oracle.scores_f64(vecs, qvecs)
     for nq, k in ((70, 100), (1, 100), (33, 7), (70, 100)):

@@ -20,7 +20,7 @@ def test_exchange_single_rank(pkg, synth, oracle):
     index = pkg.ExactIndex(v.T, id_offset=1000)
     shard = sharded.CudaShard(index, 0)
     ex = sharded.PeerExchange(0, sharded.packed_bytes(40, 50))
-    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=ex)
+    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=ex, exchange_pipelined=True)
     qd = torch.from_numpy(np.ascontiguousarray(q.T)).cuda()
     ref_i, ref_s = oracle.topk_ip(v, q, 50)
     s64 = oracle.scores_f64(v, q)
@@ -38,6 +38,11 @@ def test_exchange_single_rank(pkg, synth, oracle):
         ex.push(torch.empty(sharded.packed_bytes(40, 50) + 16, dtype=torch.uint8, device="cuda"), 0)   # larger than a mailbox part
     with pytest.raises(ValueError):
         ex.merge(40, 50, 1)                                         # a merge without its push
+    packed = shard.local_search(qd, 50, 0)
+    ex.push(packed, 0)
+    with pytest.raises(ValueError):
+        ex.push(packed, 0)                                          # the slot's previous result has not been merged
+    ex.merge(40, 50, 0)
     ex.close()
     # a payload that takes several push CTAs per peer (2.3 MB): 3000 queries, k = 64
     vq, _ = synth.gaussian(3000, 1, d=128)
