@@ -121,6 +121,26 @@ def cpu_reference_step(vecs: np.ndarray, qvecs: np.ndarray) -> float:
     return dt
 
 
+def cpu_extras(vecs: np.ndarray, qvecs: np.ndarray, scale: float) -> dict:
+    """The two other CPU timings SURVEY.md 8(d) asks for next to np.dot + argsort, on the same sample:
+    the restated matching_L2 (nnsearch.py:687-706, one query -- it is seconds per query) and a best-effort exact
+    top-K the reference does not have (torch.mm + topk on all host threads).  ``scale`` = full rows / sample rows."""
+    import torch
+    oracle = importlib.import_module("oracle.oracle")
+    out = {}
+    t0 = time.time()
+    oracle.matching_L2(TOPK, vecs.T, qvecs.T[:1])
+    out["matching_L2_s_per_query_full_db"] = (time.time() - t0) * scale
+    v, q = torch.from_numpy(np.ascontiguousarray(vecs.T)), torch.from_numpy(np.ascontiguousarray(qvecs))
+    best = 1e9
+    for _ in range(2):
+        t0 = time.time()
+        torch.topk(torch.mm(v, q), TOPK, dim=0)
+        best = min(best, time.time() - t0)
+    out["torch_mm_topk_qps_full_db"] = qvecs.shape[1] / (best * scale)
+    return out
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -309,6 +329,10 @@ def run_ours(args):
         qps_cpu = N_QUERIES / (dt * N_ROWS / sample_rows)
         cpu = {"value": qps_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
                "sample": f"np.dot + argsort[:100] (oracle.rank_ip), all 70 queries x {sample_rows} rows (1/4 of the DB, {dt:.2f} s), scaled x4 to the full DB"}
+        try:
+            cpu["other_cpu_paths"] = cpu_extras(vecs, qvecs, N_ROWS / sample_rows)
+        except Exception as e:                                   # informational only
+            cpu["other_cpu_paths"] = {"error": str(e)[:200]}
 
     peak, peak_src = measured_peaks()
     shard_rows = hi - lo
