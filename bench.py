@@ -223,14 +223,15 @@ def run_ours(args):
     queries = synth_rows_device(torch, N_QUERIES, DIM, dev, seed=1)
     torch.cuda.synchronize()
     index = pkg.ExactIndex.from_device(rows.data_ptr(), hi - lo, DIM, local, renormalise=False, id_offset=lo)
-    shard = sharded.CudaShard(index, local)
+    shard = sharded.CudaShard(index, local, lanes=args.lanes)
     exchange = None
     if world > 1 and not replicas and args.exchange in ("auto", "peer"):
         try:                                                   # collective set-up: succeeds or fails on every rank together
             exchange = sharded.PeerExchange(local, sharded.packed_bytes(N_QUERIES, TOPK))
         except RuntimeError as e:
             print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
-    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange, exchange_pipelined=args.exchange == "peer")
+    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange, exchange_pipelined=args.exchange == "peer",
+                                       lane_stream=shard.lane_stream if args.lanes > 1 else None)
     if replicas:
         searcher.world = 1                                     # no exchange step at all
 
@@ -352,7 +353,7 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2: 1,007,000 x 2048 DB (unit-norm Gaussian, seed 0), 70-query batch, exact top-100",
-                   "rows_per_gpu": shard_rows, "sharding": "none" if world == 1 else (f"{world} replicas of the whole database, one 70-query batch per GPU and step, no collective" if replicas else (f"row-sharded x{world}; e2e call: per-shard top-100 pushed into every rank's mailbox over NVLink peer memory, merge kernel waits on arrival flags; value loop: " + ("the same push on a side stream" if args.exchange == "peer" else "NCCL all-gather on its own stream + merge kernel") if exchange is not None else f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel")),
+                   "rows_per_gpu": shard_rows, "lanes": args.lanes, "sharding": "none" if world == 1 else (f"{world} replicas of the whole database, one 70-query batch per GPU and step, no collective" if replicas else (f"row-sharded x{world}; e2e call: per-shard top-100 pushed into every rank's mailbox over NVLink peer memory, merge kernel waits on arrival flags; value loop: " + ("the same push on a side stream" if args.exchange == "peer" else "NCCL all-gather on its own stream + merge kernel") if exchange is not None else f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel")),
                    "l2": "inputs larger than L2 (4.1 GB bf16 database per pass vs 126 MB L2)",
                    "arithmetic": "bf16 operands / fp32 accumulate (tcgen05) for the coarse pass, then fp32 operands / fp64 accumulate exact rescoring of ~120 candidates per query",
                    "path": {1: "scan", 2: "tcgen05 GEMM + fused top-K", 3: "exact"}.get(stats["path"], "?"),
@@ -393,6 +394,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
+                    help="search lanes per GPU in the pipelined (value) loop: 2 = consecutive batches alternate between the index "
+                         "and a workspace clone on two streams, so one batch's selection/rescoring overlaps the next batch's scan")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1, row sharding: how the per-shard lists meet -- peer-memory push + flag-waiting merge kernel, or NCCL "
                          "all-gather + merge; auto = push for the blocking (e2e) call, all-gather for the pipelined (value) loop")

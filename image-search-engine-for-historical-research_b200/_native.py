@@ -20,7 +20,7 @@ PATH_AUTO, PATH_SCAN, PATH_GEMM, PATH_EXACT = 0, 1, 2, 3
 # every symbol include/xs_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = (
     "xs_last_error", "xs_abi_version", "xs_device_count", "xs_index_create", "xs_index_create_dev",
-    "xs_index_destroy", "xs_index_info", "xs_index_stats", "xs_search", "xs_search_dev", "xs_self_knn",
+    "xs_index_destroy", "xs_index_clone", "xs_index_info", "xs_index_stats", "xs_search", "xs_search_dev", "xs_self_knn",
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
     "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
 )
@@ -55,6 +55,7 @@ def load() -> C.CDLL:
         lib.xs_index_create.argtypes = [p, i32, i64, i32, i64, i64, i32, i32, i64, C.POINTER(p)]
         lib.xs_index_create_dev.argtypes = [p, i64, i32, i32, i32, i64, C.POINTER(p)]
         lib.xs_index_destroy.argtypes = [p]
+        lib.xs_index_clone.argtypes = [p, C.POINTER(p)]
         lib.xs_index_info.argtypes = [p, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
         lib.xs_index_stats.argtypes = [p, C.POINTER(XsStats)]
         lib.xs_search.argtypes = [p, p, i32, i64, i64, i64, i32, i32, p, p]

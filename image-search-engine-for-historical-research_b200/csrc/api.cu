@@ -63,7 +63,14 @@ struct PinnedBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// The database arrays of an index, shared by the index and its clones (xs_index_clone): freed with the last holder.
+struct DbShare {
+    std::mutex mu; int refs = 1;
+    __nv_bfloat16* db16 = nullptr; __nv_bfloat16* db16t = nullptr; float* db32 = nullptr; void* dstats = nullptr;
+};
+
 struct xs_index {
+    DbShare* share = nullptr;
     int device = 0; int num_sms = 0;
     int64_t n = 0, n_pad = 0, id_offset = 0;
     int d = 0, d_pad = 0;
@@ -145,6 +152,8 @@ static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_of
     CU_TRY(cudaMalloc(&ix->db32, b32));
     CU_TRY(cudaMalloc(&ix->db16, b16));
     CU_TRY(cudaMalloc(&ix->dstats, sizeof(DevStats)));
+    ix->share = new DbShare();
+    ix->share->db16 = ix->db16; ix->share->db32 = ix->db32; ix->share->dstats = ix->dstats;
     ix->bytes = (int64_t)(b32 + b16);
     CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     for (auto& e : ix->ev) CU_TRY(cudaEventCreate(&e));
@@ -163,10 +172,21 @@ static void index_free(xs_index* ix) {
     for (Buf* b : {&ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
-    if (ix->db16) cudaFree(ix->db16);
-    if (ix->db16t) cudaFree(ix->db16t);
-    if (ix->db32) cudaFree(ix->db32);
-    if (ix->dstats) cudaFree(ix->dstats);
+    if (ix->share) {
+        bool last;
+        { std::lock_guard<std::mutex> lk(ix->share->mu); last = (--ix->share->refs == 0); }
+        if (last) {
+            if (ix->share->db16) cudaFree(ix->share->db16);
+            if (ix->share->db16t) cudaFree(ix->share->db16t);
+            if (ix->share->db32) cudaFree(ix->share->db32);
+            if (ix->share->dstats) cudaFree(ix->share->dstats);
+            delete ix->share;
+        }
+    } else {                                      // allocation failed before the share existed
+        if (ix->db16) cudaFree(ix->db16);
+        if (ix->db32) cudaFree(ix->db32);
+        if (ix->dstats) cudaFree(ix->dstats);
+    }
     for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     cudaGetLastError();
@@ -192,6 +212,7 @@ static int build_tiled_twin(xs_index* ix) {
     if (const char* e = getenv("XS_NO_TILED")) if (atoi(e)) return XS_OK;
     const size_t b16 = (size_t)ix->n_pad * ix->d_pad * 2;
     if (cudaMalloc(&ix->db16t, b16) != cudaSuccess) { cudaGetLastError(); ix->db16t = nullptr; return XS_OK; }   // optional: fall back to the row-major maps
+    ix->share->db16t = ix->db16t;
     launch_tile_db16(ix->db16, ix->db16t, ix->n_pad, ix->d_pad, ix->stream);
     CU_TRY(cudaStreamSynchronize(ix->stream));
     XS_TRY(make_tmap_tiled(&ix->tmap_dbt_b, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BN));
@@ -272,6 +293,32 @@ extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int de
 }
 
 extern "C" int xs_index_destroy(xs_index* ix) { index_free(ix); return XS_OK; }
+
+// A second search lane over the same database: shares the (read-only) database arrays and tensor maps, owns its
+// workspaces, stream, tunables and statistics -- so two searches can be in flight on two streams at once.
+extern "C" int xs_index_clone(xs_index* src, xs_index** out) {
+    if (!src || !out) return fail(XS_ERR_ARG, "null pointer");
+    *out = nullptr;
+    CU_TRY(cudaSetDevice(src->device));
+    xs_index* ix = new xs_index();
+    {
+        std::lock_guard<std::mutex> lk(src->mu);
+        ix->device = src->device; ix->num_sms = src->num_sms;
+        ix->n = src->n; ix->n_pad = src->n_pad; ix->id_offset = src->id_offset; ix->d = src->d; ix->d_pad = src->d_pad;
+        ix->db16 = src->db16; ix->db32 = src->db32; ix->dstats = src->dstats; ix->db16t = src->db16t;
+        ix->tmap_db_b = src->tmap_db_b; ix->tmap_db_a = src->tmap_db_a; ix->tmap_dbt_b = src->tmap_dbt_b; ix->tmap_dbt_h = src->tmap_dbt_h;
+        ix->eps_sigmas = src->eps_sigmas; ix->scan_max_q = src->scan_max_q; ix->force_path = src->force_path;
+        ix->gemm_splits = src->gemm_splits; ix->sample_pass = src->sample_pass; ix->pair_mode = src->pair_mode;
+        ix->share = src->share;
+        std::lock_guard<std::mutex> lk2(ix->share->mu);
+        ++ix->share->refs;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    for (auto& ev : ix->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { cudaGetLastError(); index_free(ix); return fail(XS_ERR_CUDA, "xs_index_clone: %s", cudaGetErrorString(e)); }
+    *out = ix;
+    return XS_OK;
+}
 
 extern "C" int xs_index_info(const xs_index* ix, int64_t* n, int* d, int* device, int64_t* device_bytes) {
     if (!ix) return fail(XS_ERR_ARG, "null index");

@@ -41,6 +41,16 @@ class ExactIndex:
                   "xs_index_create_dev")
         return self
 
+    def clone(self) -> "ExactIndex":
+        """A second search lane over the same device-resident database (xs_index_clone): shares the database
+        arrays, owns its workspaces -- searches on ``self`` and on the clone may overlap on two streams."""
+        other = type(self).__new__(type(self))
+        other._lib = self._lib
+        other._h = C.c_void_p()
+        other.N, other.D, other.device, other.renormalised = self.N, self.D, self.device, self.renormalised
+        nat.check(self._lib.xs_index_clone(self._h, C.byref(other._h)), "xs_index_clone")
+        return other
+
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -42,7 +42,7 @@ class ShardedSearcher:
     is ONE all-gather; ``merge(packed_all, world, nq, k) -> (ids [nq,k], sims [nq,k])``.
     """
 
-    def __init__(self, local_search, merge, group=None, exchange=None, exchange_pipelined=False):
+    def __init__(self, local_search, merge, group=None, exchange=None, exchange_pipelined=False, lane_stream=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -55,6 +55,10 @@ class ShardedSearcher:
         self.exchange_pipelined = bool(exchange_pipelined)
         self._inflight = [None, None]
         self._gathered = {}
+        # lane_stream(slot) -> a CUDA stream owned by the local searcher's lane `slot` (CudaShard with two lanes):
+        # the pipelined form then runs slot 0 and slot 1 searches on two streams, so that the selection / rescoring
+        # tail of one batch overlaps the database scan of the next.  None = everything on the caller's stream.
+        self.lane_stream = lane_stream
         # callbacks may take a result-slot argument (the CUDA shard does: two result buffers alternate)
         import inspect
         self._ls_slot = "slot" in inspect.signature(local_search).parameters
@@ -77,13 +81,30 @@ class ShardedSearcher:
             if self._inflight[slot] is not None:
                 self._inflight[slot].result()       # the slot's previous merge must be enqueued before its next push
             self.exchange.before_local_search(slot)
+        lane = self.lane_stream(slot) if self.lane_stream is not None else None
+        if lane is not None and blocking:
+            torch.cuda.current_stream(lane.device).wait_stream(lane)   # an uncollected pipelined search of this lane goes first
+            lane = None
+        if lane is None:
+            return self._enqueue(queries, k, nq, slot, use_peer, blocking, None)
+        lane.wait_stream(torch.cuda.current_stream(lane.device))     # the queries (and this slot's previous merge) come first
+        with torch.cuda.stream(lane):
+            pending = self._enqueue(queries, k, nq, slot, use_peer, blocking, lane)
+        return pending
+
+    def _enqueue(self, queries, k, nq, slot, use_peer, blocking, lane):
+        import torch
         packed = self.local_search(queries, k, slot) if self._ls_slot else self.local_search(queries, k)
         if use_peer:
             self.exchange.push(packed, slot, overlap=not blocking)
             self._inflight[slot] = _PendingPeer(self, nq, k, slot)
             return self._inflight[slot]
         if self.world == 1:
-            return _Pending(self, None, packed, nq, k, slot)
+            done = None
+            if lane is not None:
+                done = torch.cuda.Event()
+                done.record(lane)
+            return _Pending(self, None, packed, nq, k, slot, done)
         key = (nq, k, packed.device, slot)
         if key not in self._gathered:
             self._gathered[key] = torch.empty((self.world * packed.numel(),), dtype=torch.uint8, device=packed.device)
@@ -93,11 +114,14 @@ class ShardedSearcher:
 
 
 class _Pending:
-    def __init__(self, owner, work, buf, nq, k, slot):
-        self.owner, self.work, self.buf, self.nq, self.k, self.slot = owner, work, buf, nq, k, slot
+    def __init__(self, owner, work, buf, nq, k, slot, done=None):
+        self.owner, self.work, self.buf, self.nq, self.k, self.slot, self.done = owner, work, buf, nq, k, slot, done
 
     def result(self):
         if self.work is None:
+            if self.done is not None:                       # searched on a lane stream: the caller's stream waits for it
+                import torch
+                torch.cuda.current_stream().wait_event(self.done)
             return unpack(self.buf, self.nq, self.k)
         self.work.wait()                                    # stream-level wait, the host does not block
         o = self.owner
@@ -224,13 +248,26 @@ def unpack(packed, nq: int, k: int):
 class CudaShard:
     """The CUDA local searcher + merge for one rank: wraps an ExactIndex built with ``id_offset``."""
 
-    def __init__(self, index, device: int):
+    def __init__(self, index, device: int, lanes: int = 1):
         import torch
         self.torch = torch
         self.index = index
         self.device = device
         self.lib = nat.load()
         self._out = {}
+        # lanes = 2: result slot 1 searches through a clone of the index (own workspaces, same database arrays) and
+        # both slots get a stream of their own -- hand `lane_stream` to ShardedSearcher to overlap consecutive batches
+        self.lanes = [index] + [index.clone() for _ in range(max(0, int(lanes) - 1))]
+        self._streams = [torch.cuda.Stream(device) for _ in self.lanes] if len(self.lanes) > 1 else []
+
+    def lane_stream(self, slot: int):
+        return self._streams[slot % len(self._streams)] if self._streams else None
+
+    def close(self):
+        for ix in self.lanes[1:]:
+            ix.close()
+        self.lanes = self.lanes[:1]
+        self._streams = []
 
     def _buffers(self, nq, k, slot=0):
         torch = self.torch
@@ -249,8 +286,8 @@ class CudaShard:
         nq = int(queries.shape[0])
         ids, sims, status, packed = self._buffers(nq, k, slot)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.index.search_device(queries.data_ptr(), nq, k, ids.data_ptr(), sims.data_ptr(),
-                                 status_ptr=status.data_ptr(), stream=stream)
+        self.lanes[slot % len(self.lanes)].search_device(queries.data_ptr(), nq, k, ids.data_ptr(), sims.data_ptr(),
+                                                        status_ptr=status.data_ptr(), stream=stream)
         return packed
 
     def uncertified(self, nq, k) -> int:

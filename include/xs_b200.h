@@ -84,6 +84,15 @@ XS_API int xs_index_create_dev(const float* db_dev, int64_t n, int d,
 
 XS_API int xs_index_destroy(xs_index* index);
 
+/*
+ * A second search lane over the same database (no reference counterpart).  The clone shares the read-only
+ * database arrays of `src` (they are freed when the last of the index and its clones is destroyed, in any
+ * order) and owns its workspaces, stream, tunables and statistics, so searches on the index and on the clone
+ * may run concurrently on two streams: the latency-bound selection / rescoring of one batch then overlaps the
+ * database scan of the next.  Costs workspace memory only.
+ */
+XS_API int xs_index_clone(xs_index* src, xs_index** out);
+
 /* n rows, d columns, device ordinal and device bytes held; any out pointer may be NULL. */
 XS_API int xs_index_info(const xs_index* index, int64_t* n, int* d, int* device, int64_t* device_bytes);
 XS_API int xs_index_stats(const xs_index* index, xs_stats* out);

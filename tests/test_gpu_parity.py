@@ -425,6 +425,42 @@ def test_query_expansion_and_database_augmentation(pkg, synth, oracle, golden):
     np.testing.assert_array_equal(pkg.initial_rank(torch.from_numpy(feat), 7), got)
 
 
+def test_two_lanes_pipelined_and_clone_lifetime(pkg, synth, oracle):
+    """xs_index_clone: a second lane over the same database arrays.  Pipelined searches alternate between the index
+    and its clone on two streams; results equal the plain search; the clone outlives its parent."""
+    import importlib
+    import torch
+    sharded = importlib.import_module(pkg.__name__ + ".sharded")
+    v, q = synth.gaussian(30000, 96, d=256)
+    index = pkg.ExactIndex(v.T)
+    batches = [np.ascontiguousarray(q.T[i:i + 32]) for i in (0, 32, 64)]
+    want = [index.search(b, 20) for b in batches]
+    shard = sharded.CudaShard(index, 0, lanes=2)
+    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, lane_stream=shard.lane_stream)
+    qd = [torch.from_numpy(b).cuda() for b in batches]
+    pending, got = None, []
+    for it in range(30):
+        nxt = (it % 3, searcher.search_async(qd[it % 3], 20))
+        if pending is not None:
+            ids, sims = pending[1].result()
+            got.append((pending[0], ids.cpu().numpy().copy(), sims.cpu().numpy().copy()))
+        pending = nxt
+    ids, sims = pending[1].result()
+    got.append((pending[0], ids.cpu().numpy().copy(), sims.cpu().numpy().copy()))
+    assert len(got) == 30
+    for b, ids, sims in got:
+        np.testing.assert_array_equal(ids, want[b][0])
+        np.testing.assert_array_equal(sims, want[b][1])
+    ids, sims = searcher.search(qd[1], 20)                            # blocking form right after pipelined ones
+    np.testing.assert_array_equal(ids.cpu().numpy(), want[1][0])
+    clone = shard.lanes[1]
+    assert clone.device_bytes == 0 and index.device_bytes > 0          # the clone owns workspaces only
+    index.close()                                                      # the database arrays live on with the clone
+    ids2, sims2 = clone.search(batches[2], 20)
+    np.testing.assert_array_equal(ids2, want[2][0])
+    shard.close()
+
+
 def test_self_knn_pipelined_batches_and_reruns(pkg, synth, oracle):
     """More rows than one 8192-row batch (two-deep pipeline) and duplicated rows (certificate fails ->
     exact re-run inside the pipeline): every row still gets its own id first and exact neighbours."""
