@@ -80,6 +80,9 @@ struct xs_index {
     CUtensorMap tmap_dbt_b, tmap_dbt_h;          // tiled twin: boxes of 256 / 128 rows, each one contiguous run
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
+    int self_lanes = 1;                           // xs_self_knn: 2 = batches alternate between this index and an internal clone
+                                                  // (measured: 1.03 s either way at 500k x 500k -- the loop is tensor/power bound)
+    xs_index* self_lane = nullptr;                // that clone (created on first use, freed with the index)
     // workspace
     Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
@@ -167,6 +170,7 @@ static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_of
 
 static void index_free(xs_index* ix) {
     if (!ix) return;
+    if (ix->self_lane) { index_free(ix->self_lane); ix->self_lane = nullptr; }
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (Buf* b : {&ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
@@ -296,28 +300,34 @@ extern "C" int xs_index_destroy(xs_index* ix) { index_free(ix); return XS_OK; }
 
 // A second search lane over the same database: shares the (read-only) database arrays and tensor maps, owns its
 // workspaces, stream, tunables and statistics -- so two searches can be in flight on two streams at once.
-extern "C" int xs_index_clone(xs_index* src, xs_index** out) {
-    if (!src || !out) return fail(XS_ERR_ARG, "null pointer");
+static void copy_tunables(xs_index* dst, const xs_index* src) {
+    dst->eps_sigmas = src->eps_sigmas; dst->scan_max_q = src->scan_max_q; dst->force_path = src->force_path;
+    dst->gemm_splits = src->gemm_splits; dst->sample_pass = src->sample_pass; dst->pair_mode = src->pair_mode;
+}
+
+// caller holds src->mu
+static int clone_locked(xs_index* src, xs_index** out) {
     *out = nullptr;
     CU_TRY(cudaSetDevice(src->device));
     xs_index* ix = new xs_index();
-    {
-        std::lock_guard<std::mutex> lk(src->mu);
-        ix->device = src->device; ix->num_sms = src->num_sms;
-        ix->n = src->n; ix->n_pad = src->n_pad; ix->id_offset = src->id_offset; ix->d = src->d; ix->d_pad = src->d_pad;
-        ix->db16 = src->db16; ix->db32 = src->db32; ix->dstats = src->dstats; ix->db16t = src->db16t;
-        ix->tmap_db_b = src->tmap_db_b; ix->tmap_db_a = src->tmap_db_a; ix->tmap_dbt_b = src->tmap_dbt_b; ix->tmap_dbt_h = src->tmap_dbt_h;
-        ix->eps_sigmas = src->eps_sigmas; ix->scan_max_q = src->scan_max_q; ix->force_path = src->force_path;
-        ix->gemm_splits = src->gemm_splits; ix->sample_pass = src->sample_pass; ix->pair_mode = src->pair_mode;
-        ix->share = src->share;
-        std::lock_guard<std::mutex> lk2(ix->share->mu);
-        ++ix->share->refs;
-    }
+    ix->device = src->device; ix->num_sms = src->num_sms;
+    ix->n = src->n; ix->n_pad = src->n_pad; ix->id_offset = src->id_offset; ix->d = src->d; ix->d_pad = src->d_pad;
+    ix->db16 = src->db16; ix->db32 = src->db32; ix->dstats = src->dstats; ix->db16t = src->db16t;
+    ix->tmap_db_b = src->tmap_db_b; ix->tmap_db_a = src->tmap_db_a; ix->tmap_dbt_b = src->tmap_dbt_b; ix->tmap_dbt_h = src->tmap_dbt_h;
+    copy_tunables(ix, src);
+    ix->share = src->share;
+    { std::lock_guard<std::mutex> lk2(ix->share->mu); ++ix->share->refs; }
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     for (auto& ev : ix->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e != cudaSuccess) { cudaGetLastError(); index_free(ix); return fail(XS_ERR_CUDA, "xs_index_clone: %s", cudaGetErrorString(e)); }
     *out = ix;
     return XS_OK;
+}
+
+extern "C" int xs_index_clone(xs_index* src, xs_index** out) {
+    if (!src || !out) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(src->mu);
+    return clone_locked(src, out);
 }
 
 extern "C" int xs_index_info(const xs_index* ix, int64_t* n, int* d, int* device, int64_t* device_bytes) {
@@ -339,6 +349,7 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "sample_pass")) ix->sample_pass = (int)value;
     else if (!strcmp(name, "pair_mode")) ix->pair_mode = (int)value;
     else if (!strcmp(name, "timing")) ix->timing = (int)value;
+    else if (!strcmp(name, "self_lanes")) ix->self_lanes = ((int)value >= 2) ? 2 : 1;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
 }
@@ -764,12 +775,20 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
     if (!out_idx) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(ix->mu);
     CU_TRY(cudaSetDevice(ix->device));
-    ix->cur = ix->stream;
     const int64_t batch = 8192;
+    // Two lanes: even batches run on this index, odd ones on an internal clone (same database arrays, own workspaces
+    // and stream), so the selection / rescoring / copy-out of one batch overlaps the GEMM of the next.
+    const bool two = ix->self_lanes >= 2 && q_end - q_begin > batch;
+    if (two && !ix->self_lane) XS_TRY(clone_locked(ix, &ix->self_lane));
+    xs_index* lane[2] = {ix, two ? ix->self_lane : ix};
+    if (two) copy_tunables(lane[1], ix);
     const size_t nb_i = (size_t)batch * k * sizeof(int64_t), nb_s = (size_t)batch * k * sizeof(float), nb_st = (size_t)(batch + 1) * sizeof(int);
-    XS_TRY(ix->status.ensure((size_t)batch * sizeof(int)));
-    XS_TRY(ix->out_idx.ensure(nb_i));
-    XS_TRY(ix->out_score.ensure(nb_s));
+    for (int l = 0; l < (two ? 2 : 1); ++l) {
+        lane[l]->cur = lane[l]->stream;
+        XS_TRY(lane[l]->status.ensure((size_t)batch * sizeof(int)));
+        XS_TRY(lane[l]->out_idx.ensure(nb_i));
+        XS_TRY(lane[l]->out_score.ensure(nb_s));
+    }
     XS_TRY(ix->h_idx.ensure(2 * nb_i));
     XS_TRY(ix->h_score.ensure(2 * nb_s));
     XS_TRY(ix->h_status.ensure(2 * nb_st));
@@ -791,14 +810,16 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
                 if (!(hst[1 + q] & ST_UNCERTIFIED)) { ++q; continue; }
                 int64_t e = q + 1;
                 while (e < pc && e - q < 16 && (hst[1 + e] & ST_UNCERTIFIED)) ++e;
-                // rare: exact re-run after everything in flight has finished (the device result buffers are shared)
-                CU_TRY(cudaStreamSynchronize(ix->stream));
+                // rare: exact re-run on the lane that produced the batch, after its work in flight has finished (the
+                // lane's device result buffers are reused by its next batch)
+                xs_index* L = lane[ph];
+                CU_TRY(cudaStreamSynchronize(L->stream));
                 int launches = 0;
-                XS_TRY(run_exact(ix, ix->db32 + (size_t)(pr0 + q) * ix->d_pad, e - q, k, pr0 + q, ix->out_idx.as<int64_t>(),
-                                 ix->out_score.as<float>(), nullptr, &launches));
-                CU_TRY(cudaMemcpyAsync(hi + q * k, ix->out_idx.p, (size_t)(e - q) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
-                CU_TRY(cudaMemcpyAsync(hs + q * k, ix->out_score.p, (size_t)(e - q) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-                CU_TRY(cudaStreamSynchronize(ix->stream));
+                XS_TRY(run_exact(L, L->db32 + (size_t)(pr0 + q) * L->d_pad, e - q, k, pr0 + q, L->out_idx.as<int64_t>(),
+                                 L->out_score.as<float>(), nullptr, &launches));
+                CU_TRY(cudaMemcpyAsync(hi + q * k, L->out_idx.p, (size_t)(e - q) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, L->stream));
+                CU_TRY(cudaMemcpyAsync(hs + q * k, L->out_score.p, (size_t)(e - q) * k * sizeof(float), cudaMemcpyDeviceToHost, L->stream));
+                CU_TRY(cudaStreamSynchronize(L->stream));
                 total.n_exact_rerun += e - q; total.gpu_launches += launches;
                 q = e;
             }
@@ -813,32 +834,32 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
     for (int64_t r0 = q_begin; r0 < q_end && rc == XS_OK; r0 += batch, ++b) {
         const int64_t c = (q_end - r0 < batch) ? q_end - r0 : batch;
         const int h = b & 1;
+        xs_index* L = lane[h];
         CoreArgs a{};
-        a.q32 = ix->db32 + (size_t)r0 * ix->d_pad; a.nq = c; a.k = k; a.prep = true; a.prep_renorm = false;   // rows are used as stored
-        a.path = choose_path(ix, c, k);
-        a.tmap_a = (a.path == PATH_GEMM) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
-        a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
-        rc = search_core(ix, a);
+        a.q32 = L->db32 + (size_t)r0 * L->d_pad; a.nq = c; a.k = k; a.prep = true; a.prep_renorm = false;   // rows are used as stored
+        a.path = choose_path(L, c, k);
+        a.tmap_a = (a.path == PATH_GEMM) ? &L->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
+        a.out_idx = L->out_idx.as<int64_t>(); a.out_score = L->out_score.as<float>(); a.status = L->status.as<int>();
+        rc = search_core(L, a);
         if (rc != XS_OK) break;
-        total.n_queries += c; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;
+        total.n_queries += c; total.gpu_launches += L->stats.gpu_launches; total.path = L->stats.path;
         char* hi = static_cast<char*>(ix->h_idx.p) + h * nb_i;
         char* hs = static_cast<char*>(ix->h_score.p) + h * nb_s;
         int* hst = reinterpret_cast<int*>(static_cast<char*>(ix->h_status.p) + h * nb_st);
-        cudaError_t e = cudaMemcpyAsync(hi, a.out_idx, (size_t)c * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hs, a.out_score, (size_t)c * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hst + 1, a.status, (size_t)c * sizeof(int), cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(hst, ix->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(done[h], ix->stream);
+        cudaError_t e = cudaMemcpyAsync(hi, a.out_idx, (size_t)c * k * sizeof(int64_t), cudaMemcpyDeviceToHost, L->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hs, a.out_score, (size_t)c * k * sizeof(float), cudaMemcpyDeviceToHost, L->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hst + 1, a.status, (size_t)c * sizeof(int), cudaMemcpyDeviceToHost, L->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hst, L->ncand.p, sizeof(int), cudaMemcpyDeviceToHost, L->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[h], L->stream);
         if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "xs_self_knn: %s", cudaGetErrorString(e)); break; }
         if (have_prev) rc = drain(prev_h, prev_r0, prev_c, prev_coarse);
         prev_r0 = r0; prev_c = c; prev_h = h; prev_coarse = a.path != PATH_EXACT; have_prev = true;
     }
     if (rc == XS_OK && have_prev) rc = drain(prev_h, prev_r0, prev_c, prev_coarse);
-    cudaStreamSynchronize(ix->stream);
+    for (int l = 0; l < (two ? 2 : 1); ++l) { cudaStreamSynchronize(lane[l]->stream); lane[l]->ev_valid = false; }
     cudaEventDestroy(done[0]);
     cudaEventDestroy(done[1]);
     ix->stats = total;
-    ix->ev_valid = false;
     return rc;
 }
 

@@ -224,6 +224,7 @@ XS_API int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* ind
  *   "timing"       int    1 = record CUDA events so xs_index_stats reports ms_coarse/ms_total (0)
  *   "pair_mode"    int    1 = CTA-pair (cta_group::2) GEMM shape for batches > 128 queries   (1)
  *   "sample_pass"  int    1 = threshold bootstrap pass before the GEMM                    (1)
+ *   "self_lanes"   int    2 = xs_self_knn alternates its batches between the index and an internal clone (1)
  */
 XS_API int xs_set_param(xs_index* index, const char* name, double value);
 

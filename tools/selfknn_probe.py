@@ -20,10 +20,14 @@ K = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 dev = torch.device("cuda", 0)
 rows = bench.synth_rows_device(torch, N, 2048, dev, 0)
 ix = pkg.ExactIndex.from_device(rows.data_ptr(), N, 2048, 0)
+LANES = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+ix.set_param("self_lanes", LANES)
+ix.self_knn(K, 0, min(N, 20000))                     # warm-up: workspaces (and the second lane) exist before the timed run
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 sims, ids = ix.self_knn(K)
 dt = time.perf_counter() - t0
+print(f"lanes={LANES}", end=" ")
 st = ix.stats()
 print(f"self-kNN N={N} k={K}: {dt:.3f} s wall ({N/dt:.0f} rows/s, {2.0*N*N*2048/dt/1e12:.0f} TFLOP/s incl. D2H of {ids.nbytes/1e6:.0f}+{sims.nbytes/1e6:.0f} MB), stats {st}")
 assert (ids[:, 0] == np.arange(N)).all(), "own id must come first"
