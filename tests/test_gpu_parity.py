@@ -474,9 +474,14 @@ def test_self_knn_pipelined_batches_and_reruns(pkg, synth, oracle):
     _check_lists(oracle, ids[pick], ri, s64, "self-kNN pipelined")
     sub_s, sub_i = ix.self_knn(10, 9000, 9100)              # a row range
     np.testing.assert_array_equal(sub_i, ids[9000:9100])
+    ix.set_param("self_lanes", 2)                           # batches alternate between the index and an internal clone
+    sims2, ids2 = ix.self_knn(10)
+    np.testing.assert_array_equal(ids2, ids)
+    np.testing.assert_array_equal(sims2, sims)
     ix.close()
     vt, _ = synth.ties(9000, 1, d=64, n_distinct=300)       # every row has 29 exact duplicates
     ix = pkg.ExactIndex(vt.T)
+    ix.set_param("self_lanes", 2)                           # the exact re-run then happens on the lane that owns the batch
     sims, ids = ix.self_knn(8)
     st = ix.stats()
     assert (ids[:, 0] == np.arange(9000)).all()
