@@ -13,12 +13,9 @@ from .index import ExactIndex
 
 class BaseKNN(object):
     def __init__(self, database, method):
-        # knn.py:10-15 -- fp32, C-contiguous host copy owned by the object
-        if database.dtype != np.float32:
-            database = database.astype(np.float32)
-        self.N = len(database)
-        self.D = database[0].shape[-1]
-        self.database = database if database.flags['C_CONTIGUOUS'] else np.ascontiguousarray(database)
+        # same contract as knn.py:10-15: the object owns an fp32, C-contiguous host copy and exposes N, D, database
+        self.database = np.ascontiguousarray(database, dtype=np.float32)
+        self.N, self.D = int(self.database.shape[0]), int(self.database.shape[-1])
         self.method = method
 
     def add(self, batch_size=10000):
@@ -33,11 +30,7 @@ class BaseKNN(object):
             self.index = ExactIndex(aug, renormalise=False, device=self.device)
 
     def search(self, queries, k):
-        # knn.py:25-31
-        if not queries.flags['C_CONTIGUOUS']:
-            queries = np.ascontiguousarray(queries)
-        if queries.dtype != np.float32:
-            queries = queries.astype(np.float32)
+        queries = np.ascontiguousarray(queries, dtype=np.float32)       # the cast knn.py:25-29 applies before faiss
         if self.method == 'cosine':
             ids, sims = self.index.search(queries, k)
             return sims, ids
