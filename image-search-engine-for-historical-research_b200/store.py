@@ -59,6 +59,45 @@ def convert_pickle(pickle_path: str, directory: str) -> str:
     return save_store(directory, vecs, paths)
 
 
+def load_distractors(pt_path: str):
+    """Reader for the reference's R1M distractor file (``torch.save(vecs, '<net>_vecs_revisitop1m.pt')``,
+    src/extract_1m.py:98; read back at src/test_rOP1m.py:137-138): ``vecs (D, N)`` as numpy."""
+    import torch
+    t = torch.load(pt_path, map_location="cpu")
+    return t.numpy() if hasattr(t, "numpy") else np.asarray(t)
+
+
+def convert_pt(pt_path: str, directory: str, paths=None) -> str:
+    """One-off conversion of the distractor ``.pt`` file into a store."""
+    return save_store(directory, load_distractors(pt_path), paths)
+
+
+def append_store(directory: str, vecs, paths=None, chunk: int = 65536) -> str:
+    """Append the columns of ``vecs (D, M)`` to an existing store -- the store form of
+    ``vecs = np.concatenate([vecs, vecs_1m], axis=1)`` (src/test_rOP1m.py:139).  The rows file is rewritten
+    block by block into a new file and swapped in, so a reader holding the old map keeps a consistent view."""
+    vecs = np.asarray(vecs)
+    old, old_paths = open_store(directory)
+    n, d = old.shape
+    if vecs.shape[0] != d:
+        raise ValueError(f"dimension mismatch: store has D={d}, got {vecs.shape[0]}")
+    m = vecs.shape[1]
+    tmp = os.path.join(directory, ROWS_FILE + ".tmp")
+    out = np.lib.format.open_memmap(tmp, mode="w+", dtype=np.float32, shape=(n + m, d))
+    for lo in range(0, n, chunk):
+        out[lo:min(n, lo + chunk)] = old[lo:min(n, lo + chunk)]
+    for lo in range(0, m, chunk):
+        hi = min(m, lo + chunk)
+        out[n + lo:n + hi] = vecs[:, lo:hi].T
+    out.flush()
+    del out, old
+    os.replace(tmp, os.path.join(directory, ROWS_FILE))
+    new_paths = list(old_paths) + (list(paths) if paths is not None else [])
+    with open(os.path.join(directory, PATHS_FILE), "w") as f:
+        json.dump(new_paths, f)
+    return directory
+
+
 def index_from_store(directory: str, renormalise: bool = False, device: int = 0):
     """Device index straight from the mapped rows (uploaded in 8k-row tiles by xs_index_create)."""
     from .index import ExactIndex

@@ -57,3 +57,22 @@ def test_search_offline_matches_reference_statements(pkg):
         np.testing.assert_allclose(got_s[i], scores[parts][ranks], rtol=1e-6)
         np.testing.assert_allclose(scores[got_r[i]], got_s[i], rtol=1e-6)
     assert got_r.dtype == np.int64 and got_s.dtype == np.float32
+
+
+def test_distractor_file_and_append(tmp_path, pkg, synth):
+    """The R1M flow of test_rOP1m.py:137-139: dataset vectors + a torch-saved distractor matrix, concatenated."""
+    import torch
+    vecs, _ = synth.gaussian(300, 1, d=32)
+    extra, _ = synth.gaussian(500, 1, d=32)
+    pt = os.path.join(tmp_path, "net_vecs_revisitop1m.pt")
+    torch.save(torch.from_numpy(extra), pt)
+    np.testing.assert_array_equal(pkg.store.load_distractors(pt), extra)
+    d = pkg.store.save_store(os.path.join(tmp_path, "db"), vecs, [f"a{i}" for i in range(300)])
+    pkg.store.append_store(d, pkg.store.load_distractors(pt), [f"b{i}" for i in range(500)])
+    rows, paths = pkg.store.open_store(d)
+    assert rows.shape == (800, 32) and rows.dtype == np.float32 and len(paths) == 800 and paths[300] == "b0"
+    np.testing.assert_array_equal(np.asarray(rows).T, np.concatenate([vecs, extra], axis=1))
+    d2 = pkg.store.convert_pt(pt, os.path.join(tmp_path, "only1m"))
+    assert pkg.store.open_store(d2)[0].shape == (500, 32)
+    with pytest.raises(ValueError):
+        pkg.store.append_store(d, np.zeros((31, 4), np.float32))
