@@ -51,6 +51,7 @@ def load() -> C.CDLL:
         lib.xs_last_error.restype = C.c_char_p
         lib.xs_last_error.argtypes = []
         lib.xs_abi_version.restype = i32
+        lib.xs_abi_version.argtypes = []
         lib.xs_device_count.argtypes = [C.POINTER(i32)]
         lib.xs_index_create.argtypes = [p, i32, i64, i32, i64, i64, i32, i32, i64, C.POINTER(p)]
         lib.xs_index_create_dev.argtypes = [p, i64, i32, i32, i32, i64, C.POINTER(p)]

@@ -27,6 +27,35 @@ def test_header_and_library_agree(nat):
     assert lib.xs_abi_version() == 1
 
 
+def test_ctypes_signatures_match_the_header(nat):
+    """Every prototype in the header against the argtypes the ctypes mirror declares: same arity, and pointer /
+    64-bit / 32-bit / double parameters in the same positions (a mismatch here corrupts the stack silently)."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "xs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    lib = nat.load()
+    protos = re.findall(r"XS_API\s+[\w\s\*]+?\b(xs_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == len(nat.ABI_SYMBOLS)
+    for name, args in protos:
+        params = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+        argtypes = getattr(lib, name).argtypes
+        assert argtypes is not None and len(argtypes) == len(params), (name, params, argtypes)
+        for ptext, ctype in zip(params, argtypes):
+            if "*" in ptext:
+                kind = "ptr"
+            elif re.search(r"\bint64_t\b", ptext):
+                kind = "i64"
+            elif re.search(r"\bdouble\b", ptext):
+                kind = "f64"
+            else:
+                kind = "i32"
+            if kind == "ptr":
+                ok = ctype in (C.c_void_p, C.c_char_p) or hasattr(ctype, "contents") or issubclass(ctype, C._Pointer)
+            else:
+                ok = ctype is {"i64": C.c_int64, "f64": C.c_double, "i32": C.c_int}[kind]
+            assert ok, (name, ptext, ctype)
+
+
 def test_no_torch_types_in_abi():
     hdr = open(os.path.join(ROOT, "include", "xs_b200.h")).read()
     assert "torch" not in hdr.lower().replace("torch-extension", "") and "at::" not in hdr

@@ -98,3 +98,59 @@ def test_k_larger_than_a_shard(tmp_path, synth, oracle):
     vecs, qvecs = synth.gaussian(21, 2, d=8)
     ref_ids, _ = oracle.topk_ip(vecs, qvecs, 15)
     np.testing.assert_array_equal(outs[0]["ids"], ref_ids)
+
+
+def test_shard_bounds_and_packing_properties():
+    """Host-side invariants of the sharding helpers (no process group needed)."""
+    import importlib
+    import torch
+    from hypothesis import given, settings, strategies as st
+    from conftest import PKG_NAME
+    sharded = importlib.import_module(PKG_NAME + ".sharded")
+    oracle = importlib.import_module("oracle.oracle")
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 10_000_000), st.integers(1, 16))
+    def bounds(n, world):
+        b = sharded.shard_bounds(n, world)
+        sizes = np.diff(b)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+        assert (sizes >= 0).all() and sizes.max() - sizes.min() <= 1 and (np.diff(sizes) <= 0).all()
+    bounds()
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(1, 300), st.integers(1, 130))
+    def packing(nq, k):
+        nb = sharded.packed_bytes(nq, k)
+        assert nb % 16 == 0 and 0 <= nb - nq * k * 12 < 16
+        buf = torch.zeros(nb, dtype=torch.uint8)
+        ids, sims = sharded.unpack(buf, nq, k)
+        ids.copy_(torch.arange(nq * k, dtype=torch.int64).view(nq, k))
+        sims.fill_(1.5)
+        ids2, sims2 = sharded.unpack(buf, nq, k)                     # views of the same bytes
+        assert ids2[-1, -1].item() == nq * k - 1 and sims2[0, 0].item() == 1.5
+    packing()
+
+    @settings(max_examples=50, deadline=None)
+    @given(st.integers(2, 5), st.integers(1, 6), st.integers(1, 12), st.integers(0, 2**31 - 1))
+    def merge_is_order_independent(g, nq, k, seed):
+        rng = np.random.default_rng(seed)
+        # g shards with disjoint id ranges, each list sorted (score desc, id asc) as the local search leaves it
+        ids = np.empty((g, nq, k), np.int64)
+        sims = np.empty((g, nq, k), np.float32)
+        for p in range(g):
+            for j in range(nq):
+                i = np.sort(rng.choice(1000, size=k, replace=False)) + 1000 * p
+                s = rng.integers(0, 4, size=k).astype(np.float32)    # heavy ties on purpose
+                order = np.lexsort((i, -s))
+                ids[p, j], sims[p, j] = i[order], s[order]
+        a_i, a_s = oracle.merge_parts(ids, sims, k)
+        perm = rng.permutation(g)
+        b_i, b_s = oracle.merge_parts(ids[perm], sims[perm], k)
+        np.testing.assert_array_equal(a_i, b_i)
+        np.testing.assert_array_equal(a_s, b_s)
+        for j in range(nq):                                            # and it is the top-k of the union
+            flat_i, flat_s = ids[:, j].reshape(-1), sims[:, j].reshape(-1)
+            order = np.lexsort((flat_i, -flat_s))[:k]
+            np.testing.assert_array_equal(a_i[j], flat_i[order])
+    merge_is_order_independent()
