@@ -148,38 +148,87 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def set_blas_threads(n: int) -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its children, which would deflate every CPU number: pin the BLAS pool
+    to the cores this process may actually use.  Returns the thread count in effect."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        pools = threadpoolctl.threadpool_info()
+        got = max((p.get("num_threads", 1) for p in pools if p.get("user_api") == "blas"), default=n)
+    except Exception:
+        got = n
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return int(got)
+
+
+def host_db(n_rows: int):
+    """The synthetic database in the reference's layout -- (D, N) C-contiguous fp32, unit-norm Gaussian rows, seed 0 --
+    generated on the host in 50k-row chunks."""
+    from concurrent.futures import ThreadPoolExecutor
+    vecs = np.empty((DIM, n_rows), dtype=np.float32)
+
+    def fill(lo):
+        hi = min(n_rows, lo + 50_000)
+        rng = np.random.default_rng([0, lo])                              # one stream per chunk: any thread count gives the same matrix
+        blk = rng.standard_normal((DIM, hi - lo), dtype=np.float32)      # drawn in the (D, N) layout: no transposed copy
+        blk /= np.linalg.norm(blk, axis=0, keepdims=True)
+        vecs[:, lo:hi] = blk
+
+    with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+        list(ex.map(fill, range(0, n_rows, 50_000)))
+    return vecs
+
+
 # ----------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference's own CPU path on the host cores: np.dot(vecs.T, qvecs) + np.argsort(-scores, axis=0)[:100]
+    (src/main_retrieve.py:175-176 as restated in oracle/oracle.py), every step over the FULL 1,007,000-row database
+    -- the same configuration as our arm.  Only if the whole run would not fit ~9 minutes is the row count reduced
+    (and the line says so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_rows = int(os.environ.get("XS_BENCH_REF_ROWS", "125875"))     # 1/8 of the database per step (~1 GB fp32)
-    rng = np.random.default_rng(0)
-    db = rng.standard_normal((sample_rows, DIM), dtype=np.float32)
-    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    cores = host_threads()
+    blas = set_blas_threads(cores)
+    rows = int(os.environ.get("XS_BENCH_REF_ROWS", str(N_ROWS)))
+    why = "XS_BENCH_REF_ROWS asks for a row sample" if rows != N_ROWS else ""
+    t_gen = time.time()
+    vecs = host_db(rows)
     q = np.random.default_rng(1).standard_normal((N_QUERIES, DIM), dtype=np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)
-    vecs, qvecs = reference_layout(db, q)
-    del db
-    # keep the whole run within ~2 minutes whatever K is: shrink the row sample if one step is too slow
-    t1 = cpu_reference_step(vecs, qvecs)
-    budget = 90.0
-    if args.steps * t1 > budget:
-        sample_rows = max(8192, int(sample_rows * budget / (args.steps * t1)))
-        vecs = np.ascontiguousarray(vecs[:, :sample_rows])
-    for _ in range(max(1, min(args.warmup, 2))):
+    qvecs = np.ascontiguousarray(q.T)
+    t_gen = time.time() - t_gen
+    warm = max(1, min(args.warmup, 2))
+    t1 = cpu_reference_step(vecs, qvecs)                    # first warm-up step, also sizes the run
+    budget = float(os.environ.get("XS_BENCH_REF_BUDGET_S", "540"))
+    if (args.steps + warm - 1) * t1 > budget:
+        rows = max(8192, int(rows * budget / ((args.steps + warm - 1) * t1)))
+        vecs = np.ascontiguousarray(vecs[:, :rows])
+        why = f"the full run would exceed {budget:.0f} s"
+    for _ in range(warm - 1):
         cpu_reference_step(vecs, qvecs)
     dt = sum(cpu_reference_step(vecs, qvecs) for _ in range(args.steps)) / args.steps
-    qps = N_QUERIES / (dt * N_ROWS / sample_rows)
-    cores = host_threads()
+    scale = N_ROWS / rows
+    qps = N_QUERIES / (dt * scale)
+    full = rows == N_ROWS
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * N_ROWS / sample_rows * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: 1,007,000 x 2048 fp32 DB, 70-query batch, exact top-100",
-                   "path": "np.dot(vecs.T, qvecs) + np.argsort(-scores, axis=0)[:100] (src/main_retrieve.py:175-176 as restated in oracle/oracle.py)"},
+                   "rows_per_step": rows, "same_config": full,
+                   "path": "np.dot(vecs.T, qvecs) + np.argsort(-scores, axis=0)[:100] (src/main_retrieve.py:175-176 as restated in oracle/oracle.py)",
+                   "host_threads": cores, "blas_threads": blas, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+                   "setup_s": round(t_gen, 1)},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"each step = all 70 queries x {sample_rows} rows of the 1,007,000 (time scaled x{N_ROWS / sample_rows:.1f} to the full DB); numpy/OpenBLAS threads = host default"},
+                         "sample": (f"each step = all 70 queries x all {rows} rows, measured, no scaling" if full else
+                                    f"each step = all 70 queries x {rows} rows of the 1,007,000 (time scaled x{scale:.2f}: {why})")
+                                   + f"; BLAS threads = {blas}, np.argsort is single-threaded"},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,6 +236,134 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------
+def merged_parity_check(torch, dist, index, queries, ids_pipelined, world, rank, n_check=8):
+    """N > 1: every shard answers `n_check` queries on its EXACT fp32 path (force_path 3), the lists are gathered and
+    rank 0 merges them on the host (descending score, ties by ascending id) and compares with what the pipelined,
+    exchanged search returned for the same queries."""
+    q = queries[:n_check].contiguous()
+    ids = torch.empty((n_check, TOPK), dtype=torch.int64, device=q.device)
+    sims = torch.empty((n_check, TOPK), dtype=torch.float32, device=q.device)
+    index.set_param("force_path", 3)
+    index.search_device(q.data_ptr(), n_check, TOPK, ids.data_ptr(), sims.data_ptr())
+    index.set_param("force_path", 0)
+    torch.cuda.synchronize()
+    all_i = [torch.empty_like(ids) for _ in range(world)]
+    all_s = [torch.empty_like(sims) for _ in range(world)]
+    dist.all_gather(all_i, ids)
+    dist.all_gather(all_s, sims)
+    if rank != 0:
+        return None
+    gi = torch.stack(all_i).cpu().numpy()
+    gs = torch.stack(all_s).cpu().numpy()
+    got = ids_pipelined[:n_check].cpu().numpy()
+    ok = True
+    for j in range(n_check):
+        fi, fs = gi[:, j].reshape(-1), gs[:, j].reshape(-1)
+        order = np.lexsort((fi, -fs.astype(np.float64)))[:TOPK]
+        ok = ok and bool(np.array_equal(fi[order], got[j]))
+    return ok
+
+
+def extra_configs(torch, pkg, index, rows, queries, q_np, peaks):
+    """The other single-GPU configurations of BASELINE.json on the same database (N = 1 only): cfg3, the batch-1
+    online query judged by HBM bandwidth, and a large batch judged by the bf16 tensor-pipe peak."""
+    out = {}
+    dev = queries.device
+    n = index.N
+    # ---- cfg3: batch 1 ------------------------------------------------------------------------------
+    q1 = queries[:1].contiguous()
+    ids = torch.empty((1, TOPK), dtype=torch.int64, device=dev)
+    sims = torch.empty((1, TOPK), dtype=torch.float32, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    steps = 200
+    for _ in range(10):
+        index.search_device(q1.data_ptr(), 1, TOPK, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        index.search_device(q1.data_ptr(), 1, TOPK, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / steps
+    path = index.stats()["path"]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ih, sh = index.search(q_np[:1], TOPK)
+    host_ms = (time.perf_counter() - t0) / steps * 1e3
+    index.set_param("timing", 1)
+    ks = []
+    for _ in range(20):
+        index.search_device(q1.data_ptr(), 1, TOPK, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+        ks.append(index.stats()["ms_coarse"])
+    index.set_param("timing", 0)
+    scan_ms = sum(ks) / len(ks)
+    index.set_param("force_path", 3)
+    ix_, sx_ = index.search(q_np[:1], TOPK)
+    index.set_param("force_path", 0)
+    algo = n * DIM * 2
+    out["cfg3_batch1"] = {
+        "workload": "cfg3: the same 1,007,000 x 2048 database, ONE query per call, exact top-100",
+        "path": {1: "bf16 HBM scan", 2: "tcgen05 GEMM", 3: "exact"}.get(path, "?"),
+        "value_qps_device_resident": 1e3 / dev_ms, "ms_per_query_device_resident": dev_ms,
+        "e2e_qps_host_buffers": 1e3 / host_ms, "e2e_ms_per_query": host_ms,
+        "roofline": {"bound": "hbm", "kernel": "scan_scores_kernel", "kernel_ms": scan_ms, "algorithmic_bytes": algo,
+                     "achieved": algo / (scan_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": algo / (scan_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "frac_whole_query": algo / (dev_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "uncertified": int(status.sum().item()),
+        "parity_vs_exact_path": bool(np.array_equal(ih, ix_) and np.allclose(sh, sx_, rtol=1e-6)),
+    }
+    # ---- large batch: tensor-pipe bound ---------------------------------------------------------------
+    nq = 4096
+    qb = synth_rows_device(torch, nq, DIM, dev, seed=2)
+    ib = torch.empty((nq, TOPK), dtype=torch.int64, device=dev)
+    sb = torch.empty((nq, TOPK), dtype=torch.float32, device=dev)
+    stb = torch.zeros((nq,), dtype=torch.int32, device=dev)
+    for _ in range(2):
+        index.search_device(qb.data_ptr(), nq, TOPK, ib.data_ptr(), sb.data_ptr(), status_ptr=stb.data_ptr())
+    torch.cuda.synchronize()
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        index.search_device(qb.data_ptr(), nq, TOPK, ib.data_ptr(), sb.data_ptr(), status_ptr=stb.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    call_ms = e0.elapsed_time(e1) / reps
+    index.set_param("timing", 1)
+    ks = []
+    for _ in range(3):
+        index.search_device(qb.data_ptr(), nq, TOPK, ib.data_ptr(), sb.data_ptr(), status_ptr=stb.data_ptr())
+        ks.append(index.stats()["ms_coarse"])
+    index.set_param("timing", 0)
+    gemm_ms = sum(ks) / len(ks)
+    flops = 2.0 * n * DIM * nq
+    # parity of a sample against the exact path
+    pick = torch.tensor([0, 1, 127, 128, 2047, 4095], device=dev)
+    qs = qb[pick].contiguous()
+    ie = torch.empty((len(pick), TOPK), dtype=torch.int64, device=dev)
+    se = torch.empty((len(pick), TOPK), dtype=torch.float32, device=dev)
+    index.set_param("force_path", 3)
+    index.search_device(qs.data_ptr(), len(pick), TOPK, ie.data_ptr(), se.data_ptr())
+    index.set_param("force_path", 0)
+    torch.cuda.synchronize()
+    burst, sust = peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained")
+    out["batched_4096"] = {
+        "workload": "the same database, 4096-query batch (CTA-pair tcgen05 GEMM, cta_group::2), exact top-100",
+        "queries_per_s": nq / (call_ms * 1e-3), "call_ms": call_ms, "gemm_kernel_ms": gemm_ms,
+        "algorithmic_flops": flops,
+        "roofline": {"bound": "tensor", "kernel": "gemm_topk_kernel<PAIR>", "unit": "TFLOP/s",
+                     "achieved_kernel": flops / (gemm_ms * 1e-3) / 1e12, "achieved_whole_call": flops / (call_ms * 1e-3) / 1e12,
+                     "peak_burst": burst, "peak_sustained": sust,
+                     "frac_kernel_of_burst": flops / (gemm_ms * 1e-3) / 1e12 / burst if burst else None,
+                     "frac_whole_call_of_burst": flops / (call_ms * 1e-3) / 1e12 / burst if burst else None,
+                     "frac_whole_call_of_sustained": flops / (call_ms * 1e-3) / 1e12 / sust if sust else None},
+        "uncertified": int(stb.sum().item()),
+        "parity_sample_vs_exact_path": bool(torch.equal(ib[pick], ie) and torch.allclose(sb[pick], se, rtol=1e-6)),
+    }
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -223,15 +400,13 @@ def run_ours(args):
     queries = synth_rows_device(torch, N_QUERIES, DIM, dev, seed=1)
     torch.cuda.synchronize()
     index = pkg.ExactIndex.from_device(rows.data_ptr(), hi - lo, DIM, local, renormalise=False, id_offset=lo)
-    shard = sharded.CudaShard(index, local, lanes=args.lanes)
     exchange = None
     if world > 1 and not replicas and args.exchange in ("auto", "peer"):
         try:                                                   # collective set-up: succeeds or fails on every rank together
-            exchange = sharded.PeerExchange(local, sharded.packed_bytes(N_QUERIES, TOPK))
+            exchange = sharded.PeerExchange(local, N_QUERIES, TOPK)
         except RuntimeError as e:
             print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
-    searcher = sharded.ShardedSearcher(shard.local_search, shard.merge, exchange=exchange, exchange_pipelined=args.exchange == "peer",
-                                       lane_stream=shard.lane_stream if args.lanes > 1 else None)
+    shard, searcher = sharded.make_searcher(index, local, lanes=args.lanes, exchange=exchange)
     if replicas:
         searcher.world = 1                                     # no exchange step at all
 
@@ -240,9 +415,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`) --------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        ids, sims = searcher.search(queries, TOPK)
+    def pipelined(n_steps):
+        """Two batches in flight: batch i's exchange / selection tail overlaps batch i+1's scan (two lanes per GPU)."""
+        pending, out = None, None
+        for _ in range(n_steps):
+            nxt = searcher.search_async(queries, TOPK)
+            if pending is not None:
+                out = pending.result()
+            pending = nxt
+        return pending.result()
+
+    # ---- device-resident throughput (`value`): warm up the SAME loop that is timed, both slots ------------
+    warm = max(args.warmup, 3)
+    pipelined(2 * warm + 2)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -250,18 +435,12 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    pending = None                                   # two batches in flight: batch i's all-gather overlaps batch i+1's scan
-    for _ in range(args.steps):
-        nxt = searcher.search_async(queries, TOPK)
-        if pending is not None:
-            ids, sims = pending.result()
-        pending = nxt
-    ids, sims = pending.result()
+    ids, sims = pipelined(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    uncert = shard.uncertified(N_QUERIES, TOPK)
-    launches_per_step = index.stats()["gpu_launches"] + ((2 if (exchange is not None and args.exchange == "peer") else 1) if (world > 1 and not replicas) else 0)
+    ids_pipelined = ids.clone()
+    launches_per_step = index.stats()["gpu_launches"] + (1 if (world > 1 and not replicas) else 0)
 
     # ---- end to end through the host-buffer call (`e2e`) ----------------------------------------------
     q_host = queries.cpu().pin_memory()
@@ -281,7 +460,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()
         return ids_pin, sims_pin
 
-    for _ in range(3):
+    for _ in range(max(warm, 5)):
         ids_h, sims_h = e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -290,6 +469,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    reruns = int(searcher.n_rerun) + (int(index.stats()["n_exact_rerun"]) if (world == 1 or replicas) else 0)
 
     # ---- dominant kernel, timed on its own stream by the library's CUDA events --------------------------
     coarse = []
@@ -302,17 +482,30 @@ def run_ours(args):
     index.set_param("timing", 0)
 
     # max over ranks
-    t = torch.tensor([ms, e2e_s * 1e3, coarse_ms, float(uncert)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, coarse_ms, float(reruns)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, coarse_ms, uncert = [float(x) for x in t.tolist()]
+    ms, e2e_ms, coarse_ms, reruns = [float(x) for x in t.tolist()]
 
-    # ---- parity spot check of the timed configuration against the exact fp32 path ---------------------
+    # ---- parity of the timed configuration ----------------------------------------------------------------
+    # local: the coarse path against this shard's exact fp32 path
     index.set_param("force_path", 3)
     ids_x, sims_x = index.search(q_np[:4], TOPK)
     index.set_param("force_path", 0)
     ids_l, sims_l = index.search(q_np[:4], TOPK)
     parity_ok = bool((ids_x == ids_l).all() and np.allclose(sims_x, sims_l, rtol=1e-6))
+    # merged (N > 1): the exchanged, pipelined answer against a host merge of every shard's exact path
+    merged_ok = None
+    if world > 1 and not replicas:
+        merged_ok = merged_parity_check(torch, dist, index, queries, ids_pipelined, world, rank)
+
+    peaks = {"hbm_gbs": measured_peaks()[0]}
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        peaks.update({k: v for k, v in json.load(open(ppath)).items() if isinstance(v, (int, float))})
+    extras = None
+    if world == 1 and not args.no_extra_configs:
+        extras = extra_configs(torch, pkg, index, rows, queries, q_np, peaks)
 
     if exchange is not None:
         exchange.close()                                       # collective: drains, barriers, unmaps
@@ -324,12 +517,13 @@ def run_ours(args):
     # ---- CPU baseline on the host cores (rank 0, N=1 only) -------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        blas = set_blas_threads(host_threads())
         sample_rows = 251_750
         vecs, qvecs = reference_layout(full[:sample_rows].cpu().numpy(), q_np)
         dt = min(cpu_reference_step(vecs, qvecs) for _ in range(2))
         qps_cpu = N_QUERIES / (dt * N_ROWS / sample_rows)
         cpu = {"value": qps_cpu, "unit": UNIT, "cores": host_threads(), "kind": "port",
-               "sample": f"np.dot + argsort[:100] (oracle.rank_ip), all 70 queries x {sample_rows} rows (1/4 of the DB, {dt:.2f} s), scaled x4 to the full DB"}
+               "sample": f"np.dot + argsort[:100] (oracle.rank_ip), all 70 queries x {sample_rows} rows (1/4 of the DB, {dt:.2f} s), scaled x4 to the full DB; BLAS threads = {blas}; the full-size run is `--impl reference`"}
         try:
             cpu["other_cpu_paths"] = cpu_extras(vecs, qvecs, N_ROWS / sample_rows)
         except Exception as e:                                   # informational only
@@ -338,26 +532,39 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     shard_rows = hi - lo
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    if os.path.exists(tpath):
-        t = json.load(open(tpath)).get("gemm_topk_kernel", {})
-        if t.get("rows") == shard_rows:
-            traffic = t["bytes"] / 1e9                 # GB per launch, from the committed ncu --set full capture
+    for tname in ("traffic_r2.json", "traffic_r1.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get("gemm_topk_kernel", {})
+            if t.get("rows") == shard_rows:
+                traffic = t["bytes"] / 1e9                 # GB per launch, from the committed ncu --set full capture
+                break
     algo_bytes = shard_rows * DIM * 2                    # one pass over the bf16 shard
     achieved = algo_bytes / (coarse_ms * 1e-3) / 1e9
     batches = world if replicas else 1                      # 70-query batches answered per step by the whole job
     qps = batches * N_QUERIES * args.steps / (ms * 1e-3)
     e2e_qps = batches * N_QUERIES * args.steps / (e2e_ms * 1e-3)
+    if world == 1:
+        how = "none"
+    elif replicas:
+        how = f"{world} replicas of the whole database, one 70-query batch per GPU and step, no collective"
+    elif exchange is not None:
+        how = (f"row-sharded x{world}; the last kernel of every shard's search stores its top-100 (and certificate words) straight into "
+               f"every rank's mailbox over NVLink peer memory, the merge kernel waits on per-query arrival flags; no collective on the data path")
+    else:
+        how = f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel"
     line = {
-        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 2 * warm + 2,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2: 1,007,000 x 2048 DB (unit-norm Gaussian, seed 0), 70-query batch, exact top-100",
-                   "rows_per_gpu": shard_rows, "lanes": args.lanes, "sharding": "none" if world == 1 else (f"{world} replicas of the whole database, one 70-query batch per GPU and step, no collective" if replicas else (f"row-sharded x{world}; e2e call: per-shard top-100 pushed into every rank's mailbox over NVLink peer memory, merge kernel waits on arrival flags; value loop: " + ("the same push on a side stream" if args.exchange == "peer" else "NCCL all-gather on its own stream + merge kernel") if exchange is not None else f"row-sharded x{world}, NCCL all-gather of per-shard top-100 + merge kernel")),
+                   "rows_per_gpu": shard_rows, "lanes": args.lanes, "sharding": how,
+                   "value_loop": "two 70-query batches in flight (two lanes per GPU); every result's certificate words are read back and flagged queries re-run before it counts",
                    "l2": "inputs larger than L2 (4.1 GB bf16 database per pass vs 126 MB L2)",
                    "arithmetic": "bf16 operands / fp32 accumulate (tcgen05) for the coarse pass, then fp32 operands / fp64 accumulate exact rescoring of ~120 candidates per query",
                    "path": {1: "scan", 2: "tcgen05 GEMM + fused top-K", 3: "exact"}.get(stats["path"], "?"),
-                   "uncertified_queries_last_step": int(uncert), "parity_spot_check": parity_ok},
+                   "kernels_per_step": int(launches_per_step),
+                   "exact_reruns_total": int(reruns), "parity_spot_check": parity_ok, "merged_parity_vs_exact_shards": merged_ok},
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": N_QUERIES * DIM * 4,
                 "d2h_bytes_per_step": N_QUERIES * TOPK * 12 + N_QUERIES * 4 + 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),
@@ -368,6 +575,8 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if extras:
+        line["extra_configs"] = extras
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -394,12 +603,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="N=1: skip the cfg3 (batch-1) and 4096-query sub-records")
     ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
                     help="search lanes per GPU in the pipelined (value) loop: 2 = consecutive batches alternate between the index "
                          "and a workspace clone on two streams, so one batch's selection/rescoring overlaps the next batch's scan")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
-                    help="N>1, row sharding: how the per-shard lists meet -- peer-memory push + flag-waiting merge kernel, or NCCL "
-                         "all-gather + merge; auto = push for the blocking (e2e) call, all-gather for the pipelined (value) loop")
+                    help="N>1, row sharding: how the per-shard lists meet -- peer (= auto): the search's last kernel stores them into "
+                         "every rank's mailbox and the merge kernel waits on per-query flags; nccl: all-gather + merge kernel")
     ap.add_argument("--sharding", default="rows", choices=["rows", "replicas"],
                     help="N > 1: 'rows' (default) = the database row-sharded over the GPUs + NCCL candidate merge (strong scaling, the "
                          "north-star layout); 'replicas' = every GPU holds the whole database and answers its own batches (weak scaling)")

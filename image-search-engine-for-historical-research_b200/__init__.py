@@ -11,12 +11,12 @@ backed by hand-written sm_100a CUDA behind the C ABI in ``include/xs_b200.h``.  
 """
 from .index import ExactIndex
 from .knn import KNN, BaseKNN
-from .nnsearch import matching, matching_L2, cached_index, clear_index_cache
+from .nnsearch import matching, matching_L2, cached_index, leased_index, clear_index_cache
 from .ranking import rank_ip, rank_ip_torch
 from .reranking import (feature_enhancement, qge1, average_query_expansion, database_augmentation,
                         initial_rank)
 from . import diffusion, store
 
 __all__ = ["ExactIndex", "KNN", "BaseKNN", "matching", "matching_L2", "rank_ip", "rank_ip_torch",
-           "cached_index", "clear_index_cache", "feature_enhancement", "qge1", "average_query_expansion",
+           "cached_index", "leased_index", "clear_index_cache", "feature_enhancement", "qge1", "average_query_expansion",
            "database_augmentation", "initial_rank", "diffusion", "store"]

@@ -80,12 +80,18 @@ struct xs_index {
     CUtensorMap tmap_dbt_b, tmap_dbt_h;          // tiled twin: boxes of 256 / 128 rows, each one contiguous run
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
+    int eps_mode = 0;                             // certificate: 0 = statistical band (8 sigma, random rotation, model check), 1 = worst-case band
+    int inline_boot = 1;                          // small batches: threshold bootstrap inside the GEMM launch (0: separate sample pass)
+    bool rotate = true; uint32_t rot_seed = 0;    // random rotation applied before bf16 rounding (fixed at build time)
+    uint32_t boot_arrived = 0, boot_epoch = 0;    // host mirrors of the in-kernel bootstrap's arrival counter / epoch
     int self_lanes = 1;                           // xs_self_knn: 2 = batches alternate between this index and an internal clone
                                                   // (measured: 1.03 s either way at 500k x 500k -- the loop is tensor/power bound)
     xs_index* self_lane = nullptr;                // that clone (created on first use, freed with the index)
     // workspace
+    Buf boot_samp, boot_sync, q32r;
     Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
+    PinnedBuf h_aqe;                              // pinned staging of xs_aqe_search's id lists
     cudaStream_t stream = nullptr;                // the index's own stream (host API, build)
     cudaStream_t cur = nullptr;                   // stream of the call in progress (the caller's for *_dev entry points)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -128,9 +134,27 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d_pad
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// ---- process-wide defaults picked up by xs_index_create* --------------------------------------------------
+static std::mutex g_cfg_mu;
+static int g_rotate = -1;                         // -1: not set -> on unless XS_NO_ROTATE=1
+static uint32_t g_rot_seed = 0x5EEDB200u;
+static void default_rotation(bool* on, uint32_t* seed) {
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    if (g_rotate < 0) { const char* e = getenv("XS_NO_ROTATE"); g_rotate = (e && atoi(e)) ? 0 : 1; }
+    *on = g_rotate != 0; *seed = g_rot_seed;
+}
+extern "C" int xs_config_set(const char* name, double value) {
+    if (!name) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    if (!strcmp(name, "rotation")) g_rotate = value != 0.0 ? 1 : 0;
+    else if (!strcmp(name, "rotation_seed")) g_rot_seed = (uint32_t)(uint64_t)value;
+    else return fail(XS_ERR_ARG, "unknown configuration key '%s'", name);
+    return XS_OK;
+}
+
 // ---- ABI: misc -----------------------------------------------------------------------------------------
 extern "C" const char* xs_last_error(void) { return g_err.c_str(); }
-extern "C" int xs_abi_version(void) { return 1; }
+extern "C" int xs_abi_version(void) { return 2; }
 extern "C" int xs_device_count(int* count) {
     int c = 0;
     cudaError_t e = cudaGetDeviceCount(&c);
@@ -143,6 +167,8 @@ extern "C" int xs_device_count(int* count) {
 static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_offset) {
     if (n <= 0 || d <= 0) return fail(XS_ERR_ARG, "empty database (n=%lld, d=%d)", (long long)n, d);
     if (n >= (int64_t)0xFFFFFF00u) return fail(XS_ERR_UNSUPPORTED, "more than 2^32-256 rows per index; shard the database");
+    // the rescoring kernels stage eight fp32 rows per CTA in shared memory and the row kernels one: 4096 columns is what fits
+    if (d > 4096) return fail(XS_ERR_UNSUPPORTED, "d=%d > 4096 columns is not supported by the rescoring kernels", d);
     CU_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -151,6 +177,7 @@ static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_of
     ix->n = n; ix->d = d; ix->id_offset = id_offset;
     ix->d_pad = (int)round_up(d, COL_ALIGN);
     ix->n_pad = round_up(n, ROW_ALIGN);
+    default_rotation(&ix->rotate, &ix->rot_seed);
     const size_t b32 = (size_t)n * ix->d_pad * sizeof(float), b16 = (size_t)ix->n_pad * ix->d_pad * 2;
     CU_TRY(cudaMalloc(&ix->db32, b32));
     CU_TRY(cudaMalloc(&ix->db16, b16));
@@ -173,9 +200,9 @@ static void index_free(xs_index* ix) {
     if (ix->self_lane) { index_free(ix->self_lane); ix->self_lane = nullptr; }
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->q32r, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
-    ix->h_idx.release(); ix->h_score.release(); ix->h_status.release();
+    ix->h_idx.release(); ix->h_score.release(); ix->h_status.release(); ix->h_aqe.release();
     if (ix->share) {
         bool last;
         { std::lock_guard<std::mutex> lk(ix->share->mu); last = (--ix->share->refs == 0); }
@@ -266,7 +293,7 @@ extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int6
         rc = stage_host_rows(db, dtype, colmajor, colmajor ? stride_col : stride_row, r0, rows, d, ix->stage.p, ix->stream);
         if (rc != XS_OK) break;
         launch_layout_rows(ix->stage.p, dtype, colmajor, colmajor ? rows : d, rows, d, ix->d_pad, ix->db32 + (size_t)r0 * ix->d_pad, ix->stream);
-        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->dstats, ix->stream);
+        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->rotate, ix->rot_seed, ix->dstats, ix->stream);
         cudaError_t e = cudaStreamSynchronize(ix->stream);      // the staging tile is reused by the next chunk
         if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e));
     }
@@ -286,7 +313,7 @@ extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int de
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         launch_layout_rows(db_dev + (size_t)r0 * d, XS_F32, false, d, rows, d, ix->d_pad, ix->db32 + (size_t)r0 * ix->d_pad, ix->stream);
-        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->dstats, ix->stream);
+        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->rotate, ix->rot_seed, ix->dstats, ix->stream);
     }
     cudaError_t e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); index_free(ix); return rc; }
@@ -296,13 +323,18 @@ extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int de
     return XS_OK;
 }
 
-extern "C" int xs_index_destroy(xs_index* ix) { index_free(ix); return XS_OK; }
+extern "C" int xs_index_destroy(xs_index* ix) {
+    if (ix) { std::lock_guard<std::mutex> lk(ix->mu); }      // a call still inside the library on another thread finishes first
+    index_free(ix);
+    return XS_OK;
+}
 
 // A second search lane over the same database: shares the (read-only) database arrays and tensor maps, owns its
 // workspaces, stream, tunables and statistics -- so two searches can be in flight on two streams at once.
 static void copy_tunables(xs_index* dst, const xs_index* src) {
     dst->eps_sigmas = src->eps_sigmas; dst->scan_max_q = src->scan_max_q; dst->force_path = src->force_path;
     dst->gemm_splits = src->gemm_splits; dst->sample_pass = src->sample_pass; dst->pair_mode = src->pair_mode;
+    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot;
 }
 
 // caller holds src->mu
@@ -315,6 +347,7 @@ static int clone_locked(xs_index* src, xs_index** out) {
     ix->db16 = src->db16; ix->db32 = src->db32; ix->dstats = src->dstats; ix->db16t = src->db16t;
     ix->tmap_db_b = src->tmap_db_b; ix->tmap_db_a = src->tmap_db_a; ix->tmap_dbt_b = src->tmap_dbt_b; ix->tmap_dbt_h = src->tmap_dbt_h;
     copy_tunables(ix, src);
+    ix->rotate = src->rotate; ix->rot_seed = src->rot_seed;
     ix->share = src->share;
     { std::lock_guard<std::mutex> lk2(ix->share->mu); ++ix->share->refs; }
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
@@ -349,6 +382,8 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "sample_pass")) ix->sample_pass = (int)value;
     else if (!strcmp(name, "pair_mode")) ix->pair_mode = (int)value;
     else if (!strcmp(name, "timing")) ix->timing = (int)value;
+    else if (!strcmp(name, "certificate")) ix->eps_mode = ((int)value == 1) ? 1 : 0;
+    else if (!strcmp(name, "inline_boot")) ix->inline_boot = (int)value != 0;
     else if (!strcmp(name, "self_lanes")) ix->self_lanes = ((int)value >= 2) ? 2 : 1;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
@@ -386,6 +421,7 @@ struct CoreArgs {
     int64_t* out_idx; float* out_score; int* status;   // device; pitch = k
     int* ncand;                 // device counter of rescored candidates (nullptr: the index's own)
     int path;                   // PATH_*
+    const PushTarget* push;     // non-null: results also go straight into the peer-exchange mailboxes (out_idx etc. may be null)
 };
 
 __global__ void boost_self_kernel(float* scores, int64_t pitch, int nq, int64_t self_base) {
@@ -432,27 +468,41 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
 
 // Completion counters of the split finalise: zeroed when (re)allocated, the kernel resets them after use.
 static int ensure_tickets(xs_index* ix, int64_t nq) {
-    const size_t need = (size_t)nq * sizeof(int);
+    const size_t need = (size_t)nq * 3 * sizeof(int);      // completion tickets, candidate counters, certificate flags
     if (need <= ix->fin_ticket.cap) return XS_OK;
     XS_TRY(ix->fin_ticket.ensure(need));
     CU_TRY(cudaMemsetAsync(ix->fin_ticket.p, 0, ix->fin_ticket.cap, ix->cur));
     return XS_OK;
 }
 
-// Query preparation: one fused kernel when the raw layout allows it, else layout -> (zero pad) -> prep.
-static int prepare_queries(xs_index* ix, const CoreArgs& a, __nv_bfloat16* q16, int* launches) {
+// Query preparation (one launch): q32 (normalised when asked), rotated bf16 / fp32 copies for the coarse kernels, eps.
+static int prepare_queries(xs_index* ix, const CoreArgs& a, __nv_bfloat16* q16, float* q32r, int* launches) {
     if (!a.prep) return XS_OK;
-    const int64_t nq_pad = round_up(a.nq, GEMM_BM);
-    if (a.raw && launch_prep_queries_fused(a.raw, a.q32, q16, a.nq, nq_pad, ix->d, ix->d_pad, a.prep_renorm, ix->dstats,
-                                           ix->eps_sigmas, ix->eps.as<float>(), ix->cur)) { ++*launches; return XS_OK; }
-    if (a.raw) { launch_layout_rows(a.raw, XS_F32, false, ix->d, a.nq, ix->d, ix->d_pad, a.q32, ix->cur); ++*launches; }
-    if (q16 && nq_pad > a.nq) {
-        const int64_t cnt = (nq_pad - a.nq) * ix->d_pad;
-        zero_rows_bf16_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ix->cur>>>(q16 + a.nq * ix->d_pad, cnt);
-        ++*launches;
-    }
-    launch_prep_queries(a.q32, q16, a.nq, ix->d_pad, a.prep_renorm, ix->dstats, ix->eps_sigmas, ix->eps.as<float>(), ix->cur);
+    launch_prep_queries(a.raw, ix->d, a.q32, q16, q32r, a.nq, round_up(a.nq, GEMM_BM), ix->d_pad, a.prep_renorm, ix->rotate, ix->rot_seed,
+                        ix->dstats, ix->eps_sigmas, ix->eps_mode, ix->eps.as<float>(), ix->cur);
     ++*launches;
+    return XS_OK;
+}
+
+// Everything the finalise stage needs that does not depend on the coarse path.
+static int fill_finalise(xs_index* ix, const CoreArgs& a, int64_t q0, int64_t c, FinaliseArgs* fa, int* ncand) {
+    const int k = a.k;
+    fa->db32 = ix->db32; fa->q32 = a.q32 + q0 * ix->d_pad; fa->d_pad = ix->d_pad; fa->eps = ix->eps.as<float>() + q0;
+    fa->k = k; fa->exact = false; fa->id_offset = ix->id_offset;
+    fa->self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
+    fa->out_idx = a.out_idx ? a.out_idx + q0 * k : nullptr; fa->out_score = a.out_score ? a.out_score + q0 * k : nullptr;
+    fa->status = a.status ? a.status + q0 : nullptr; fa->n_cand = ncand; fa->out_pitch = k;
+    fa->cand_max = finalise_cand_max(k, ix->eps_mode);
+    XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k, fa->cand_max)));
+    XS_TRY(ensure_tickets(ix, c));
+    fa->work = ix->fin_work.p; fa->ticket = ix->fin_ticket.as<int>();
+    if (a.push) {
+        // the mailbox part holds ALL nq queries of the call: advance the per-query pointers to this batch
+        fa->push = *a.push;
+        for (int g = 0; g < fa->push.world; ++g) {
+            fa->push.ids[g] += q0 * k; fa->push.scores[g] += q0 * k; fa->push.status[g] += q0; fa->push.flags[g] += q0;
+        }
+    }
     return XS_OK;
 }
 
@@ -470,14 +520,16 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
     ix->ev_valid = timing;
 
     if (a.path == PATH_EXACT) {
-        XS_TRY(prepare_queries(ix, a, nullptr, &launches));
+        if (a.push) return fail(XS_ERR_UNSUPPORTED, "the exact path does not feed the peer exchange directly (k=%d too large for the coarse filter?)", k);
+        XS_TRY(prepare_queries(ix, a, nullptr, nullptr, &launches));
         if (timing) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
         XS_TRY(run_exact(ix, a.q32, nq, k, a.self_base, a.out_idx, a.out_score, a.status, &launches));
         if (timing) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
     } else if (a.path == PATH_SCAN) {
-        XS_TRY(prepare_queries(ix, a, nullptr, &launches));
+        XS_TRY(ix->q32r.ensure((size_t)nq * ix->d_pad * sizeof(float)));
+        XS_TRY(prepare_queries(ix, a, nullptr, ix->q32r.as<float>(), &launches));
         const int P = (int)((ix->n + SLICE_ROWS - 1) / SLICE_ROWS);
-        const int cap = 2 * k + 256;
+        const int cap = (ix->eps_mode == 1 ? 4 : 2) * k + 256;
         const int64_t chunk_max = 8;
         XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
         XS_TRY(ix->ghist.ensure((size_t)chunk_max * HIST_BINS * sizeof(uint32_t)));
@@ -489,20 +541,15 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
             CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
-            launch_scan_scores(ix->db16, a.q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
+            launch_scan_scores(ix->db16, ix->q32r.as<float>() + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
             launches += (c + 1) / 2;
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), false, ix->pool_items.as<uint64_t>(),
                                    ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->cur);
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
-            fa.P = P; fa.cap = cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad; fa.eps = ix->eps.as<float>() + q0;
-            fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset; fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
-            fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
-            fa.status = a.status + q0; fa.n_cand = ncand; fa.out_pitch = k;
-            XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
-            XS_TRY(ensure_tickets(ix, c));
-            fa.work = ix->fin_work.p; fa.ticket = ix->fin_ticket.as<int>();
+            fa.P = P; fa.cap = cap;
+            XS_TRY(fill_finalise(ix, a, q0, c, &fa, ncand));
             launch_finalise(fa, c, ix->cur);
             launches += 1 + finalise_launches(fa, c);
         }
@@ -512,11 +559,28 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         const int64_t nq_pad = round_up(nq < batch_max ? nq : batch_max, GEMM_BM);
         CUtensorMap tmap_q;
         if (!a.tmap_a) XS_TRY(ix->q16.ensure((size_t)round_up(nq, GEMM_BM) * ix->d_pad * 2));
-        XS_TRY(prepare_queries(ix, a, a.tmap_a ? nullptr : ix->q16.as<__nv_bfloat16>(), &launches));
+        XS_TRY(prepare_queries(ix, a, a.tmap_a ? nullptr : ix->q16.as<__nv_bfloat16>(), nullptr, &launches));
         (void)nq_pad;
         for (int64_t q0 = 0; q0 < nq; q0 += batch_max) {
             const int64_t c = (nq - q0 < batch_max) ? nq - q0 : batch_max;
             GemmPlan plan = plan_gemm(c, ix->n_pad, k, ix->num_sms, ix->gemm_splits, ix->pair_mode != 0);
+            if (!ix->inline_boot) plan.inline_boot = 0;
+            InlineBoot boot{};
+            if (plan.inline_boot) {
+                // the CTAs of this launch meet once inside the kernel: sample lists, arrival counter, published thresholds
+                XS_TRY(ix->boot_samp.ensure((size_t)GEMM_BM * BOOT_MAX_GRID * 8 * sizeof(float)));
+                if (!ix->boot_sync.p) {
+                    XS_TRY(ix->boot_sync.ensure(16 + GEMM_BM * sizeof(uint64_t)));
+                    CU_TRY(cudaMemsetAsync(ix->boot_sync.p, 0, ix->boot_sync.cap, ix->cur));
+                    ix->boot_arrived = 0; ix->boot_epoch = 0;
+                }
+                boot.samp = ix->boot_samp.as<float>();
+                boot.arrive = ix->boot_sync.as<uint32_t>();
+                boot.thr_pub = reinterpret_cast<uint64_t*>(static_cast<char*>(ix->boot_sync.p) + 16);
+                ix->boot_arrived += (uint32_t)plan.grid;
+                boot.arrive_target = ix->boot_arrived;
+                boot.epoch = ++ix->boot_epoch;
+            }
             const int64_t slots = (int64_t)((plan.m_tiles + 1) & ~1) * plan.splits * GEMM_BM;
             XS_TRY(ix->pool_items.ensure((size_t)slots * plan.cap * 8));
             XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
@@ -531,7 +595,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const float* thr0 = nullptr;
             XS_TRY(ix->thr0.ensure((size_t)c * sizeof(float)));
             GemmPlan sp = plan_gemm_sample(plan, ix->num_sms, k);
-            if (ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 3 * k && (size_t)sp.splits * 64 <= 200 * 1024) {
+            if (!plan.inline_boot && ix->sample_pass && plan.n_tiles >= 2 * ix->num_sms && 8 * sp.splits >= 3 * k && (size_t)sp.splits * 64 <= 200 * 1024) {
                 const int64_t sslots = (int64_t)sp.m_tiles * sp.splits * GEMM_BM;
                 XS_TRY(ix->pool_items.ensure((size_t)(sslots > slots ? sslots : slots) * plan.cap * 8));
                 XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
@@ -539,7 +603,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 sp.db_tiled = ix->db16t ? 1 : 0;
                 cudaError_t es = launch_gemm_topk(*ta, ix->db16t ? ix->tmap_dbt_h : ix->tmap_db_a, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                                   ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
-                                                  (int)row0, nullptr, ix->cur);
+                                                  (int)row0, nullptr, nullptr, ix->cur);
                 if (es != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk (sample) launch failed: %s", cudaGetErrorString(es));
                 launch_sample_threshold(ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), sp.splits, sp.cap, k,
                                         ix->eps.as<float>() + q0, ix->thr0.as<float>(), c, ix->cur);
@@ -550,19 +614,13 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             plan.db_tiled = ix->db16t ? 1 : 0;
             cudaError_t e = launch_gemm_topk(*ta, ix->db16t ? (plan.pair ? ix->tmap_dbt_h : ix->tmap_dbt_b) : (plan.pair ? ix->tmap_db_a : ix->tmap_db_b), plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
-                                             (int)row0, thr0, ix->cur);
+                                             (int)row0, thr0, plan.inline_boot ? &boot : nullptr, ix->cur);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
-            fa.P = plan.splits; fa.cap = plan.cap; fa.db32 = ix->db32; fa.q32 = a.q32 + q0 * ix->d_pad; fa.d_pad = ix->d_pad;
-            fa.eps = ix->eps.as<float>() + q0; fa.k = k; fa.exact = false; fa.id_offset = ix->id_offset;
-            fa.self_base = a.self_base >= 0 ? a.self_base + q0 : -1;
-            fa.out_idx = a.out_idx + q0 * k; fa.out_score = a.out_score ? a.out_score + q0 * k : nullptr;
-            fa.status = a.status + q0; fa.n_cand = ncand; fa.out_pitch = k;
-            XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k)));
-            XS_TRY(ensure_tickets(ix, c));
-            fa.work = ix->fin_work.p; fa.ticket = ix->fin_ticket.as<int>();
+            fa.P = plan.splits; fa.cap = plan.cap;
+            XS_TRY(fill_finalise(ix, a, q0, c, &fa, ncand));
             launch_finalise(fa, c, ix->cur);
             launches += 1 + finalise_launches(fa, c);
         }
@@ -748,11 +806,13 @@ extern "C" int xs_aqe_search(xs_index* ix, const int64_t* top_ids, int64_t nq, i
     XS_TRY(ix->out_idx.ensure((size_t)nq * k * sizeof(int64_t)));
     XS_TRY(ix->out_score.ensure((size_t)nq * k * sizeof(float)));
     // ids arrive as the caller saw them (row + id_offset); the kernel wants local rows
-    std::vector<int64_t> local((size_t)nq * kq);
-    for (size_t i = 0; i < local.size(); ++i) local[i] = top_ids[i] - ix->id_offset;
-    CU_TRY(cudaMemcpyAsync(ix->aqe_ids.p, local.data(), local.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    // (staged in pinned memory owned by the index: the copy is asynchronous and nothing waits for it on the host)
+    const size_t n_ids = (size_t)nq * kq;
+    XS_TRY(ix->h_aqe.ensure(n_ids * sizeof(int64_t)));
+    int64_t* local = ix->h_aqe.as<int64_t>();
+    for (size_t i = 0; i < n_ids; ++i) local[i] = top_ids[i] - ix->id_offset;
+    CU_TRY(cudaMemcpyAsync(ix->aqe_ids.p, local, n_ids * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
     launch_aqe_queries(ix->db32, ix->aqe_ids.as<int64_t>(), nq, kq, w, ix->n, ix->d_pad, ix->q32.as<float>(), ix->stream);
-    CU_TRY(cudaStreamSynchronize(ix->stream));          // `local` is pageable and about to go out of scope
     CoreArgs a{};
     a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = false; a.tmap_a = nullptr; a.a_row0 = 0;
     a.self_base = -1; a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
@@ -895,7 +955,7 @@ extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, i
     if (dtype == XS_F32 && !colmajor) a.raw = ix->q_raw.as<float>();
     else { launch_layout_rows(ix->q_raw.p, dtype, colmajor, colmajor ? nq : ix->d, nq, ix->d, ix->d_pad, ix->q32.as<float>(), ix->stream); ++launches; }
     a.q32 = ix->q32.as<float>(); a.nq = nq; a.prep = true; a.prep_renorm = renormalise_q != 0;
-    XS_TRY(prepare_queries(ix, a, nullptr, &launches));
+    XS_TRY(prepare_queries(ix, a, nullptr, nullptr, &launches));
     for (int64_t b0 = 0; b0 < nq; b0 += col_block) {
         const int64_t cb = (nq - b0 < col_block) ? nq - b0 : col_block;
         for (int64_t q0 = 0; q0 < cb; q0 += chunk) {
@@ -924,45 +984,59 @@ extern "C" int xs_merge_candidates(int device, const int64_t* in_idx, const floa
                                    int64_t* out_idx, float* out_score, void* stream) {
     if (!in_idx || !in_score || !out_idx) return fail(XS_ERR_ARG, "null pointer");
     if (n_parts <= 0 || nq <= 0 || k <= 0) return fail(XS_ERR_ARG, "bad sizes");
-    if ((int64_t)n_parts * k > 16384) return fail(XS_ERR_UNSUPPORTED, "n_parts*k = %lld > 16384", (long long)n_parts * k);
     // two dense arrays: ids advance nq*k*8 bytes per part, scores nq*k*4
-    return xs_merge_candidates_strided(device, in_idx, in_score, nq * k * 8, nq * k * 4, n_parts, nq, k, out_idx, out_score, stream);
+    return xs_merge_candidates_strided(device, in_idx, in_score, nullptr, nq * k * 8, nq * k * 4, 0, n_parts, nq, k, out_idx, out_score, nullptr, stream);
 }
 
-extern "C" int xs_merge_candidates_strided(int device, const void* in_idx, const void* in_score, int64_t idx_part_stride,
-                                           int64_t score_part_stride, int n_parts, int64_t nq, int k,
-                                           int64_t* out_idx, float* out_score, void* stream) {
+extern "C" int xs_merge_candidates_strided(int device, const void* in_idx, const void* in_score, const void* in_status,
+                                           int64_t idx_part_stride, int64_t score_part_stride, int64_t status_part_stride,
+                                           int n_parts, int64_t nq, int k,
+                                           int64_t* out_idx, float* out_score, int32_t* out_status, void* stream) {
     if (!in_idx || !in_score || !out_idx) return fail(XS_ERR_ARG, "null pointer");
     if (n_parts <= 0 || nq <= 0 || k <= 0) return fail(XS_ERR_ARG, "bad sizes");
     if ((int64_t)n_parts * k > 16384) return fail(XS_ERR_UNSUPPORTED, "n_parts*k = %lld > 16384", (long long)n_parts * k);
     CU_TRY(cudaSetDevice(device));
-    launch_merge_parts(in_idx, in_score, idx_part_stride, score_part_stride, n_parts, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream));
+    launch_merge_parts(in_idx, in_score, in_status, idx_part_stride, score_part_stride, status_part_stride, n_parts, nq, k,
+                       out_idx, out_score, out_status, static_cast<cudaStream_t>(stream));
     CU_TRY(cudaGetLastError());
     return XS_OK;
 }
 
-// ---- peer exchange: per-shard result lists pushed into every rank's mailbox over NVLink peer mappings --------
+// ---- peer exchange: per-shard result lists stored into every rank's mailbox over NVLink peer mappings --------
+// Mailbox of one rank (its own HBM, exported through CUDA IPC):
+//   header   acks [2 slots][W] | merge tickets [2] | push tickets [2][W]
+//   flags    [2 slots][W senders][max_q]   per-query arrival epochs
+//   data     [2 slots][W senders][part_bytes]; a part = ids int64 [nq][k] | scores f32 [nq][k] | certificate bits int32 [nq]
 struct xs_exchange {
     int device = 0, world = 1, rank = 0;
     int64_t part_bytes = 0;                       // mailbox bytes per (slot, sender), multiple of 16
-    char* local = nullptr;                        // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
+    int64_t max_q = 0;                            // queries per search the flag area is sized for
+    char* local = nullptr;                        // this rank's mailbox
     char* peer[XCHG_MAX_WORLD] = {};              // every rank's mailbox as mapped here (peer[rank] == local)
     bool connected = false;
     uint32_t push_epoch[2] = {0, 0}, merge_epoch[2] = {0, 0};
     std::mutex mu;                                // epochs and launches of one exchange are serialised
-    static constexpr size_t FLAGS_OFF = 0, ACKS_OFF = 2 * XCHG_MAX_WORLD * 4, TICKET_OFF = 4 * XCHG_MAX_WORLD * 4,
-                            PUSH_TICKET_OFF = TICKET_OFF + 64, DATA_OFF = 1024;
-    size_t total() const { return DATA_OFF + (size_t)2 * world * part_bytes; }
+    static constexpr size_t ACKS_OFF = 0, TICKET_OFF = 2 * XCHG_MAX_WORLD * 4, PUSH_TICKET_OFF = TICKET_OFF + 64, FLAGS_OFF = 1024;
+    size_t flags_bytes() const { return (((size_t)2 * world * max_q * 4) + 255) & ~(size_t)255; }
+    size_t data_off() const { return FLAGS_OFF + flags_bytes(); }
+    size_t total() const { return data_off() + (size_t)2 * world * part_bytes; }
+    char* part(int g, int slot, int sender) const { return peer[g] + data_off() + ((size_t)slot * world + sender) * part_bytes; }
+    uint32_t* flags(int g, int slot, int sender) const { return reinterpret_cast<uint32_t*>(peer[g] + FLAGS_OFF) + ((size_t)slot * world + sender) * max_q; }
 };
 
-extern "C" int xs_exchange_create(int device, int world, int rank, int64_t part_bytes, xs_exchange** out, unsigned char* handle_out) {
+extern "C" int64_t xs_exchange_part_bytes(int64_t nq, int k) {
+    return (nq * k * 12 + nq * 4 + 15) / 16 * 16;
+}
+
+extern "C" int xs_exchange_create(int device, int world, int rank, int64_t max_queries, int k_max, xs_exchange** out, unsigned char* handle_out) {
     if (!out || !handle_out) return fail(XS_ERR_ARG, "null pointer");
     if (world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return fail(XS_ERR_ARG, "bad world/rank (%d/%d, at most %d ranks)", rank, world, XCHG_MAX_WORLD);
-    if (part_bytes <= 0 || part_bytes % 16) return fail(XS_ERR_ARG, "part_bytes must be a positive multiple of 16");
+    if (max_queries <= 0 || k_max <= 0) return fail(XS_ERR_ARG, "max_queries and k_max must be positive");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
     CU_TRY(cudaSetDevice(device));
     xs_exchange* ex = new xs_exchange();
-    ex->device = device; ex->world = world; ex->rank = rank; ex->part_bytes = part_bytes;
+    ex->device = device; ex->world = world; ex->rank = rank;
+    ex->max_q = max_queries; ex->part_bytes = xs_exchange_part_bytes(max_queries, k_max);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ex->local), ex->total());
     if (e == cudaSuccess) e = cudaMemset(ex->local, 0, ex->total());
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1001,42 +1075,88 @@ extern "C" int xs_exchange_connect(xs_exchange* ex, const unsigned char* handles
     return XS_OK;
 }
 
-extern "C" int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t bytes, int slot, void* stream) {
-    if (!ex || !packed_dev) return fail(XS_ERR_ARG, "null pointer");
+static int exchange_check_use(xs_exchange* ex, int slot, int64_t nq, int k) {
     if (!ex->connected && ex->world > 1) return fail(XS_ERR_ARG, "exchange not connected");
-    if (slot < 0 || slot > 1 || bytes <= 0 || bytes % 16 || bytes > ex->part_bytes) return fail(XS_ERR_ARG, "bad slot/bytes (%d, %lld of %lld)", slot, (long long)bytes, (long long)ex->part_bytes);
+    if (slot < 0 || slot > 1 || nq <= 0 || k <= 0 || nq > ex->max_q || xs_exchange_part_bytes(nq, k) > ex->part_bytes)
+        return fail(XS_ERR_ARG, "bad slot/sizes (slot %d, nq %lld of %lld, %lld of %lld bytes)", slot, (long long)nq, (long long)ex->max_q,
+                    (long long)xs_exchange_part_bytes(nq, k), (long long)ex->part_bytes);
+    return XS_OK;
+}
+
+// The search with the sending end of the exchange fused into its last kernel: the emit step of every query stores the
+// k results into all mailboxes and releases that query's flag -- no packed local result, no push kernel, no collective.
+extern "C" int xs_search_dev_push(xs_index* ix, const float* q_dev, int64_t nq, int renormalise_q, int k,
+                                  xs_exchange* ex, int slot, void* stream) {
+    XS_TRY(check_search_args(ix, nq, k));
+    if (!q_dev || !ex) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> lk2(ex->mu);
+    XS_TRY(exchange_check_use(ex, slot, nq, k));
+    if (ex->device != ix->device) return fail(XS_ERR_ARG, "index and exchange live on different devices");
+    if (ex->push_epoch[slot] != ex->merge_epoch[slot]) return fail(XS_ERR_ARG, "search into slot %d before its previous result was merged", slot);
+    CU_TRY(cudaSetDevice(ix->device));
+    ix->cur = static_cast<cudaStream_t>(stream);
+    XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
+    XS_TRY(ix->status.ensure((size_t)nq * sizeof(int)));
+    PushTarget pt{};
+    pt.world = ex->world;
+    for (int g = 0; g < ex->world; ++g) {
+        char* part = ex->part(g, slot, ex->rank);
+        pt.ids[g] = reinterpret_cast<int64_t*>(part);
+        pt.scores[g] = reinterpret_cast<float*>(part + (size_t)nq * k * 8);
+        pt.status[g] = reinterpret_cast<int32_t*>(part + (size_t)nq * k * 12);
+        pt.flags[g] = ex->flags(g, slot, ex->rank);
+    }
+    pt.my_acks = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD;
+    pt.epoch = ex->push_epoch[slot] + 1;
+    CoreArgs a{};
+    a.raw = q_dev;
+    a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
+    a.self_base = -1; a.out_idx = nullptr; a.out_score = nullptr; a.status = ix->status.as<int>();
+    a.path = choose_path(ix, nq, k);
+    a.push = &pt;
+    XS_TRY(search_core(ix, a));
+    ++ex->push_epoch[slot];
+    return XS_OK;
+}
+
+extern "C" int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t nq, int k, int slot, void* stream) {
+    if (!ex || !packed_dev) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lock(ex->mu);
+    XS_TRY(exchange_check_use(ex, slot, nq, k));
     if (ex->push_epoch[slot] != ex->merge_epoch[slot]) return fail(XS_ERR_ARG, "push into slot %d before its previous result was merged", slot);
     CU_TRY(cudaSetDevice(ex->device));
     PushArgs a{};
     for (int g = 0; g < ex->world; ++g) {
-        a.dst[g] = ex->peer[g] + xs_exchange::DATA_OFF + ((size_t)slot * ex->world + ex->rank) * ex->part_bytes;
-        a.flag[g] = reinterpret_cast<uint32_t*>(ex->peer[g] + xs_exchange::FLAGS_OFF) + slot * XCHG_MAX_WORLD + ex->rank;
+        a.dst[g] = ex->part(g, slot, ex->rank);
+        a.flag[g] = ex->flags(g, slot, ex->rank);
     }
     a.my_acks = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD;
     a.tickets = reinterpret_cast<uint32_t*>(ex->local + xs_exchange::PUSH_TICKET_OFF) + slot * XCHG_MAX_WORLD;
     a.epoch = ++ex->push_epoch[slot];
-    launch_exchange_push(packed_dev, bytes, a, ex->world, static_cast<cudaStream_t>(stream));
+    a.nq = nq;
+    launch_exchange_push(packed_dev, xs_exchange_part_bytes(nq, k), a, ex->world, static_cast<cudaStream_t>(stream));
     CU_TRY(cudaGetLastError());
     return XS_OK;
 }
 
-extern "C" int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64_t* out_idx, float* out_score, void* stream) {
+extern "C" int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64_t* out_idx, float* out_score, int32_t* out_status, void* stream) {
     if (!ex || !out_idx) return fail(XS_ERR_ARG, "null pointer");
-    if (slot < 0 || slot > 1 || nq <= 0 || k <= 0 || nq * k * 12 > ex->part_bytes) return fail(XS_ERR_ARG, "bad slot/sizes");
-    if ((int64_t)ex->world * k > 16384) return fail(XS_ERR_UNSUPPORTED, "world*k = %lld > 16384", (long long)ex->world * k);
     std::lock_guard<std::mutex> lock(ex->mu);
+    XS_TRY(exchange_check_use(ex, slot, nq, k));
+    if ((int64_t)ex->world * k > 16384) return fail(XS_ERR_UNSUPPORTED, "world*k = %lld > 16384", (long long)ex->world * k);
     if (ex->merge_epoch[slot] >= ex->push_epoch[slot]) return fail(XS_ERR_ARG, "merge of slot %d without a matching push", slot);
     CU_TRY(cudaSetDevice(ex->device));
     MergeSync ms{};
-    ms.flags = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::FLAGS_OFF) + slot * XCHG_MAX_WORLD;
+    ms.flags = ex->flags(ex->rank, slot, 0);
+    ms.flag_stride = ex->max_q;
     ms.ticket = reinterpret_cast<uint32_t*>(ex->local + xs_exchange::TICKET_OFF) + slot;
     for (int g = 0; g < ex->world; ++g)
         ms.ack[g] = reinterpret_cast<uint32_t*>(ex->peer[g] + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD + ex->rank;
     ms.epoch = ++ex->merge_epoch[slot];
-    const char* base = ex->local + xs_exchange::DATA_OFF + (size_t)slot * ex->world * ex->part_bytes;
-    launch_merge_parts(base, base + nq * k * 8, ex->part_bytes, ex->part_bytes, ex->world, nq, k, out_idx, out_score,
-                       static_cast<cudaStream_t>(stream), &ms);
+    const char* base = ex->part(ex->rank, slot, 0);
+    launch_merge_parts(base, base + nq * k * 8, base + nq * k * 12, ex->part_bytes, ex->part_bytes, ex->part_bytes, ex->world, nq, k,
+                       out_idx, out_score, out_status, static_cast<cudaStream_t>(stream), &ms);
     CU_TRY(cudaGetLastError());
     return XS_OK;
 }

@@ -55,162 +55,187 @@ void launch_layout_rows(const void* src_tile, int dtype, bool colmajor, int64_t 
     }
 }
 
+// ---- random rotation ------------------------------------------------------------------------------------
+// Before anything is rounded to bf16, database rows and queries go through the same orthogonal map
+//     R = H D2 H D1        (D1, D2: random sign flips from the index's private seed; H: normalised Walsh-Hadamard)
+// so that <Rv, Rq> = <v, q> while the bf16 rounding errors of Rv / Rq no longer depend on any structure of the data
+// (constant components, low-entropy mantissas, rows built against a known query ...): for ANY fixed pair (v, q) the
+// coordinates of Rv, Rq are generic, and the statistical error model behind eps (see prep_queries_kernel) holds with
+// the stated probability over the seed instead of "for data that happens to look random".  The exact stage never sees
+// R: rescoring uses the original fp32 rows and queries.
+// d_pad is a multiple of 64, not necessarily a power of two: H is block diagonal over the binary decomposition of
+// d_pad (largest block first in round 1, smallest first in round 2, so the two rounds mix across block borders).
+__device__ __forceinline__ float rot_sign(uint32_t seed, uint32_t round, uint32_t i) {
+    uint32_t h = (i + round * 0x9E3779B9u) * 0x85EBCA6Bu ^ seed;
+    h ^= h >> 15; h *= 0xC2B2AE35u; h ^= h >> 13; h *= 0x27D4EB2Fu; h ^= h >> 16;
+    return (h & 0x80000000u) ? -1.f : 1.f;
+}
+// Whole CTA, row x[0..d_pad) in shared memory.
+__device__ void block_rotate(float* x, int d_pad, uint32_t seed) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int round = 0; round < 2; ++round) {
+        for (int i = tid; i < d_pad; i += nt) x[i] *= rot_sign(seed, (uint32_t)round, (uint32_t)i);
+        __syncthreads();
+        int o = 0, rem = d_pad;
+        while (rem > 0) {
+            const int B = (round == 0) ? (1 << (31 - __clz(rem))) : (rem & -rem);      // largest / smallest power of two first
+            for (int lh = 0; (1 << lh) < B; ++lh) {
+                const int h = 1 << lh;
+                for (int i = tid; i < (B >> 1); i += nt) {
+                    const int j = o + ((i >> lh) << (lh + 1)) + (i & (h - 1));
+                    const float a = x[j], b = x[j + h];
+                    x[j] = a + b; x[j + h] = a - b;
+                }
+                __syncthreads();
+            }
+            const float scale = rsqrtf((float)B);
+            for (int i = tid; i < B; i += nt) x[o + i] *= scale;
+            o += B; rem -= B;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- finish_rows / prep_queries ------------------------------------------------------------------
-// One warp per row.  Sum of squares and of fourth powers in fp64 (fixed lane-strided order).
-__device__ __forceinline__ void row_moments(const float* row, int d_pad, double& s2, double& s4) {
+// One CTA of ROW_THREADS threads per row, the row held in shared memory; sums in fp64, fixed order.
+constexpr int ROW_THREADS = 128;
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {      // red: 2 * ROW_THREADS/32 doubles
+    a = warp_sum(a); b = warp_sum(b);
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane_id() == 0) { red[warp] = a; red[ROW_THREADS / 32 + warp] = b; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int w = 0; w < ROW_THREADS / 32; ++w) { ta += red[w]; tb += red[ROW_THREADS / 32 + w]; }
+    a = ta; b = tb;
+}
+__device__ __forceinline__ void smem_moments(const float* x, int d_pad, double& s2, double& s4, double* red) {
     double a2 = 0.0, a4 = 0.0;
-    for (int c = lane_id() * 4; c < d_pad; c += 128) {
-        float4 v = *reinterpret_cast<const float4*>(row + c);
-        double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
-        double q0 = x0 * x0, q1 = x1 * x1, q2 = x2 * x2, q3 = x3 * x3;
-        a2 += (q0 + q1) + (q2 + q3);
-        a4 += (q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3);
+    for (int c = threadIdx.x; c < d_pad; c += ROW_THREADS) {
+        const double v = x[c], q = v * v;
+        a2 += q; a4 += q * q;
     }
-    s2 = warp_sum(a2);
-    s4 = warp_sum(a4);
+    block_sum2(a2, a4, red);
+    s2 = a2; s4 = a4;
+}
+// bf16 rounding of x[0..d_pad) into dst (row-major); returns the squared norms of the rounding residual and of the rounded row
+__device__ __forceinline__ void smem_round_bf16(const float* x, int d_pad, __nv_bfloat16* dst, double& res2, double& r2, double* red) {
+    double a = 0.0, b = 0.0;
+    for (int c = threadIdx.x * 2; c < d_pad; c += 2 * ROW_THREADS) {
+        const float v0 = x[c], v1 = x[c + 1];
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+        if (dst) *reinterpret_cast<__nv_bfloat162*>(dst + c) = pk;
+        const float w0 = __low2float(pk), w1 = __high2float(pk);
+        const double e0 = (double)v0 - (double)w0, e1 = (double)v1 - (double)w1;
+        a += e0 * e0 + e1 * e1;
+        b += (double)w0 * w0 + (double)w1 * w1;
+    }
+    block_sum2(a, b, red);
+    res2 = a; r2 = b;
 }
 
-__device__ __forceinline__ void scale_and_round(float* row32, __nv_bfloat16* row16, int d_pad, float scale, bool do_scale) {
-    for (int c = lane_id() * 4; c < d_pad; c += 128) {
-        float4 v = *reinterpret_cast<const float4*>(row32 + c);
-        if (do_scale) {
-            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-            *reinterpret_cast<float4*>(row32 + c) = v;
-        }
-        if (row16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(row16 + c) = pk;
-        }
-    }
-}
-
-__global__ void finish_rows_kernel(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad,
-                                   int renorm, DevStats* stats) {
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= rows) return;
+__global__ void __launch_bounds__(ROW_THREADS)
+finish_rows_kernel(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, int renorm, int rotate, uint32_t seed, DevStats* stats) {
+    extern __shared__ float fr_smem[];
+    __shared__ double red[2 * ROW_THREADS / 32];
+    float* x = fr_smem;
+    const int64_t r = blockIdx.x;
     float* row = rows32 + r * d_pad;
+    for (int c = threadIdx.x * 4; c < d_pad; c += 4 * ROW_THREADS) *reinterpret_cast<float4*>(x + c) = *reinterpret_cast<const float4*>(row + c);
+    __syncthreads();
     double s2, s4;
-    row_moments(row, d_pad, s2, s4);
-    float scale = 1.f;
+    smem_moments(x, d_pad, s2, s4, red);
     if (renorm) {
         // a zero row stays zero (the reference would produce NaNs, nnsearch.py:697)
-        scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
-        double sc = scale;
-        s4 *= sc * sc * sc * sc;
-        s2 *= sc * sc;
+        const float scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
+        for (int c = threadIdx.x; c < d_pad; c += ROW_THREADS) { const float v = x[c] * scale; x[c] = v; row[c] = v; }
+        __syncthreads();
+        smem_moments(x, d_pad, s2, s4, red);
     }
-    scale_and_round(row, rows16 ? rows16 + r * d_pad : nullptr, d_pad, scale, renorm != 0);
-    if (lane_id() == 0) {
-        float n4 = (float)sqrt(sqrt(s4)) * 1.000001f, n2 = (float)sqrt(s2) * 1.000001f;
+    if (rotate) { block_rotate(x, d_pad, seed); double t2; smem_moments(x, d_pad, t2, s4, red); }
+    double res2, r2;
+    smem_round_bf16(x, d_pad, rows16 ? rows16 + r * d_pad : nullptr, res2, r2, red);
+    if (threadIdx.x == 0) {
+        const float n4 = (float)sqrt(sqrt(s4)) * 1.000001f, n2 = (float)sqrt(s2) * 1.000001f, rho = (float)sqrt(res2) * 1.000001f;
         atomicMax(&stats->v4max_bits, __float_as_uint(n4));
         atomicMax(&stats->vnmax_bits, __float_as_uint(n2));
+        atomicMax(&stats->rhomax_bits, __float_as_uint(rho));
     }
 }
 
-void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm,
+void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm, bool rotate, uint32_t seed,
                         DevStats* stats, cudaStream_t st) {
     if (rows <= 0) return;
-    const int wpb = 8;
-    finish_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(rows32, rows16, rows, d_pad, renorm ? 1 : 0, stats);
+    const size_t smem = (size_t)d_pad * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(finish_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    finish_rows_kernel<<<(unsigned)rows, ROW_THREADS, smem, st>>>(rows32, rows16, rows, d_pad, renorm ? 1 : 0, rotate ? 1 : 0, seed, stats);
 }
 
-// eps[q] bounds |bf16 coarse score - exact score| for query q against ANY database row:
-// both operands are rounded to bf16 (unit roundoff u = 2^-9), so the error of one product is
-// ~ v_i q_i (d1 + d2) with independent roundings of variance <= u^2/3; over the row the standard
-// deviation is <= u sqrt(2/3) sqrt(sum (v_i q_i)^2) <= u sqrt(2/3) ||v||_4 ||q||_4 (Cauchy-Schwarz).
-// eps = sigmas * that bound + a small absolute term for the fp32 accumulation inside the tensor core.
-__global__ void prep_queries_kernel(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, int renorm,
-                                    const DevStats* stats, float eps_sigmas, float* eps) {
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= nq) return;
-    float* row = q32 + r * d_pad;
-    double s2, s4;
-    row_moments(row, d_pad, s2, s4);
-    float scale = 1.f;
-    if (renorm) {
-        scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
-        double sc = scale;
-        s4 *= sc * sc * sc * sc;
-        s2 *= sc * sc;
-    }
-    scale_and_round(row, q16 ? q16 + r * d_pad : nullptr, d_pad, scale, renorm != 0);
-    if (lane_id() == 0) {
-        const float v4 = __uint_as_float(stats->v4max_bits), vn = __uint_as_float(stats->vnmax_bits);
-        const float q4 = (float)sqrt(sqrt(s4)), qn = (float)sqrt(s2);
-        const float u = 1.0f / 512.0f;
-        eps[r] = eps_sigmas * u * 0.8165f * q4 * v4 + 2e-5f * qn * vn;
-    }
-}
-
-// Fast path for d == d_pad <= 2048: the raw row goes straight into registers (16 float4 per lane,
-// all loads issued up front), moments, scaling, fp32 + bf16 stores and eps in one kernel; the rows
-// [nq, nq_pad) of the bf16 copy (GEMM tile padding) are zero-filled by the same launch.
-__global__ void prep_queries_fused_kernel(const float* __restrict__ raw, float* __restrict__ q32, __nv_bfloat16* __restrict__ q16,
-                                          int64_t nq, int64_t nq_pad, int d_pad, int renorm, const DevStats* stats,
-                                          float eps_sigmas, float* __restrict__ eps) {
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = lane_id();
-    if (r >= nq_pad) return;
-    if (r >= nq) {
-        if (q16) for (int c = lane * 8; c < d_pad; c += 256) *reinterpret_cast<uint4*>(q16 + r * d_pad + c) = make_uint4(0, 0, 0, 0);
+// Query preparation, one launch: optional copy from the caller's raw fp32 rows (pitch d), optional normalisation
+// (nnsearch.py:693-697), the rotated copies the coarse kernels read (bf16 for the GEMM, fp32 for the batch-1 scan),
+// zero rows [nq, nq_pad) of the bf16 copy (GEMM tile padding) and the per-query band eps.
+//
+// eps[q] bounds |coarse score - exact score| of query q against ANY database row.
+//   mode 0 (statistical, default): both operands are rounded to bf16 (unit roundoff u = 2^-9 relative to the binade
+//     centre); over a row the error is a sum of d independent zero-mean terms with standard deviation
+//     <= u sqrt(2/3) ||v'||_4 ||q'||_4 (primes: rotated vectors) -- independence is what the random rotation buys --
+//     and eps = sigmas * that + a small absolute term for fp32 accumulation and the rotation's own rounding.
+//   mode 1 (worst case): |<v16,q16> - <v',q'>| <= rho_v ||q16|| + ||v'|| rho_q by Cauchy-Schwarz with the stored
+//     residual norms rho = ||x' - bf16(x')||, plus d_pad 2^-22 ||v|| ||q|| for ANY order of fp32 accumulation and
+//     1e-5 ||v|| ||q|| for the rotation arithmetic.  No assumption at all, ~3x the candidates.
+__global__ void __launch_bounds__(ROW_THREADS)
+prep_queries_kernel(const float* __restrict__ raw, int raw_pitch, int d, float* q32, __nv_bfloat16* q16, float* q32r,
+                    int64_t nq, int d_pad, int renorm, int rotate, uint32_t seed, const DevStats* stats,
+                    float eps_sigmas, int eps_mode, float* __restrict__ eps) {
+    extern __shared__ float pq_smem[];
+    __shared__ double red[2 * ROW_THREADS / 32];
+    pdl_wait();
+    const int64_t r = blockIdx.x;
+    if (r >= nq) {                                      // GEMM tile padding
+        if (q16) for (int c = threadIdx.x * 8; c < d_pad; c += 8 * ROW_THREADS) *reinterpret_cast<uint4*>(q16 + r * d_pad + c) = make_uint4(0, 0, 0, 0);
         return;
     }
-    float4 v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int c = j * 128 + lane * 4;
-        v[j] = (c < d_pad) ? *reinterpret_cast<const float4*>(raw + r * d_pad + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    double a2 = 0.0, a4 = 0.0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        double x0 = v[j].x, x1 = v[j].y, x2 = v[j].z, x3 = v[j].w;
-        double q0 = x0 * x0, q1 = x1 * x1, q2 = x2 * x2, q3 = x3 * x3;
-        a2 += (q0 + q1) + (q2 + q3);
-        a4 += (q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3);
-    }
-    double s2 = warp_sum(a2), s4 = warp_sum(a4);
-    float scale = 1.f;
+    float* x = pq_smem;
+    if (raw) { for (int c = threadIdx.x; c < d_pad; c += ROW_THREADS) x[c] = (c < d) ? raw[r * raw_pitch + c] : 0.f; }
+    else     { for (int c = threadIdx.x * 4; c < d_pad; c += 4 * ROW_THREADS) *reinterpret_cast<float4*>(x + c) = *reinterpret_cast<const float4*>(q32 + r * d_pad + c); }
+    __syncthreads();
+    double s2, s4;
+    smem_moments(x, d_pad, s2, s4, red);
     if (renorm) {
-        scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
-        double sc = scale;
-        s4 *= sc * sc * sc * sc;
-        s2 *= sc * sc;
+        const float scale = (s2 > 0.0) ? (float)(1.0 / sqrt(s2)) : 0.f;
+        for (int c = threadIdx.x; c < d_pad; c += ROW_THREADS) x[c] *= scale;
+        __syncthreads();
+        smem_moments(x, d_pad, s2, s4, red);
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int c = j * 128 + lane * 4;
-        if (c < d_pad) {
-            float4 w = v[j];
-            if (renorm) { w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale; }
-            *reinterpret_cast<float4*>(q32 + r * d_pad + c) = w;
-            if (q16) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(q16 + r * d_pad + c) = pk;
-            }
-        }
-    }
-    if (lane == 0) {
-        const float v4 = __uint_as_float(stats->v4max_bits), vn = __uint_as_float(stats->vnmax_bits);
+    if (raw || renorm) for (int c = threadIdx.x * 4; c < d_pad; c += 4 * ROW_THREADS) *reinterpret_cast<float4*>(q32 + r * d_pad + c) = *reinterpret_cast<const float4*>(x + c);
+    if (rotate) { __syncthreads(); block_rotate(x, d_pad, seed); double t2; smem_moments(x, d_pad, t2, s4, red); }
+    if (q32r) for (int c = threadIdx.x * 4; c < d_pad; c += 4 * ROW_THREADS) *reinterpret_cast<float4*>(q32r + r * d_pad + c) = *reinterpret_cast<const float4*>(x + c);
+    double res2, r2;
+    smem_round_bf16(x, d_pad, q16 ? q16 + r * d_pad : nullptr, res2, r2, red);
+    if (threadIdx.x == 0) {
+        const float v4 = __uint_as_float(stats->v4max_bits), vn = __uint_as_float(stats->vnmax_bits), vrho = __uint_as_float(stats->rhomax_bits);
         const float q4 = (float)sqrt(sqrt(s4)), qn = (float)sqrt(s2);
-        eps[r] = eps_sigmas * (1.0f / 512.0f) * 0.8165f * q4 * v4 + 2e-5f * qn * vn;
+        float e;
+        if (eps_mode == 1) {
+            const float q16n = (float)sqrt(r2) * 1.000001f, qrho = (float)sqrt(res2) * 1.000001f;
+            e = vrho * q16n + vn * qrho + ((float)d_pad * 2.3841858e-7f + 1e-5f) * qn * vn;
+        } else {
+            e = eps_sigmas * (1.0f / 512.0f) * 0.8165f * q4 * v4 + 2e-5f * qn * vn;
+        }
+        eps[r] = e;
     }
 }
 
-bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16, int64_t nq, int64_t nq_pad, int d, int d_pad,
-                               bool renorm, const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st) {
-    if (d != d_pad || d_pad > 2048 || (reinterpret_cast<uintptr_t>(raw) & 15)) return false;
-    const int wpb = 4;
+void launch_prep_queries(const float* raw, int d, float* q32, __nv_bfloat16* q16, float* q32r, int64_t nq, int64_t nq_pad, int d_pad,
+                         bool renorm, bool rotate, uint32_t seed, const DevStats* stats, float eps_sigmas, int eps_mode, float* eps,
+                         cudaStream_t st) {
+    if (nq <= 0) return;
     const int64_t rows = q16 ? nq_pad : nq;
-    prep_queries_fused_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(raw, q32, q16, nq, rows, d_pad, renorm ? 1 : 0,
-                                                                                       stats, eps_sigmas, eps);
-    return true;
+    const size_t smem = (size_t)d_pad * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(prep_queries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_pdl(prep_queries_kernel, dim3((unsigned)rows), dim3(ROW_THREADS), smem, st,
+               raw, d, d, q32, q16, q32r, nq, d_pad, renorm ? 1 : 0, rotate ? 1 : 0, seed, stats, eps_sigmas, eps_mode, eps);
 }
 
 // ---- tiled bf16 copy ---------------------------------------------------------------------------------
@@ -301,13 +326,6 @@ void launch_aqe_queries(const float* db32, const int64_t* top_ids, int64_t nq, i
                         float* q_out, cudaStream_t st) {
     if (nq <= 0) return;
     aqe_queries_kernel<<<(unsigned)nq, 256, 0, st>>>(db32, top_ids, kq, w, n, d_pad, q_out);
-}
-
-void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
-                         const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st) {
-    if (nq <= 0) return;
-    const int wpb = 4;
-    prep_queries_kernel<<<(unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, st>>>(q32, q16, nq, d_pad, renorm ? 1 : 0, stats, eps_sigmas, eps);
 }
 
 }  // namespace xs

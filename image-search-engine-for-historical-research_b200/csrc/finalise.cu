@@ -15,7 +15,30 @@ namespace xs {
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_MAX_LISTS = 4096;          // partial lists per query that the shared-memory gather supports
 constexpr int FIN_SMEM_BUDGET = 200 * 1024;  // dynamic shared memory the finalise kernel may ask for
-constexpr int FIN_SPLIT_MAX_Q = 1 << 20;     // coarse-mode batches use the select -> rescore -> emit split (the fused kernel serves exact mode)
+constexpr int FIN_FUSED_MAX_Q = 128;         // coarse-mode batches up to this size: ONE kernel (select + rescore + emit, several CTAs per query)
+constexpr float MODEL_CHECK = 0.75f;         // a rescored candidate whose |coarse - exact| exceeds this fraction of eps voids the certificate
+
+// ---- peer-exchange handshake words (system scope: written by kernels running on OTHER GPUs over NVLink) ----
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// Spin until *p >= want.  A peer that never arrives is a protocol error: trap after ~20 s instead of hanging the GPU.
+__device__ __forceinline__ void wait_word_sys(const uint32_t* p, uint32_t want) {
+    if (ld_acquire_sys(p) >= want) return;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        __nanosleep(64);
+        if (clock64() - t0 > 40000000000ll) { printf("xs: peer exchange timed out (want %u, have %u)\n", want, ld_acquire_sys(p)); __trap(); }
+    }
+}
 
 // Exact inner products of TWO database rows with the query row held in shared memory: fp32
 // operands, fp64 accumulation, fixed order (lane-strided float4s, chunk by chunk), warp-reduced.
@@ -98,12 +121,12 @@ __device__ void block_sort_desc(uint64_t* a, int m) {
 // the kk-th largest key -- never above it, at most one bin (typically 1-3 items) below.  The exactness
 // band is cut from that edge, so a lower value only adds a few candidates.  Replaces four 8-bit radix
 // passes with warp-match aggregation (28k cycles at 6.6k items) by ~4k cycles.
-template <typename Each>
+template <int NT, typename Each>
 __device__ uint32_t block_kth_edge(Each each, uint32_t kk, uint32_t* bins, uint32_t* sh, uint32_t* wsum) {
-    constexpr int NB = 4096, PER = NB / FIN_THREADS;
+    constexpr int NB = 4096, PER = NB / NT;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { sh[0] = 0xFFFFFFFFu; sh[1] = 0u; sh[2] = 0u; }
-    for (int i = threadIdx.x; i < NB; i += FIN_THREADS) bins[i] = 0;
+    for (int i = threadIdx.x; i < NB; i += NT) bins[i] = 0;
     __syncthreads();
     uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
     each([&](uint64_t it, bool valid) { if (valid) { const uint32_t key = item_key(it); kmin = min(kmin, key); kmax = max(kmax, key); } });
@@ -128,7 +151,7 @@ __device__ uint32_t block_kth_edge(Each each, uint32_t kk, uint32_t* bins, uint3
     if (lane == 0) wsum[warp] = suf;
     __syncthreads();
     uint32_t above = 0;
-    for (int w = warp + 1; w < FIN_THREADS / 32; ++w) above += wsum[w];
+    for (int w = warp + 1; w < NT / 32; ++w) above += wsum[w];
     const uint32_t incl = above + suf, excl = incl - mine;
     if (incl >= kk && excl < kk) {                      // exactly one thread
         uint32_t run = excl;
@@ -186,6 +209,46 @@ __device__ void gather_pool(const uint64_t* __restrict__ pool_items, int64_t q, 
     }
     (void)total;
     __syncthreads();
+}
+
+// Last step of every finalise form, whole CTA: `items` (shared memory) holds the query's candidates sorted by
+// (exact score desc, id asc).  Writes the first k to the caller's arrays and / or straight into every rank's mailbox
+// (peer exchange: ids, scores and the certificate word, then the query's arrival flag per rank).
+__device__ void emit_topk(const FinaliseArgs& a, int64_t q, const uint64_t* items, int ncand, uint32_t selfkey, int status) {
+    const int kout = min(a.k, ncand);
+    if (kout < a.k) status |= ST_UNCERTIFIED;           // a short list (NaN scores, a bad threshold) is never handed out as certified
+    const PushTarget& p = a.push;
+    if (p.world > 0) {
+        // the receivers must have merged this slot's previous epoch before it is overwritten
+        if ((int)threadIdx.x < p.world && p.epoch > 1) wait_word_sys(p.my_acks + threadIdx.x, p.epoch - 1);
+        __syncthreads();
+    }
+    for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
+        int64_t id = -1;
+        float sc = -INFINITY;
+        if (r < kout) {
+            const uint64_t it = items[r];
+            uint32_t key = item_key(it);
+            if (a.self_base >= 0 && key == 0xFFFFFFFFu) key = selfkey;
+            id = (int64_t)item_row(it) + a.id_offset;
+            sc = key_score(key);
+        }
+        if (a.out_idx) a.out_idx[q * a.out_pitch + r] = id;
+        if (a.out_score) a.out_score[q * a.out_pitch + r] = sc;
+        for (int g = 0; g < p.world; ++g) {
+            p.ids[g][q * a.k + r] = id;
+            p.scores[g][q * a.k + r] = sc;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (a.status) a.status[q] = status;
+        for (int g = 0; g < p.world; ++g) p.status[g][q] = status;
+    }
+    if (p.world > 0) {
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + q, p.epoch);
+    }
 }
 
 // SPLIT = false: the whole of stage 2 in one CTA per query (large batches, exact mode).
@@ -264,7 +327,7 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
             const uint64_t T = block_kth_largest(each, kk, 8, hist, misc);
             cut = T; cut_key = (uint32_t)(T >> 32);
         } else {
-            const uint32_t edge = block_kth_edge(each, kk, bins, edge_sh, edge_wsum);
+            const uint32_t edge = block_kth_edge<FIN_THREADS>(each, kk, bins, edge_sh, edge_wsum);
             cut_key = score_key(key_score(edge) - 2.f * a.eps[q]);
             cut = (uint64_t)cut_key << 32;
         }
@@ -323,24 +386,8 @@ finalise_kernel(FinaliseArgs a, int cand_max, int item_cap) {
     for (int c = ncand + threadIdx.x; c < m; c += blockDim.x) cand[c] = 0ull;
     block_sort_desc(cand, m);
 
-    const int kout = min(a.k, ncand);
-    for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
-        int64_t id = -1;
-        float sc = -INFINITY;
-        if (r < kout) {
-            uint64_t it = cand[r];
-            uint32_t key = item_key(it);
-            if (a.self_base >= 0 && key == 0xFFFFFFFFu) key = sh_selfkey;
-            id = (int64_t)item_row(it) + a.id_offset;
-            sc = key_score(key);
-        }
-        a.out_idx[q * a.out_pitch + r] = id;
-        if (a.out_score) a.out_score[q * a.out_pitch + r] = sc;
-    }
-    if (threadIdx.x == 0) {
-        if (a.status) a.status[q] = uncertified ? ST_UNCERTIFIED : 0;
-        if (a.n_cand) atomicAdd(a.n_cand, ncand);
-    }
+    emit_topk(a, q, cand, ncand, sh_selfkey, uncertified ? ST_UNCERTIFIED : 0);
+    if (threadIdx.x == 0 && a.n_cand) atomicAdd(a.n_cand, ncand);
 }
 
 // ---- split pipeline: rescore on every SM, then sort + emit ---------------------------------------------
@@ -381,7 +428,11 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
             acc = fma((double)x.z, (double)w.z, acc); acc = fma((double)x.w, (double)w.w, acc);
         }
         acc = warp_sum(acc);
-        if (lane == 0) cand[c] = make_item((float)acc, row);
+        if (lane == 0) {
+            // model check: the band assumes |coarse - exact| stays well inside eps; a candidate that says otherwise voids it
+            if (fabsf(key_score(item_key(cand[c])) - (float)acc) > MODEL_CHECK * a.eps[q]) atomicOr(&a.w_flag[q], ST_UNCERTIFIED);
+            cand[c] = make_item((float)acc, row);
+        }
         __syncwarp();
     }
     // ---- completion ticket ----
@@ -415,45 +466,225 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
         }
     }
     block_sort_desc(items, m);
-    const int kout = min(a.k, ncand);
-    for (int r = threadIdx.x; r < a.k; r += blockDim.x) {
-        int64_t id = -1;
-        float sc = -INFINITY;
-        if (r < kout) {
-            const uint64_t it = items[r];
-            uint32_t key = item_key(it);
-            if (a.self_base >= 0 && key == 0xFFFFFFFFu) key = sh_selfkey;
-            id = (int64_t)item_row(it) + a.id_offset;
-            sc = key_score(key);
-        }
-        a.out_idx[q * a.out_pitch + r] = id;
-        if (a.out_score) a.out_score[q * a.out_pitch + r] = sc;
-    }
+    const int flags = __ldcg(&a.w_flag[q]);
+    emit_topk(a, q, items, ncand, sh_selfkey, flags);
     if (threadIdx.x == 0) {
-        if (a.status) a.status[q] = a.w_flag[q];
+        a.w_ncand[q] = 0; a.w_flag[q] = 0;              // the counters are shared with the fused form: leave them zero
         if (a.n_cand) atomicAdd(a.n_cand, ncand);
     }
 }
 
-int finalise_cand_max(int k) {
+// ---- fused form for small batches: select + rescore + emit in ONE launch ---------------------------------------
+// grid (nq, S).  Every one of a query's S CTAs repeats the cheap part (gather the pools, conservative k-th, band) and
+// gets the same answer; the candidates are then dealt by row id (row % S), each CTA rescores its share exactly and
+// appends the results to the query's global list; the last CTA to finish (ticket) sorts, emits and -- with the peer
+// exchange on -- stores the k results into every rank's mailbox.  One launch instead of two and no hand-over through
+// HBM between them: the per-step fixed cost that bounds strong scaling.
+constexpr int FF_THREADS = 256, FF_WARPS = FF_THREADS / 32;
+__global__ void __launch_bounds__(FF_THREADS)
+finalise_fused_kernel(FinaliseArgs a, int cand_max, int item_cap) {
+    extern __shared__ uint64_t ff_smem[];
+    uint64_t* mine = ff_smem;                           // [cand_max] this CTA's share of the band
+    uint64_t* items = ff_smem + cand_max;               // phase 1: [item_cap] gathered pool items | offsets | 4096 bins
+    const bool staged = a.P <= FIN_MAX_LISTS;
+    int* offs = reinterpret_cast<int*>(items + item_cap);
+    uint32_t* bins = reinterpret_cast<uint32_t*>(offs + (staged ? ((a.P + 4) & ~3) : 4));
+    float* rows = reinterpret_cast<float*>(ff_smem + cand_max);      // phase 2 (aliases phase 1): [FF_WARPS][d_pad] row staging
+    uint64_t* sorted = ff_smem + cand_max;              // phase 3 (aliases): the query's rescored candidates
+    __shared__ uint32_t edge_sh[4];
+    __shared__ uint32_t edge_wsum[FF_WARPS];
+    __shared__ int scan_scratch[33];
+    __shared__ uint32_t sh_found, sh_nmine, sh_flag, sh_tot, sh_selfkey, sh_last;
+    pdl_wait();
+    const int64_t q = blockIdx.x;
+    const uint32_t y = blockIdx.y, S = gridDim.y;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) { sh_found = 0; sh_nmine = 0; sh_flag = 0; sh_tot = 0; sh_selfkey = 0; }
+    __syncthreads();
+    uint32_t total = 0;
+    {
+        uint32_t thr = 0, t = 0;
+        for (int p = threadIdx.x; p < a.P; p += FF_THREADS) {
+            const int64_t slot = pool_slot(q, p, a.P);
+            const int c = a.pool_count[slot];
+            if (staged) offs[p] = c; else t += (uint32_t)c;
+            thr = max(thr, a.pool_thr[slot]);
+        }
+        if (thr) atomicMax(&sh_flag, thr);
+        if (!staged && t) atomicAdd(&sh_tot, t);
+        __syncthreads();
+        if (staged) { block_exclusive_scan(offs, a.P, scan_scratch); total = (uint32_t)offs[a.P]; }
+        else total = sh_tot;
+    }
+    const uint32_t max_thr = sh_flag;
+    const bool in_smem = staged && total <= (uint32_t)item_cap;
+    if (in_smem) gather_pool(a.pool_items, q, a.P, a.cap, offs, (int)total, items);
+
+    auto each = [&](auto fn) {
+        if (in_smem) {
+            const int n_up = ((int)total + FF_THREADS - 1) / FF_THREADS * FF_THREADS;
+            for (int i = threadIdx.x; i < n_up; i += FF_THREADS) {
+                const bool valid = i < (int)total;
+                fn(valid ? items[i] : 0ull, valid);
+            }
+        } else {
+            for (int p = warp; p < a.P; p += FF_WARPS) {
+                const int64_t slot = pool_slot(q, p, a.P);
+                const int cnt = a.pool_count[slot];
+                const uint64_t* lst = a.pool_items + slot * a.cap;
+                for (int b = 0; b < cnt; b += 32) {
+                    const int i = b + lane;
+                    const bool valid = i < cnt;
+                    fn(valid ? lst[i] : 0ull, valid);
+                }
+            }
+        }
+    };
+
+    const uint32_t kk = min((uint32_t)a.k, total);
+    uint64_t cut = 0;
+    uint32_t cut_key = 0;
+    if (total > kk) {
+        const uint32_t edge = block_kth_edge<FF_THREADS>(each, kk, bins, edge_sh, edge_wsum);
+        cut_key = score_key(key_score(edge) - 2.f * a.eps[q]);
+        cut = (uint64_t)cut_key << 32;
+    }
+    __syncthreads();
+    each([&](uint64_t it, bool valid) {
+        const bool take = valid && it >= cut;
+        const bool take_mine = take && (item_row(it) % S == y);
+        const uint32_t m_all = __ballot_sync(0xffffffffu, take), m_mine = __ballot_sync(0xffffffffu, take_mine);
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (m_all) atomicAdd(&sh_found, (uint32_t)__popc(m_all));
+            if (m_mine) base = atomicAdd(&sh_nmine, (uint32_t)__popc(m_mine));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t pos = base + __popc(m_mine & lanemask_lt());
+        if (take_mine && pos < (uint32_t)cand_max) mine[pos] = it;
+    });
+    __syncthreads();                                    // also: phase 1's shared memory is free from here on
+    const uint32_t found = sh_found;
+    const int nmine = (int)min(sh_nmine, (uint32_t)cand_max);
+    // certificate: nothing that could belong to the exact top-k was dropped upstream (every CTA of the query computes the same bit)
+    const bool uncertified = (found > (uint32_t)cand_max) || (max_thr != 0 && max_thr >= cut_key);
+
+    // ---- exact rescoring of this CTA's share: one warp per candidate, the 8 KB row staged with cp.async ----
+    const float* qrow = a.q32 + q * a.d_pad;
+    const float band_check = MODEL_CHECK * a.eps[q];
+    float* buf = rows + (size_t)warp * a.d_pad;
+    const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
+    for (int c = warp; c < nmine; c += FF_WARPS) {
+        const uint64_t it = mine[c];
+        const uint32_t row = item_row(it);
+        const float* v = a.db32 + (int64_t)row * a.d_pad;
+        for (int i = lane * 4; i < a.d_pad; i += 128)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sbuf + (uint32_t)i * 4u), "l"(v + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        double acc = 0.0;
+        for (int i = lane * 4; i < a.d_pad; i += 128) {
+            const float4 x = *reinterpret_cast<const float4*>(buf + i);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(qrow + i));
+            acc = fma((double)x.x, (double)w.x, acc); acc = fma((double)x.y, (double)w.y, acc);
+            acc = fma((double)x.z, (double)w.z, acc); acc = fma((double)x.w, (double)w.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float exact = (float)acc;
+            if (fabsf(key_score(item_key(it)) - exact) > band_check) atomicOr(&a.w_flag[q], ST_UNCERTIFIED);   // model check
+            const int pos = atomicAdd(&a.w_ncand[q], 1);
+            if (pos < cand_max) a.w_cand[q * cand_max + pos] = make_item(exact, row);
+        }
+        __syncwarp();
+    }
+    // ---- completion ticket ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sh_last = (atomicAdd(&a.w_ticket[q], 1) == (int)S - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    // ---- sort + emit (the query's last CTA only) ----
+    const int ncand = min(__ldcg(&a.w_ncand[q]), cand_max);
+    const int flags = __ldcg(&a.w_flag[q]) | (uncertified ? ST_UNCERTIFIED : 0);
+    int m = 1;
+    while (m < ncand) m <<= 1;
+    if (m < 2) m = 2;
+    for (int c = threadIdx.x; c < m; c += FF_THREADS) sorted[c] = (c < ncand) ? __ldcg(a.w_cand + q * cand_max + c) : 0ull;
+    __syncthreads();
+    if (a.self_base >= 0) {
+        const uint32_t self_row = (uint32_t)(a.self_base + q);
+        for (int c = threadIdx.x; c < ncand; c += FF_THREADS)
+            if (item_row(sorted[c]) == self_row)
+                sorted[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
+        if (threadIdx.x < 32) {
+            const double s = exact_dot1(a.db32 + (int64_t)self_row * a.d_pad, qrow, a.d_pad);
+            if (threadIdx.x == 0) sh_selfkey = score_key((float)s);
+        }
+    }
+    block_sort_desc(sorted, m);
+    emit_topk(a, q, sorted, ncand, sh_selfkey, flags);
+    if (threadIdx.x == 0) {
+        a.w_ncand[q] = 0; a.w_flag[q] = 0; a.w_ticket[q] = 0;       // ready for the next call
+        if (a.n_cand) atomicAdd(a.n_cand, ncand);
+    }
+}
+
+// Candidates per query the rescoring stage can hold: the band of the statistical certificate is a few dozen rows wide
+// on top of k; the worst-case band (mode 1) is ~8x wider.
+int finalise_cand_max(int k, int mode) {
     int m = 256;
     while (m < 2 * k) m <<= 1;
+    if (mode == 1) m *= 4;
     return m;
 }
-size_t finalise_work_bytes(int64_t nq, int k) { return (size_t)nq * finalise_cand_max(k) * sizeof(uint64_t) + (size_t)nq * 3 * sizeof(int); }
+size_t finalise_work_bytes(int64_t nq, int k, int cand_max) {
+    (void)k;
+    return (size_t)nq * (size_t)cand_max * sizeof(uint64_t);
+}
+
+static int finalise_form(const FinaliseArgs& a, int64_t nq) {     // 0: one CTA per query, 1: select -> rescore+emit, 2: fused
+    if (a.exact || !a.work || !a.ticket) return 0;
+    return nq <= FIN_FUSED_MAX_Q ? 2 : 1;
+}
+int finalise_launches(const FinaliseArgs& a, int64_t nq) { return finalise_form(a, nq) == 1 ? 2 : 1; }
 
 void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
     FinaliseArgs a = a_in;
-    const int cand_max = finalise_cand_max(a.k);
-    const bool split = !a.exact && a.work && a.ticket && nq <= FIN_SPLIT_MAX_Q;
-    if (split) {
+    const int cand_max = a.cand_max > 0 ? a.cand_max : finalise_cand_max(a.k, 0);
+    const int form = finalise_form(a, nq);
+    if (form) {
         a.w_cand = static_cast<uint64_t*>(a.work);
-        a.w_ncand = reinterpret_cast<int*>(a.w_cand + (size_t)nq * cand_max);
-        a.w_flag = a.w_ncand + nq;
         a.w_ticket = a.ticket;                       // zero-initialised once by the owner, self-resetting
+        a.w_ncand = a.ticket + nq;
+        a.w_flag = a.ticket + 2 * nq;
     }
     const size_t offs_bytes = ((a.P <= FIN_MAX_LISTS) ? (size_t)((a.P + 4) & ~3) : 4) * sizeof(int);
+    if (form == 2) {
+        // phase 1 (items + offsets + bins) and phase 2 (row staging) share one region; 64 KB keeps three CTAs on an SM
+        size_t region = (size_t)FF_WARPS * a.d_pad * sizeof(float);
+        if (region < (size_t)cand_max * sizeof(uint64_t)) region = (size_t)cand_max * sizeof(uint64_t);
+        const size_t fixed1 = offs_bytes + 4096 * sizeof(uint32_t);
+        if (region < fixed1 + 2048 * sizeof(uint64_t)) region = fixed1 + 2048 * sizeof(uint64_t);
+        size_t want_items = (size_t)a.P * (size_t)a.cap;
+        size_t room = (region - fixed1) / sizeof(uint64_t);
+        if (want_items > room && region < 64 * 1024) { region = 64 * 1024; room = (region - fixed1) / sizeof(uint64_t); }
+        int item_cap = (int)(want_items < room ? want_items : room) & ~1;
+        if (a.P > FIN_MAX_LISTS) item_cap = 0;
+        const size_t smem = (size_t)cand_max * sizeof(uint64_t) + region;
+        static int num_sms = 0;
+        if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
+        // CTAs per query: as many as fit in ONE wave at three CTAs per SM, at most 16
+        int S = (int)((int64_t)3 * num_sms / nq);
+        S = S < 1 ? 1 : (S > 16 ? 16 : S);
+        cudaFuncSetAttribute(finalise_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024));
+        launch_pdl(finalise_fused_kernel, dim3((unsigned)nq, (unsigned)S), dim3(FF_THREADS), smem, st, a, cand_max, item_cap);
+        return;
+    }
     const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float) + 4096 * sizeof(uint32_t);
     // room for the gathered pool items: what the pools can hold, capped by the shared-memory budget
     size_t want_items = (size_t)a.P * (size_t)a.cap;
@@ -463,20 +694,19 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     item_cap = (item_cap + 1) & ~1;                  // keeps the fp32 query row behind it 16-byte aligned
     if (a.P > FIN_MAX_LISTS) item_cap = 0;
     const size_t smem = fixed + (size_t)item_cap * sizeof(uint64_t);
-    if (split) {
+    if (form == 1) {
         cudaFuncSetAttribute(finalise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<true>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
         size_t rsm = (size_t)RS_WARPS * a.d_pad * sizeof(float);
         if (rsm < (size_t)cand_max * sizeof(uint64_t)) rsm = (size_t)cand_max * sizeof(uint64_t);
         if (rsm > 48 * 1024) cudaFuncSetAttribute(finalise_rescore_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-        const unsigned rs_split = nq <= 128 ? 16u : (nq <= 512 ? 8u : 4u);
+        const unsigned rs_split = nq <= 512 ? 8u : 4u;
         launch_pdl(finalise_rescore_emit_kernel, dim3((unsigned)nq, rs_split), dim3(RS_WARPS * 32), rsm, st, a, cand_max);
     } else {
         cudaFuncSetAttribute(finalise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<false>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
     }
 }
-int finalise_launches(const FinaliseArgs& a, int64_t nq) { return (!a.exact && a.work && a.ticket && nq <= FIN_SPLIT_MAX_Q) ? 2 : 1; }
 
 // ---- threshold bootstrap ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -526,38 +756,22 @@ void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, 
 }
 
 // ---- multi-GPU merge -------------------------------------------------------------------------------
-// ---- peer-exchange handshake words (system scope: written by kernels running on OTHER GPUs over NVLink) ----
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-// Spin until *p >= want.  A peer that never arrives is a protocol error: trap after ~20 s instead of hanging the GPU.
-__device__ __forceinline__ void wait_word_sys(const uint32_t* p, uint32_t want) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(p) < want) {
-        __nanosleep(64);
-        if (clock64() - t0 > 40000000000ll) { printf("xs: peer exchange timed out (want %u, have %u)\n", want, ld_acquire_sys(p)); __trap(); }
-    }
-}
-
 // in: [parts][nq][k] (score desc, id asc inside every part; parts own increasing id ranges, so the
 // flat position p*k + r orders equal scores by ascending id).  One CTA per query.
-// With sync.flags set this is the receiving end of the peer exchange: part p was written into this GPU's
-// mailbox by rank p's push kernel, which then released flags[p] = epoch; the last CTA to finish reading
-// acknowledges the epoch to every peer (their next push into this mailbox slot waits for it).
+// With sync.flags set this is the receiving end of the peer exchange: query q of part p was stored into this GPU's
+// mailbox by rank p (its emit step or its push kernel), which then released flags[p][q] = epoch, so a query is merged
+// as soon as ITS lists are in; the last CTA to finish reading acknowledges the epoch to every peer (their next store
+// into this mailbox slot waits for it).
 __global__ void __launch_bounds__(512)
-merge_parts_kernel(const char* in_idx, const char* in_score, int64_t idx_stride, int64_t score_stride, int parts,
-                   int64_t nq, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_score, int m, const MergeSync sync) {
+merge_parts_kernel(const char* in_idx, const char* in_score, const char* in_status, int64_t idx_stride, int64_t score_stride, int64_t status_stride,
+                   int parts, int64_t nq, int k, int64_t* __restrict__ out_idx, float* __restrict__ out_score, int32_t* __restrict__ out_status,
+                   int m, const MergeSync sync) {
     extern __shared__ uint64_t cand[];                  // [m] power of two >= parts*k
     __shared__ int s_last;
     const int64_t q = blockIdx.x;
     const int total = parts * k;
     if (sync.flags) {
-        if ((int)threadIdx.x < parts) wait_word_sys(sync.flags + threadIdx.x, sync.epoch);
+        if ((int)threadIdx.x < parts) wait_word_sys(sync.flags + (int64_t)threadIdx.x * sync.flag_stride + q, sync.epoch);
         __syncthreads();
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -584,6 +798,12 @@ merge_parts_kernel(const char* in_idx, const char* in_score, int64_t idx_stride,
         out_idx[q * k + r] = id;
         if (out_score) out_score[q * k + r] = s;
     }
+    if (out_status && threadIdx.x == 0) {               // a query is certified only if every shard certified its list
+        int32_t st = 0;
+        if (in_status)
+            for (int p = 0; p < parts; ++p) st |= reinterpret_cast<const int32_t*>(in_status + (int64_t)p * status_stride)[q];
+        out_status[q] = st;
+    }
     if (sync.flags) {
         __syncthreads();                                // every read of the mailbox by this CTA has completed
         if (threadIdx.x == 0) {
@@ -598,9 +818,9 @@ merge_parts_kernel(const char* in_idx, const char* in_score, int64_t idx_stride,
     }
 }
 
-// part p's id list starts at in_idx + p*idx_stride BYTES, its score list at in_score + p*score_stride BYTES
-void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride, int64_t score_stride, int parts, int64_t nq, int k,
-                        int64_t* out_idx, float* out_score, cudaStream_t st, const MergeSync* sync) {
+void launch_merge_parts(const void* in_idx, const void* in_score, const void* in_status, int64_t idx_stride, int64_t score_stride,
+                        int64_t status_stride, int parts, int64_t nq, int k,
+                        int64_t* out_idx, float* out_score, int32_t* out_status, cudaStream_t st, const MergeSync* sync) {
     if (nq <= 0) return;
     int m = 2;
     while (m < parts * k) m <<= 1;
@@ -608,14 +828,16 @@ void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_st
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     MergeSync none{};
-    merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(static_cast<const char*>(in_idx), static_cast<const char*>(in_score), idx_stride, score_stride,
-                                                      parts, nq, k, out_idx, out_score, m, sync ? *sync : none);
+    merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(static_cast<const char*>(in_idx), static_cast<const char*>(in_score), static_cast<const char*>(in_status),
+                                                      idx_stride, score_stride, status_stride, parts, nq, k, out_idx, out_score, out_status, m,
+                                                      sync ? *sync : none);
 }
 
-// Sending end of the peer exchange: the CTAs of column g copy this rank's packed result into rank g's mailbox
-// (plain 16-byte stores through the NVLink peer mapping, every load issued before the first store; g == rank is a
-// local copy) and the last of them releases rank g's arrival flag.  Before overwriting the slot they wait for
-// rank g's acknowledgement of the slot's previous epoch.
+// Sending end of the peer exchange as a kernel of its own (for payloads that were not produced by an emit step with
+// the push fused in): the CTAs of column g copy this rank's packed result into rank g's mailbox (plain 16-byte stores
+// through the NVLink peer mapping, every load issued before the first store; g == rank is a local copy) and the last
+// of them releases rank g's per-query arrival flags.  Before overwriting the slot they wait for rank g's
+// acknowledgement of the slot's previous epoch.
 constexpr int PUSH_THREADS = 1024, PUSH_UNROLL = 8;
 __global__ void __launch_bounds__(PUSH_THREADS)
 exchange_push_kernel(const uint4* __restrict__ src, int64_t n16, const PushArgs a) {
@@ -645,8 +867,10 @@ exchange_push_kernel(const uint4* __restrict__ src, int64_t n16, const PushArgs 
             s_last = (atomicAdd(a.tickets + g, 1u) == gridDim.y - 1) ? 1 : 0;
             if (s_last) { a.tickets[g] = 0; __threadfence_system(); }
         }
-        if (s_last) st_release_sys(a.flag[g], a.epoch);
     }
+    __syncthreads();
+    if (s_last)             // fence.sys above + relaxed stores = release of the whole payload, one flag per query
+        for (int64_t i = threadIdx.x; i < a.nq; i += PUSH_THREADS) st_relaxed_sys(a.flag[g] + i, a.epoch);
 }
 
 void launch_exchange_push(const void* src, int64_t bytes, const PushArgs& a, int world, cudaStream_t st) {

@@ -137,6 +137,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// device-scope handshake words of the in-kernel threshold bootstrap
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const uint64_t* p) {
+    uint64_t v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+constexpr int BOOT_PER_LANE = (BOOT_MAX_GRID * 8 + 31) / 32;      // sample scores per lane of the selecting warp
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
                  int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
                  int k, int k_keep, int cap, int sample_mode, int db_tiled, uint64_t hint_db, const float* __restrict__ eps, const float* __restrict__ thr0,
-                 uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr) {
+                 uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr, const InlineBoot boot) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     using S = Shape<MODE>;
@@ -339,10 +350,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 pool_thr[slot] = 0u;
                 continue;
             }
-            for (int t = t0; t < t1; ++t, ++it) {
-                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
-                tc_fence_after();
+            // one accumulator -> this thread's list: keep what beats the running threshold, trim a list that could overflow
+            auto filter_tile = [&](uint32_t acc, int t) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
 #pragma unroll 1
                 for (int c = 0; c < TILE_N / 32; ++c) {
@@ -376,6 +385,127 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         if (lane == src) { cnt = c_new; thr = fmaxf(thr, key_score(T)); thr_rec = max(thr_rec, T); }
                     }
                 }
+            };
+            int t_first = t0;
+            if (boot.on) {
+                // ---- in-kernel threshold bootstrap (one job per CTA, every CTA resident) ------------------------------
+                // The FIRST tile of every CTA doubles as the sample: (A) its 8 best scores per query go to global memory,
+                // (B) once all CTAs have arrived, CTA c takes the k-th best of query c's sample (a valid lower bound of the
+                // database's k-th best) minus the band and publishes it, (C) every thread picks up its query's threshold
+                // and only then filters the tile, which has been waiting in its TMEM accumulator.  Meanwhile TMA and MMA
+                // run ahead into the ring and the second accumulator, so the exchange hides behind the second tile's
+                // HBM stream.  Replaces the separate bootstrap GEMM + threshold-select launches.
+                float top[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
+                mbar_wait(smem_u32(&bars->tfull[0]), 0);
+                tc_fence_after();
+                {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+#pragma unroll 1
+                    for (int c = 0; c < TILE_N / 32; ++c) {
+                        uint32_t v[32];
+                        tc_ld32(taddr + c * 32, v);
+                        tc_ld_wait();
+                        const int64_t lim = n_valid - ((int64_t)t0 * tile_stride * TILE_N + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float s = __uint_as_float(v[i]);
+                            if (s > top[7] && i < lim) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) { const float hi = fmaxf(top[j], s); s = fminf(top[j], s); top[j] = hi; }
+                            }
+                        }
+                    }
+                }
+                if (active) {
+                    float4* dst = reinterpret_cast<float4*>(boot.samp + ((size_t)q * gridDim.x + blockIdx.x) * 8);
+                    dst[0] = make_float4(top[0], top[1], top[2], top[3]);
+                    dst[1] = make_float4(top[4], top[5], top[6], top[7]);
+                }
+                __threadfence();
+                const int n_warps_on = (int)((min(nq, (int64_t)GEMM_BM) + 31) >> 5);      // epilogue warps that hold queries (this branch)
+                asm volatile("bar.sync 1, %0;" :: "r"(n_warps_on * 32) : "memory");
+                if (ew == 0) {
+                    if (lane == 0) {
+                        __threadfence();
+                        atomicAdd(boot.arrive, 1u);
+                    }
+                    if ((int64_t)blockIdx.x < nq) {
+                        // (B) this CTA owns queries blockIdx.x, blockIdx.x + grid, ...
+                        if (lane == 0) {
+                            const long long w0 = clock64();
+                            while ((int32_t)(ld_acquire_gpu_u32(boot.arrive) - boot.arrive_target) < 0) {
+                                __nanosleep(40);
+                                if (clock64() - w0 > 8000000000ll) { printf("xs gemm_topk: bootstrap arrival timeout (block %d)\n", blockIdx.x); __trap(); }
+                            }
+                        }
+                        __syncwarp();
+                        const int n_samp = (int)gridDim.x * 8;
+                        for (int64_t qq = blockIdx.x; qq < nq; qq += gridDim.x) {
+                            const float* src = boot.samp + (size_t)qq * gridDim.x * 8;
+                            uint32_t keys[BOOT_PER_LANE];
+                            int valid_cnt = 0;
+#pragma unroll
+                            for (int j = 0; j < BOOT_PER_LANE; ++j) {
+                                const int i = j * 32 + lane;
+                                const float s = (i < n_samp) ? __ldcg(src + i) : -INFINITY;
+                                keys[j] = (s > -INFINITY) ? score_key(s) : 0u;
+                                valid_cnt += (s > -INFINITY) ? 1 : 0;
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
+                            float t_pub = -INFINITY;
+                            if (valid_cnt >= k) {
+                                uint32_t prefix = 0, mask = 0, kk = (uint32_t)k;
+#pragma unroll 1
+                                for (int pass = 0; pass < 4; ++pass) {
+                                    const int shift = 24 - 8 * pass;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) my_hist[lane * 8 + j] = 0;
+                                    __syncwarp();
+#pragma unroll
+                                    for (int j = 0; j < BOOT_PER_LANE; ++j) {
+                                        const bool in = keys[j] != 0u && ((keys[j] & mask) == prefix);
+                                        hist_add(my_hist, (keys[j] >> shift) & 255u, in);
+                                    }
+                                    __syncwarp();
+                                    uint32_t dg, kr;
+                                    warp_pick_digit(my_hist, kk, dg, kr);
+                                    kk = kr;
+                                    prefix |= dg << shift;
+                                    mask |= 255u << shift;
+                                    __syncwarp();
+                                }
+                                // the main pass keeps scores strictly above the threshold: k-th best of the sample, minus the band
+                                t_pub = nextafterf(key_score(prefix) - 2.f * eps[qq], -INFINITY);
+                            }
+                            if (lane == 0)
+                                st_release_gpu_u64(boot.thr_pub + qq, ((uint64_t)boot.epoch << 32) | (uint64_t)__float_as_uint(t_pub));
+                        }
+                    }
+                }
+                // (C)
+                if (active) {
+                    const long long w0 = clock64();
+                    uint64_t w;
+                    while ((uint32_t)((w = ld_acquire_gpu_u64(boot.thr_pub + q)) >> 32) != boot.epoch) {
+                        __nanosleep(40);
+                        if (clock64() - w0 > 8000000000ll) { printf("xs gemm_topk: bootstrap threshold timeout (block %d)\n", blockIdx.x); __trap(); }
+                    }
+                    thr = __uint_as_float((uint32_t)w);
+                }
+                __syncwarp();
+                filter_tile(0u, t0);
+                release_acc(0u);
+                t_first = t0 + 1;
+                it = 1;
+            }
+            for (int t = t_first; t < t1; ++t, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
+                tc_fence_after();
+                filter_tile(acc, t);
                 release_acc(acc);
             }
             // end of job: keep only what can still matter -- everything within 2*eps below this
@@ -443,6 +573,13 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
     p.tile_stride = 1;
     p.sample_mode = 0;
     p.half = 0;
+    // in-kernel threshold bootstrap: one query tile, exactly one job per CTA (so every CTA is resident and its first tile
+    // can serve as the sample), and a sample that holds well over k scores
+    p.inline_boot = 0;
+    if (!p.pair && p.m_tiles == 1 && forced_splits <= 0 && p.n_tiles >= 16) {
+        const int s = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+        if (s <= BOOT_MAX_GRID && 8 * s >= (5 * k + 3) / 4 + 8) { p.splits = s; p.grid = s; p.inline_boot = 1; }
+    }
     return p;
 }
 
@@ -466,6 +603,7 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
     p.tile_stride = all_tiles / s;
     p.splits = s;                                   // one tile per job
     p.sample_mode = 1;                              // register top-8 per (query, tile)
+    p.inline_boot = 0;
     const int64_t jobs = (int64_t)p.m_tiles * p.splits;
     p.grid = (int)(jobs < num_sms ? jobs : num_sms);
     return p;
@@ -474,7 +612,7 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
-                             const float* thr0, cudaStream_t st) {
+                             const float* thr0, const InlineBoot* boot, cudaStream_t st) {
     auto kern = plan.pair ? gemm_topk_kernel<MODE_PAIR> : (plan.half ? gemm_topk_kernel<MODE_HALF> : gemm_topk_kernel<MODE_FULL>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
@@ -495,9 +633,14 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     const int k_blocks = d_pad / GEMM_BK;
     // streamed-once database tiles: evict-first measured 0.603 ms per pass against 0.642 ms with evict-normal / evict-last
     const uint64_t hint_db = HINT_EVICT_FIRST;
+    InlineBoot ib{};
+    if (plan.inline_boot) {
+        if (!boot || !boot->samp || !boot->arrive || !boot->thr_pub || plan.grid != plan.splits || plan.pair || plan.half) return cudaErrorInvalidValue;
+        ib = *boot; ib.on = 1;
+    }
     return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, k_blocks,
                               a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, plan.db_tiled, hint_db, eps, thr0,
-                              pool_items, pool_count, pool_thr);
+                              pool_items, pool_count, pool_thr, ib);
 }
 
 }  // namespace xs

@@ -24,6 +24,7 @@ constexpr int ST_UNCERTIFIED = 1;
 struct DevStats {                 // device-side database statistics (uint-ordered positive floats)
     unsigned int v4max_bits;      // max over rows of ||v||_4
     unsigned int vnmax_bits;      // max over rows of ||v||_2
+    unsigned int rhomax_bits;     // max over rows of ||v' - bf16(v')||_2  (v' = rotated row): worst-case band
 };
 
 // ---- build.cu -----------------------------------------------------------------------------------
@@ -31,17 +32,16 @@ struct DevStats {                 // device-side database statistics (uint-order
 // column-major ([d][pitch], the reference's (D,N) layout); writes fp32 rows [rows][d_pad].
 void launch_layout_rows(const void* src_tile, int dtype, bool colmajor, int64_t pitch,
                         int64_t rows, int d, int d_pad, float* dst32, cudaStream_t st);
-// Optional L2 normalisation, bf16 copy, ||.||_4 / ||.||_2 maxima.  dst16 rows have pitch d_pad.
-void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm,
+// Optional L2 normalisation (in place), then the bf16 copy of the ROTATED row (build.cu: random rotation) and the
+// database statistics behind eps.  dst16 rows have pitch d_pad.
+void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm, bool rotate, uint32_t seed,
                         DevStats* stats, cudaStream_t st);
-// Query preparation: normalise (optional), fp32 + bf16 copies, per-query error band eps.
-void launch_prep_queries(float* q32, __nv_bfloat16* q16, int64_t nq, int d_pad, bool renorm,
-                         const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
-
-// One-kernel variant reading the caller's raw fp32 row-major queries (d == d_pad <= 2048, 16-byte aligned);
-// also zero-fills bf16 rows [nq, nq_pad).  Returns false (nothing launched) when the fast path does not apply.
-bool launch_prep_queries_fused(const float* raw, float* q32, __nv_bfloat16* q16, int64_t nq, int64_t nq_pad, int d, int d_pad,
-                               bool renorm, const DevStats* stats, float eps_sigmas, float* eps, cudaStream_t st);
+// Query preparation in one launch: raw (optional, fp32 row-major, pitch d) -> q32 [nq][d_pad] (normalised when asked),
+// q16 [nq_pad][d_pad] bf16 of the rotated queries (rows >= nq zero), q32r fp32 rotated queries (batch-1 scan), eps[q]
+// (eps_mode 0: statistical band, 1: worst-case band).  q16 / q32r may be null.
+void launch_prep_queries(const float* raw, int d, float* q32, __nv_bfloat16* q16, float* q32r, int64_t nq, int64_t nq_pad, int d_pad,
+                         bool renorm, bool rotate, uint32_t seed, const DevStats* stats, float eps_sigmas, int eps_mode, float* eps,
+                         cudaStream_t st);
 
 // AQE (Reranking.py:195-208): q_out[q] = normalise( sum_j ((kq-j)/kq)^w * db32[top_ids[q][j]] ), float64 inside.
 void launch_aqe_queries(const float* db32, const int64_t* top_ids, int64_t nq, int kq, double w, int64_t n, int d_pad,
@@ -79,6 +79,17 @@ struct GemmPlan {
     int pair;         // 1: cta_group::2 kernel, clusters of two CTAs, 256 x 256 tiles (needs the box-128 database map)
     int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)
     int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
+    int inline_boot;  // 1: one job per CTA; the first tile of every CTA is the threshold sample (no separate bootstrap launch)
+};
+// In-kernel threshold bootstrap of gemm_topk_kernel (plan.inline_boot): the CTAs meet once through these words.
+constexpr int BOOT_MAX_GRID = 160;        // CTAs (= sample lists per query) the selecting warp holds in registers
+struct InlineBoot {
+    int on;
+    float* samp;                  // [128 queries][grid][8] best scores of every CTA's first tile
+    uint32_t* arrive;             // CTA arrival counter (monotonic across launches)
+    uint32_t arrive_target;       // counter value once every CTA of THIS launch has arrived
+    uint64_t* thr_pub;            // [128] (epoch << 32 | threshold bits), written by the CTA that owns the query
+    uint32_t epoch;               // distinguishes this launch's thresholds from the previous launch's
 };
 GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits, bool allow_pair);
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k);
@@ -86,9 +97,21 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k);
 cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
-                             const float* thr0, cudaStream_t st);
+                             const float* thr0, const InlineBoot* boot, cudaStream_t st);
 
 // ---- finalise.cu --------------------------------------------------------------------------------
+constexpr int XCHG_MAX_WORLD = 16;
+// Peer exchange, sending end fused into the emit step: the K results of a query go straight into every rank's mailbox
+// (NVLink peer mappings; g == this rank is the local mailbox) and the query's arrival flag is released per rank.
+struct PushTarget {
+    int world;                           // 0: off
+    int64_t* ids[XCHG_MAX_WORLD];        // rank g's mailbox part for (slot, this rank): ids [nq][k]
+    float* scores[XCHG_MAX_WORLD];       //   scores [nq][k]
+    int32_t* status[XCHG_MAX_WORLD];     //   certificate bits [nq]
+    uint32_t* flags[XCHG_MAX_WORLD];     // rank g's per-query arrival flags for (slot, this rank)
+    const uint32_t* my_acks;             // local acknowledgement words of this slot, one per receiving rank
+    uint32_t epoch;
+};
 struct FinaliseArgs {
     const uint64_t* pool_items; const int* pool_count; const uint32_t* pool_thr;
     int P, cap;
@@ -97,36 +120,42 @@ struct FinaliseArgs {
     int k; bool exact;          // exact: pool scores are already fp32-exact -> no rescoring
     int64_t id_offset;
     int64_t self_base;          // >= 0: query q is database row self_base + q and must rank first
-    int64_t* out_idx; float* out_score; int* status; int* n_cand;
+    int64_t* out_idx; float* out_score; int* status; int* n_cand;   // out_idx / out_score / status may be null when push is on
     int64_t out_pitch;          // elements between consecutive queries in out_idx / out_score
-    void* work;                 // optional: finalise_work_bytes(nq, k) of scratch -> enables the 3-kernel split for small batches
-    int* ticket;                // [nq] zero-initialised completion counters (self-resetting), required for the split
+    void* work;                 // finalise_work_bytes(nq, k, cand_max) of scratch for the multi-CTA-per-query forms
+    int* ticket;                // [3 * nq] zero-initialised words (completion tickets, candidate counters, flags; self-resetting)
+    int cand_max;               // candidates per query that can be rescored (power of two); 0 = default for k
     uint64_t* w_cand; int* w_ncand; int* w_flag; int* w_ticket;   // carved out by launch_finalise
+    PushTarget push;
 };
-int  finalise_cand_max(int k);
-size_t finalise_work_bytes(int64_t nq, int k);
+int  finalise_cand_max(int k, int mode);                  // mode 0: statistical band, 1: worst-case band (more candidates)
+size_t finalise_work_bytes(int64_t nq, int k, int cand_max);
 int  finalise_launches(const FinaliseArgs& a, int64_t nq);
 void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);
 // thr0[q] = (k-th best pooled coarse score) - 2 eps[q], one ulp lower; -inf when fewer than k items.
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st);
 // Multi-GPU merge of [parts][nq][k] lists.
-constexpr int XCHG_MAX_WORLD = 16;
 struct MergeSync {                       // receiving end of the peer exchange (all zero = plain merge)
-    const uint32_t* flags;               // local arrival flags of this slot, one per sending rank
+    const uint32_t* flags;               // local per-query arrival flags of this slot: flags[g * flag_stride + q]
+    int64_t flag_stride;
     uint32_t epoch;
     uint32_t* ticket;                    // local CTA counter of this slot
     uint32_t* ack[XCHG_MAX_WORLD];       // rank g's acknowledgement word for (slot, this rank)
 };
-struct PushArgs {                        // sending end
+struct PushArgs {                        // sending end as a kernel of its own (whole packed payload)
     void* dst[XCHG_MAX_WORLD];           // rank g's mailbox part for (slot, this rank)
-    uint32_t* flag[XCHG_MAX_WORLD];      // rank g's arrival flag for (slot, this rank)
+    uint32_t* flag[XCHG_MAX_WORLD];      // rank g's per-query arrival flags for (slot, this rank)
     const uint32_t* my_acks;             // local acknowledgement words of this slot, one per receiving rank
     uint32_t* tickets;                   // local CTA counters of this slot, one per receiving rank (large payloads)
     uint32_t epoch;
+    int64_t nq;                          // flags [0, nq) are released
 };
-void launch_merge_parts(const void* in_idx, const void* in_score, int64_t idx_stride_bytes, int64_t score_stride_bytes, int parts, int64_t nq, int k,
-                        int64_t* out_idx, float* out_score, cudaStream_t st, const MergeSync* sync = nullptr);
+// part p: ids at in_idx + p*idx_stride BYTES, scores at in_score + p*score_stride BYTES, optional certificate bits at
+// in_status + p*status_stride BYTES; out_status[q] = OR over the parts.
+void launch_merge_parts(const void* in_idx, const void* in_score, const void* in_status, int64_t idx_stride_bytes, int64_t score_stride_bytes,
+                        int64_t status_stride_bytes, int parts, int64_t nq, int k,
+                        int64_t* out_idx, float* out_score, int32_t* out_status, cudaStream_t st, const MergeSync* sync = nullptr);
 void launch_exchange_push(const void* src, int64_t bytes, const PushArgs& a, int world, cudaStream_t st);
 // ---- sort.cu ------------------------------------------------------------------------------------
 // Full ranking (K == N): stable segmented radix sort of c exact score rows; writes columns q0..q0+c of

@@ -109,6 +109,12 @@ class ExactIndex:
                                           C.c_void_p(status_ptr) if status_ptr else None,
                                           C.c_void_p(stream) if stream else None), "xs_search_dev")
 
+    def search_device_push(self, q_ptr: int, nq: int, k: int, exchange_handle, slot: int, stream: int = 0, renormalise: bool = False):
+        """Device search whose last kernel stores the results into every rank's peer-exchange mailbox
+        (xs_search_dev_push); collect them with ``PeerExchange.merge``."""
+        nat.check(self._lib.xs_search_dev_push(self._h, C.c_void_p(q_ptr), int(nq), int(bool(renormalise)), int(k),
+                                               exchange_handle, int(slot), C.c_void_p(stream) if stream else None), "xs_search_dev_push")
+
     def self_knn(self, k: int, begin: int = 0, end: int | None = None):
         """Top-k neighbours of database rows ``[begin, end)`` among all rows; a row's own id is
         first (src/utils/diffusion.py:67,108).  Returns ``(sims, ids)`` like ``KNN.search``."""

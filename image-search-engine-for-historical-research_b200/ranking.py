@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .nnsearch import cached_index
+from .nnsearch import leased_index
 
 
 def rank_ip(vecs, qvecs, K=None, return_scores=False, index=None):
@@ -19,7 +19,10 @@ def rank_ip(vecs, qvecs, K=None, return_scores=False, index=None):
     which is all that ``compute_map`` on truncated ranks or the web UI (online.py:152) reads.
     With ``return_scores`` also returns the matching fp32 scores, same shape.
     """
-    ix = index if index is not None else cached_index(np.asarray(vecs).T, renormalise=False)
+    if index is None:
+        with leased_index(np.asarray(vecs).T, renormalise=False) as ix:
+            return rank_ip(vecs, qvecs, K=K, return_scores=return_scores, index=ix)
+    ix = index
     q = np.asarray(qvecs).T
     if K is None or K >= ix.N or K > 4096:
         out = ix.rank_all(q, return_scores=return_scores)

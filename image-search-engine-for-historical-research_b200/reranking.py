@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 
 from .index import ExactIndex
-from .nnsearch import cached_index, matching_L2
+from .nnsearch import leased_index, matching_L2_once
 
 
 def feature_enhancement(it_times, k, ranks, qvecs, vecs, w, K=None, index=None):
@@ -28,7 +28,10 @@ def feature_enhancement(it_times, k, ranks, qvecs, vecs, w, K=None, index=None):
     first K rows.  As in the reference, ``ranks`` is not fed back between iterations (:196-207 never
     reassign it), so every iteration yields the same result and one pass is computed.
     """
-    ix = index if index is not None else cached_index(np.asarray(vecs).T, renormalise=False)
+    if index is None:
+        with leased_index(np.asarray(vecs).T, renormalise=False) as ix:
+            return feature_enhancement(it_times, k, ranks, qvecs, vecs, w, K=K, index=ix)
+    ix = index
     top = np.ascontiguousarray(np.asarray(ranks)[:k, :].T, dtype=np.int64)          # (Q, k), best first
     if K is None or K >= ix.N or K > 4096:
         _, _, qe = ix.aqe_search(top, 1, w=w, return_queries=True)
@@ -86,7 +89,7 @@ def average_query_expansion(qvecs, vecs, K, dataset=None, gnd=None, top_k=3, dev
     q_aug = np.concatenate([q, np.mean(v[ids, :], axis=1)], axis=1)
     ids = _nearest_rows(v, v, top_k + 1, device)
     v_aug = np.concatenate([v, np.mean(v[ids[:, 1:top_k + 1], :], axis=1)], axis=1)
-    match_idx, _ = matching_L2(K, v_aug, q_aug)
+    match_idx, _ = matching_L2_once(K, v_aug, q_aug, device)      # a one-off database: not worth a cache slot
     return match_idx.T
 
 
@@ -100,7 +103,7 @@ def database_augmentation(qvecs, vecs, K, dataset=None, gnd=None, top_k=3, devic
     q_aug = np.tensordot(weights, np.concatenate([np.expand_dims(q, 1), v[ids, :]], axis=1), axes=(0, 1))
     ids = _nearest_rows(v, v, top_k + 1, device)
     v_aug = np.tensordot(weights, v[ids, :], axes=(0, 1))
-    match_idx, _ = matching_L2(K, v_aug, q_aug)
+    match_idx, _ = matching_L2_once(K, v_aug, q_aug, device)
     return match_idx.T
 
 

@@ -45,7 +45,7 @@ enum { XS_F32 = 0, XS_F64 = 1 };
 typedef struct xs_stats {
     int64_t n_queries;       /* queries in the last call                                          */
     int64_t n_exact_rerun;   /* queries whose bf16 candidate set could not be certified and were   */
-                             /* re-run on the exact fp32 path (never a silent miss)               */
+                             /* re-run on the exact fp32 path                                     */
     int64_t n_candidates;    /* total candidates rescored in fp32 (sum over queries)              */
     int32_t path;            /* 1 = batch-1 HBM scan, 2 = tcgen05 GEMM + fused top-K, 3 = exact   */
     int32_t gpu_launches;    /* kernels launched by the last call                                 */
@@ -59,6 +59,15 @@ XS_API const char* xs_last_error(void);
 XS_API int xs_abi_version(void);
 /* Number of visible CUDA devices (0 and XS_ERR_CUDA if the driver is absent). */
 XS_API int xs_device_count(int* count);
+/*
+ * Process-wide defaults picked up by xs_index_create* (no reference counterpart):
+ *   "rotation"       1 (default) / 0: apply the seeded random rotation (sign flips + Walsh-Hadamard, twice) to rows
+ *                    and queries before they are rounded to bf16, so the rounding errors cannot line up with
+ *                    structure in the data (the exact stage always uses the unrotated fp32 values)
+ *   "rotation_seed"  the 32-bit seed of that rotation; results never depend on it, only which inputs could defeat
+ *                    the statistical certificate does
+ */
+XS_API int xs_config_set(const char* name, double value);
 
 /*
  * Build a device-resident index from a HOST matrix of n rows x d columns.
@@ -72,7 +81,8 @@ XS_API int xs_device_count(int* count);
  * renormalise  1: divide every row by its L2 norm first (matching_L2 semantics, :693-697);
  *              0: use rows as given (KNN / np.dot semantics).
  * id_offset    added to every returned id (row-sharding across GPUs: shard g passes its first row).
- * Device layout: bf16 row-major copy (coarse scoring) + fp32 row-major copy (exact rescoring).
+ * Device layout: bf16 copies of the (rotated) rows for coarse scoring + fp32 row-major copy (exact rescoring).
+ * d <= 4096 (XS_ERR_UNSUPPORTED beyond: the rescoring kernels stage whole rows in shared memory).
  */
 XS_API int xs_index_create(const void* db, int dtype, int64_t n, int d,
                     int64_t stride_row, int64_t stride_col,
@@ -115,8 +125,9 @@ XS_API int xs_search(xs_index* index, const void* q, int dtype, int64_t nq,
 /*
  * Same with DEVICE buffers on the index's device, enqueued on `stream` (a cudaStream_t).
  * q_dev is fp32 row-major [nq, d].  out_status_dev (may be NULL) receives one int32 per query:
- * 0 = certified by the bf16 coarse pass, 1 = needs the exact path.  With out_status_dev == NULL
- * the call synchronises the stream once to re-run uncertified queries itself.
+ * 0 = certified by the bf16 coarse pass, 1 = needs the exact path -- the CALLER must then re-run those
+ * queries (xs_set_param "force_path" 3) before using them.  With out_status_dev == NULL the call
+ * synchronises the stream once and re-runs uncertified queries itself.
  */
 XS_API int xs_search_dev(xs_index* index, const float* q_dev, int64_t nq, int renormalise_q, int k,
                   int64_t* out_idx_dev, float* out_score_dev, int32_t* out_status_dev,
@@ -161,35 +172,45 @@ XS_API int xs_merge_candidates(int device, const int64_t* in_idx, const float* i
                         int64_t* out_idx, float* out_score, void* stream);
 
 /*
- * Same merge for lists that were gathered as ONE packed buffer per rank ([ids | scores] bytes back to
- * back): part p's ids start idx_part_stride BYTES after part p-1's, its scores score_part_stride bytes.
+ * Same merge for lists that were gathered as ONE packed buffer per rank (ids | scores | certificate bits back to
+ * back): part p's ids start idx_part_stride BYTES after part p-1's, its scores score_part_stride bytes, its
+ * certificate words (int32 per query, may be NULL) status_part_stride bytes.  out_status_dev (may be NULL)
+ * receives the OR over the parts: a merged query is certified only if every shard certified its list.
  */
-XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const void* in_score, int64_t idx_part_stride,
-                                       int64_t score_part_stride, int n_parts, int64_t nq, int k,
-                                       int64_t* out_idx, float* out_score, void* stream);
+XS_API int xs_merge_candidates_strided(int device, const void* in_idx, const void* in_score, const void* in_status,
+                                       int64_t idx_part_stride, int64_t score_part_stride, int64_t status_part_stride,
+                                       int n_parts, int64_t nq, int k,
+                                       int64_t* out_idx, float* out_score, int32_t* out_status_dev, void* stream);
 
 /*
  * Peer exchange: the all-gather + merge of the row-sharded search without a collective library on the data
- * path.  Every rank owns a mailbox in its own HBM, exported through CUDA IPC; after its local search a rank
- * PUSHES its packed result ([ids int64 nq*k | scores f32 nq*k], what xs_search_dev wrote) into every rank's
- * mailbox with plain stores over the NVLink peer mappings and releases an arrival flag; the MERGE kernel of
- * each rank waits for the world's flags, merges, and acknowledges the slot so that it can be overwritten.
+ * path.  Every rank owns a mailbox in its own HBM, exported through CUDA IPC.  The SENDING end is fused into the
+ * search: xs_search_dev_push runs the local search and its last kernel stores every query's k results (ids,
+ * scores, certificate word) straight into all ranks' mailboxes with plain stores over the NVLink peer mappings,
+ * then releases that query's arrival flag on every rank.  The MERGE kernel of each rank waits per query for the
+ * world's flags, merges, and acknowledges the slot so that it can be overwritten.  xs_exchange_push is the
+ * sending end as a kernel of its own, for a packed result produced elsewhere (xs_search_dev into a buffer of
+ * xs_exchange_part_bytes(nq, k) bytes laid out  ids int64 [nq*k] | scores f32 [nq*k] | status int32 [nq]).
  * One process per GPU; the 64-byte handles travel through whatever channel the host processes share.
  * (No reference counterpart: the reference is single-process.  Replaces ncclAllGather + xs_merge_candidates
- * of SURVEY.md section 8e on the latency path.)
+ * of SURVEY.md section 8e.)
  *
- * Protocol: every rank calls push(slot) / merge(slot) in the same order; slots 0 and 1 alternate, and the
- * merge of a slot must be enqueued before the next push into the same slot (at most two searches in flight).
- * A peer that never arrives traps the waiting kernel after ~20 s instead of hanging the GPU.
- * xs_exchange_destroy synchronises the device; the caller must barrier across ranks before calling it.
+ * Protocol: every rank calls search_dev_push|push(slot) / merge(slot) in the same order; slots 0 and 1 alternate,
+ * and the merge of a slot must be enqueued before the next push into the same slot (at most two searches in
+ * flight).  Enqueue the merge on the stream of the push (or behind it): then the only thing a merge kernel ever
+ * waits for is another GPU.  A peer that never arrives traps the waiting kernel after ~20 s instead of hanging
+ * the GPU.  xs_exchange_destroy synchronises the device; the caller must barrier across ranks before calling it.
  */
 typedef struct xs_exchange xs_exchange;
-XS_API int xs_exchange_create(int device, int world, int rank, int64_t part_bytes, xs_exchange** out,
+XS_API int64_t xs_exchange_part_bytes(int64_t nq, int k);
+XS_API int xs_exchange_create(int device, int world, int rank, int64_t max_queries, int k_max, xs_exchange** out,
                               unsigned char* handle_out /* 64 bytes */);
 XS_API int xs_exchange_connect(xs_exchange* ex, const unsigned char* handles /* world x 64 bytes, by rank */);
-XS_API int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t bytes, int slot, void* stream);
+XS_API int xs_search_dev_push(xs_index* index, const float* q_dev, int64_t nq, int renormalise_q, int k,
+                              xs_exchange* ex, int slot, void* stream);
+XS_API int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t nq, int k, int slot, void* stream);
 XS_API int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64_t* out_idx_dev, float* out_score_dev,
-                             void* stream);
+                             int32_t* out_status_dev, void* stream);
 XS_API int xs_exchange_destroy(xs_exchange* ex);
 
 /*
@@ -218,6 +239,11 @@ XS_API int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* ind
 /*
  * Tunables (set before searching; all have safe defaults):
  *   "eps_sigmas"   float  width of the bf16 error band in standard deviations      (8.0)
+ *   "certificate"  int    0 = statistical band: eps_sigmas standard deviations of the bf16 rounding error, made
+ *                             data-independent by the random rotation, plus a model check on every rescored
+ *                             candidate; 1 = worst-case band from stored residual norms (Cauchy-Schwarz, no
+ *                             assumption; about 3x the rescored candidates)                                 (0)
+ *   "inline_boot"  int    1 = batches <= 128 queries bootstrap their score threshold inside the GEMM launch  (1)
  *   "scan_max_q"   int    largest batch served by the batch-1 HBM scan kernel      (1)
  *   "force_path"   int    0 = auto, 1 = scan, 2 = tcgen05 GEMM, 3 = exact fp32      (0)
  *   "gemm_splits"  int    database splits per query tile, 0 = auto                 (0)

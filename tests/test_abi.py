@@ -24,7 +24,7 @@ def test_header_and_library_agree(nat):
     lib = nat.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.xs_abi_version() == 1
+    assert lib.xs_abi_version() == 2
 
 
 def test_ctypes_signatures_match_the_header(nat):

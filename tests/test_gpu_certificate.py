@@ -1,0 +1,155 @@
+"""Inputs built to break the bf16 coarse filter's certificate.
+
+The coarse pass rounds rows and queries to bf16 and keeps every row within 2*eps of the K-th coarse score; eps is a
+multiple of the standard deviation of the rounding error under an independence assumption.  Structured data breaks
+independence when the rounding errors of many coordinates line up: constant components, low-entropy mantissas, rows
+that are copies of the query, and -- the sharpest case -- rows constructed against a known query so that every one of
+their rounding errors pushes the coarse score the same way.  The product's answer is (1) a seeded random rotation
+before the rounding, which makes the assumption hold for any data that was not built against the seed, (2) a model
+check on every rescored candidate, (3) an opt-in worst-case band ("certificate" = 1) that assumes nothing.
+
+Required outcome for every family, K = 1 and K = 100, on every coarse path: index lists identical to the oracle
+(or an exact re-run, which is how "identical" is reached when the certificate is refused).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).bfloat16().float().numpy()
+
+
+def _quantise(x, bits):
+    """Keep `bits` explicit mantissa bits (round to nearest): every value is exactly representable in bf16 for bits <= 7."""
+    m, e = np.frexp(x.astype(np.float64))
+    s = 2.0 ** (bits + 1)
+    return np.ldexp(np.round(m * s) / s, e).astype(np.float32)
+
+
+def _unit(x):
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+def _check(pkg, oracle, rows, queries, ks=(1, 100), paths=(0, 2, 1), certificate=0, tag=""):
+    """rows [N, D], queries [Q, D] used as given (np.dot semantics).  Returns total exact re-runs."""
+    vecs, qvecs = np.ascontiguousarray(rows.T), np.ascontiguousarray(queries.T)
+    s64 = oracle.scores_f64(vecs, qvecs)
+    reruns = 0
+    with pkg.ExactIndex(rows) as ix:
+        ix.set_param("certificate", certificate)
+        for k in ks:
+            ref_i, ref_s = oracle.topk_ip(vecs, qvecs, k)
+            for path in paths:
+                ix.set_param("force_path", path)
+                ids, sims = ix.search(queries, k)
+                reruns += ix.stats()["n_exact_rerun"]
+                for j in range(queries.shape[0]):
+                    ok, msg = oracle.compare_topk(ids[j], ref_i[j], lambda i, j=j: s64[i, j])
+                    assert ok, f"{tag} k={k} path={path} certificate={certificate} query {j}: {msg}"
+                np.testing.assert_allclose(sims, ref_s, rtol=1e-5, atol=1e-7)
+    return reruns
+
+
+def test_constant_component_rows_and_queries(pkg, oracle):
+    """Rows whose components are all equal round the same way in every coordinate: the coarse error of such a row is
+    ~2^-8 * score instead of a sum of independent terms.  Mixed with generic rows and near-copies at score ~1."""
+    rng = np.random.default_rng(11)
+    d, n = 256, 12000
+    gen = _unit(rng.standard_normal((n, d)))
+    const = np.full((1, d), 1.0 / np.sqrt(d), np.float32)
+    # 400 near-constant rows: the constant vector plus perturbations from 1e-7 to 1e-2
+    scales = np.repeat(np.float32([1e-7, 1e-5, 1e-3, 1e-2]), 100)[:, None]
+    near = _unit(const + scales * rng.standard_normal((400, d)).astype(np.float32))
+    rows = np.concatenate([gen, near, const], axis=0)
+    rng.shuffle(rows, axis=0)
+    queries = np.concatenate([const, near[:3], near[150:153], near[399:400], gen[:4]], axis=0)
+    _check(pkg, oracle, rows, queries, tag="constant-component")
+
+
+def test_low_entropy_mantissas(pkg, oracle):
+    """Rows and queries quantised to 4 (and 2) mantissa bits: exactly representable in bf16, so their own rounding error
+    is zero and every candidate's error comes from the other operand alone -- no averaging over independent terms."""
+    rng = np.random.default_rng(12)
+    d, n = 256, 12000
+    base = _unit(rng.standard_normal((n, d)))
+    rows = np.concatenate([_quantise(base[: n // 2], 4), _quantise(base[n // 2: 3 * n // 4], 2), base[3 * n // 4:]], axis=0)
+    queries = np.concatenate([_quantise(base[:4] + 0.05 * rng.standard_normal((4, d)).astype(np.float32), 4),
+                              base[n - 4:] + np.float32(1e-3), _quantise(base[5000:5004], 2)], axis=0)
+    _check(pkg, oracle, rows, queries, tag="low-entropy")
+
+
+def test_copies_of_the_query_among_quantised_rows(pkg, oracle):
+    """Rows = query +- tiny perturbations (exact scores differ in the 6th..8th digit, far below the bf16 resolution)
+    mixed with bf16-exact rows: the top-K is decided entirely by the exact stage, and there are more near-ties than K."""
+    rng = np.random.default_rng(13)
+    d, n = 256, 8000
+    base = _unit(rng.standard_normal((n, d)))
+    q = _unit(rng.standard_normal((6, d)))
+    q[1] = 1.0 / np.sqrt(d)                                        # a constant-component query
+    q[2] = _quantise(q[2:3], 3)[0]                                 # a low-entropy query
+    copies = []
+    for j in range(6):
+        for scale in (1e-7, 1e-6, 1e-5, 1e-4):
+            copies.append(q[j] + np.float32(scale) * rng.standard_normal((40, d)).astype(np.float32))
+    rows = np.concatenate([_quantise(base, 4)] + copies, axis=0)
+    perm = rng.permutation(rows.shape[0])
+    _check(pkg, oracle, rows[perm], q, tag="query copies")
+
+
+def _conspiring(d=256, n_fill=6000, n_bad=160, seed=14):
+    """One query, all components 2^-4 (unit norm at d = 256, exact in bf16).  `bad` rows are exact in bf16 and score
+    1 + m 2^-15 (m components one bf16 ulp up), coarse == exact.  The `good` row has every component just under half
+    an ulp above 2^-4: it rounds DOWN to the query (coarse 1.0) while its exact score 1 + 0.98 * 2^-8 beats every bad
+    row.  Without the rotation the coarse pass sees >= K bad rows 2.5e-3 above the good one -- outside any band
+    derived from independent rounding errors -- and the candidates it does rescore show zero error."""
+    assert d == 256
+    rng = np.random.default_rng(seed)
+    c = np.float32(2.0 ** -4)
+    q = np.full((1, d), c, np.float32)
+    ulp = np.float32(2.0 ** -11)
+    bad = np.full((n_bad, d), c, np.float32)
+    for i in range(n_bad):
+        m = 82 + (i % 9)
+        bad[i, rng.choice(d, size=m, replace=False)] += ulp
+    good = np.full((1, d), c * np.float32(1.0 + 0.98 * 2.0 ** -8), np.float32)
+    assert np.array_equal(_bf16_round(good), q) and np.array_equal(_bf16_round(bad), bad)
+    fill = _unit(rng.standard_normal((n_fill, d)))
+    rows = np.concatenate([fill[: n_fill // 2], bad[: n_bad // 2], good, bad[n_bad // 2:], fill[n_fill // 2:]], axis=0)
+    return rows, q, n_fill // 2 + n_bad // 2
+
+
+def test_rows_built_against_the_query(pkg, oracle):
+    """The sharpest family (see _conspiring).  Default configuration: the random rotation decorrelates the rounding
+    errors from the construction and the lists are identical to the oracle's.  Rotation off: the worst-case band
+    (certificate = 1) still gets it right, because it assumes nothing about the errors."""
+    nat = importlib.import_module(pkg.__name__ + "._native")
+    rows, q, good_id = _conspiring()
+    ref1, _ = oracle.topk_ip(np.ascontiguousarray(rows.T), np.ascontiguousarray(q.T), 1)
+    assert ref1[0, 0] == good_id                                   # the construction does what it says
+    _check(pkg, oracle, rows, q, tag="conspiring rows, rotation on")
+    _check(pkg, oracle, rows, q, certificate=1, tag="conspiring rows, rotation on, worst-case band")
+    nat.config_set("rotation", 0)
+    try:
+        _check(pkg, oracle, rows, q, certificate=1, tag="conspiring rows, rotation OFF, worst-case band")
+        # for the record: without rotation the statistical band is defeated by this family (that is why rotation is on)
+        with pkg.ExactIndex(rows) as ix:
+            ix.set_param("force_path", 2)
+            ids, _ = ix.search(q, 1)
+            print(f"rotation off, statistical band: top-1 = {ids[0, 0]} (true {good_id}), reruns {ix.stats()['n_exact_rerun']}")
+    finally:
+        nat.config_set("rotation", 1)
+
+
+@pytest.mark.parametrize("certificate", [0, 1])
+def test_worst_case_band_on_the_plain_families(pkg, synth, oracle, certificate):
+    """Both certificates on ordinary data (Gaussian and non-negative rows), all paths; the worst-case band must not
+    fall back to the exact path there (its candidate buffers are sized for it)."""
+    for fam in ("G", "P"):
+        v, q = synth.gaussian(20000, 12, d=512, family=fam)
+        r = _check(pkg, oracle, np.ascontiguousarray(v.T), np.ascontiguousarray(q.T), ks=(1, 100), certificate=certificate, tag=f"family {fam}")
+        assert r == 0, f"family {fam} certificate {certificate}: {r} exact re-runs"

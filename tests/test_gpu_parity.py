@@ -181,11 +181,14 @@ def test_merge_kernel_matches_host_merge(pkg, synth, oracle):
     pb = sharded.packed_bytes(6, k)
     packed_all = torch.zeros((world * pb,), dtype=torch.uint8, device="cuda")
     for g in range(world):
-        gi, gs = sharded.unpack(packed_all[g * pb:(g + 1) * pb], 6, k)
+        gi, gs, gst = sharded.unpack(packed_all[g * pb:(g + 1) * pb], 6, k)
         gi.copy_(ids_all[g]); gs.copy_(sims_all[g])
-    pi, ps = cs.merge(packed_all, world, 6, k)
+        if g == 1:
+            gst[4] = 1                                  # shard 1 could not certify query 4
+    pi, ps, pst = cs.merge(packed_all, world, 6, k)
     torch.cuda.synchronize()
     assert torch.equal(pi, mi) and torch.equal(ps, ms)
+    assert pst.cpu().tolist() == [0, 0, 0, 0, 1, 0]    # the merged certificate word is the OR over the shards
     hi, hs = oracle.merge_parts(np.stack(ids_parts), np.stack(sims_parts), k)
     np.testing.assert_array_equal(mi.cpu().numpy(), hi)
     np.testing.assert_array_equal(ms.cpu().numpy(), hs)

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = "image-search-engine-for-historical-research_b200"
 
 
-def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
+def _worker(rank, world, port, n, nq, d, k, ties, out_dir, flag_queries=()):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -31,22 +31,35 @@ def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
     lo, hi = bounds[rank], bounds[rank + 1]
     shard = np.ascontiguousarray(vecs[:, lo:hi])
 
-    def local_search(queries, kk):
+    calls = {"coarse": 0, "exact": 0}
+
+    def local_search(queries, kk, exact=False):
+        """Stand-in for the CUDA shard: the oracle's exact answer.  To exercise the certificate plumbing, rank 1
+        claims it could NOT certify the queries listed in `flag_queries` and hands out a deliberately wrong list
+        for them (its worst rows) unless asked for the exact path."""
+        calls["exact" if exact else "coarse"] += 1
         ids, sims = oracle.topk_ip(shard, queries.numpy().T, min(kk, hi - lo))
         pad = kk - ids.shape[1]
         if pad:
             ids = np.concatenate([ids, -np.ones((ids.shape[0], pad), np.int64) - lo], axis=1)
             sims = np.concatenate([sims, np.full((sims.shape[0], pad), -np.inf, np.float32)], axis=1)
-        packed = torch.empty((sharded.packed_bytes(ids.shape[0], kk),), dtype=torch.uint8)
-        pi, ps = sharded.unpack(packed, ids.shape[0], kk)
-        pi.copy_(torch.from_numpy(ids + lo)); ps.copy_(torch.from_numpy(sims))
+        status = np.zeros(ids.shape[0], np.int32)
+        if not exact and rank == 1:
+            for j in flag_queries:
+                if j < ids.shape[0]:
+                    status[j] = 1
+                    sims[j] = -1.0                      # garbage the merge would otherwise rank last
+        packed = torch.zeros((sharded.packed_bytes(ids.shape[0], kk),), dtype=torch.uint8)
+        pi, ps, pst = sharded.unpack(packed, ids.shape[0], kk)
+        pi.copy_(torch.from_numpy(ids + lo)); ps.copy_(torch.from_numpy(sims)); pst.copy_(torch.from_numpy(status))
         return packed
 
     def merge(packed_all, world_, nq_, kk):
         parts = [sharded.unpack(packed_all[g * sharded.packed_bytes(nq_, kk):(g + 1) * sharded.packed_bytes(nq_, kk)], nq_, kk)
                  for g in range(world_)]
         i, s = oracle.merge_parts(np.stack([p[0].numpy() for p in parts]), np.stack([p[1].numpy() for p in parts]), kk)
-        return torch.from_numpy(i), torch.from_numpy(s)
+        st = np.bitwise_or.reduce(np.stack([p[2].numpy() for p in parts]), axis=0)
+        return torch.from_numpy(i), torch.from_numpy(s), torch.from_numpy(st)
 
     searcher = sharded.ShardedSearcher(local_search, merge)
     qt = torch.from_numpy(np.ascontiguousarray(qvecs.T))
@@ -58,13 +71,17 @@ def _worker(rank, world, port, n, nq, d, k, ties, out_dir):
     assert torch.equal(torch.flip(ids2, dims=[0]), ids) and torch.equal(torch.flip(sims2, dims=[0]), sims)
     ids_b, sims_b = searcher.search(qt, k)                # blocking form agrees
     assert torch.equal(ids_b, ids) and torch.equal(sims_b, sims)
+    if flag_queries:                                      # every rank re-ran the flagged queries, and only those
+        assert calls["exact"] == 3 and searcher.n_rerun == 3 * len([j for j in flag_queries if j < nq]), (calls, searcher.n_rerun)
+    else:
+        assert calls["exact"] == 0 and searcher.n_rerun == 0
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=ids.numpy(), sims=sims.numpy())
     dist.destroy_process_group()
 
 
-def _run(tmp_path, n, nq, d, k, ties=False, world=2):
+def _run(tmp_path, n, nq, d, k, ties=False, world=2, flag_queries=()):
     port = 29000 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, n, nq, d, k, ties, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, nq, d, k, ties, str(tmp_path), tuple(flag_queries)), nprocs=world, join=True)
     return [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
 
 
@@ -81,6 +98,18 @@ def test_two_rank_search_matches_unsharded(tmp_path, synth, oracle):
     vecs, qvecs = synth.gaussian(601, 5, d=48)
     ref_ids, ref_sims = oracle.topk_ip(vecs, qvecs, 9)
     for o in outs:                       # every rank ends up with the full answer
+        np.testing.assert_array_equal(o["ids"], ref_ids)
+        np.testing.assert_array_equal(o["sims"], ref_sims)
+
+
+def test_uncertified_queries_are_rerun_on_every_rank(tmp_path, synth, oracle):
+    """A shard that cannot certify a query says so in the status word that travels with its list; the merged word
+    is the OR over the shards, so every rank re-runs the same queries on the exact path (the sharded
+    search used to drop the certificate on the floor)."""
+    outs = _run(tmp_path, n=601, nq=5, d=48, k=9, flag_queries=(1, 3))
+    vecs, qvecs = synth.gaussian(601, 5, d=48)
+    ref_ids, ref_sims = oracle.topk_ip(vecs, qvecs, 9)
+    for o in outs:
         np.testing.assert_array_equal(o["ids"], ref_ids)
         np.testing.assert_array_equal(o["sims"], ref_sims)
 
@@ -122,13 +151,14 @@ def test_shard_bounds_and_packing_properties():
     @given(st.integers(1, 300), st.integers(1, 130))
     def packing(nq, k):
         nb = sharded.packed_bytes(nq, k)
-        assert nb % 16 == 0 and 0 <= nb - nq * k * 12 < 16
+        assert nb % 16 == 0 and 0 <= nb - nq * k * 12 - nq * 4 < 16
         buf = torch.zeros(nb, dtype=torch.uint8)
-        ids, sims = sharded.unpack(buf, nq, k)
+        ids, sims, status = sharded.unpack(buf, nq, k)
         ids.copy_(torch.arange(nq * k, dtype=torch.int64).view(nq, k))
         sims.fill_(1.5)
-        ids2, sims2 = sharded.unpack(buf, nq, k)                     # views of the same bytes
-        assert ids2[-1, -1].item() == nq * k - 1 and sims2[0, 0].item() == 1.5
+        status.fill_(7)
+        ids2, sims2, status2 = sharded.unpack(buf, nq, k)            # views of the same bytes
+        assert ids2[-1, -1].item() == nq * k - 1 and sims2[0, 0].item() == 1.5 and status2[-1].item() == 7 and status2.numel() == nq
     packing()
 
     @settings(max_examples=50, deadline=None)
