@@ -424,9 +424,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     dst[1] = make_float4(top[4], top[5], top[6], top[7]);
                 }
                 __threadfence();
-                const int n_warps_on = (int)((min(nq, (int64_t)GEMM_BM) + 31) >> 5);      // epilogue warps that hold queries (this branch)
+                // warps that hold queries are those with sub < n_warps_on (a query's tile row is sub * 32 + lane); only they get here
+                const int n_warps_on = (int)((min(nq, (int64_t)GEMM_BM) + 31) >> 5);
                 asm volatile("bar.sync 1, %0;" :: "r"(n_warps_on * 32) : "memory");
-                if (ew == 0) {
+                if (sub == 0) {                                  // the warp that holds queries 0..31 (TMEM sub-partition 0): always populated
                     if (lane == 0) {
                         __threadfence();
                         atomicAdd(boot.arrive, 1u);

@@ -382,3 +382,64 @@ def make_searcher(index, device: int, lanes: int = 1, exchange: "PeerExchange | 
                                local_push=shard.local_push if exchange is not None else None,
                                lane_stream=shard.lane_stream if lanes > 1 else None, check=check)
     return shard, searcher
+
+
+def self_knn_rowsharded(searcher: ShardedSearcher, rows_local, bounds, k: int, rank: int, group=None, block: int = 8192):
+    """The N x N self-kNN graph (``self.knn.search(self.features, n_trunc)``, src/utils/diffusion.py:67) over a database
+    that is ROW-SHARDED across the ranks -- the variant for databases beyond one GPU.
+
+    ``rows_local``: this rank's rows, fp32 ``[n_local, D]`` torch tensor on its device (what its index was built from);
+    ``bounds``: ``shard_bounds(N, world)``.  The owners take turns: a block of ``block`` query rows is broadcast from
+    its owner, every rank searches it against its own shard, the per-shard lists meet through ``searcher`` (peer
+    exchange or all-gather + merge) and the owner keeps the merged block.  Two blocks are in flight, so the exchange
+    of one overlaps the scan of the next.  Returns ``(sims [n_local, k], ids [n_local, k])`` for the LOCAL rows, a
+    row's own id first (diffusion.py:108 relies on it)."""
+    import torch
+    dist = searcher.dist
+    world = searcher.world
+    n_local = int(rows_local.shape[0])
+    dev = rows_local.device
+    out_i = torch.empty((n_local, k), dtype=torch.int64, device=dev)
+    out_s = torch.empty((n_local, k), dtype=torch.float32, device=dev)
+    bufs = [torch.empty((block, rows_local.shape[1]), dtype=torch.float32, device=dev) for _ in range(3)] if world > 1 else []
+    pending = []                                         # (handle, owner, b0, c)
+
+    def collect(entry):
+        h, owner, b0, c = entry
+        ids, sims = h.result()
+        if owner != rank:
+            return
+        lo = bounds[rank] + b0
+        own = torch.arange(lo, lo + c, device=dev, dtype=torch.int64)
+        ids, sims = ids.clone(), sims.clone()
+        wrong = torch.nonzero(ids[:, 0] != own).flatten()
+        if wrong.numel():                                # duplicated rows: an equal-score neighbour with a lower id came first
+            for r in wrong.tolist():
+                pos = torch.nonzero(ids[r] == own[r]).flatten()
+                p = int(pos[0]) if pos.numel() else k - 1
+                self_sim = sims[r, p] if pos.numel() else torch.dot(rows_local[b0 + r], rows_local[b0 + r])
+                ids[r, 1:p + 1] = ids[r, 0:p].clone()
+                sims[r, 1:p + 1] = sims[r, 0:p].clone()
+                ids[r, 0], sims[r, 0] = own[r], self_sim
+        out_i[b0:b0 + c] = ids
+        out_s[b0:b0 + c] = sims
+
+    step = 0
+    for owner in range(world):
+        n_o = bounds[owner + 1] - bounds[owner]
+        for b0 in range(0, n_o, block):
+            c = min(block, n_o - b0)
+            if world > 1:
+                blk = bufs[step % 3][:c]
+                if owner == rank:
+                    blk.copy_(rows_local[b0:b0 + c])
+                dist.broadcast(blk, src=owner if group is None else dist.get_global_rank(group, owner), group=group)
+            else:
+                blk = rows_local[b0:b0 + c]
+            if len(pending) == 2:                        # the buffer about to be reused two steps from now is free again
+                collect(pending.pop(0))
+            pending.append((searcher.search_async(blk, k), owner, b0, c))
+            step += 1
+    while pending:
+        collect(pending.pop(0))
+    return out_s, out_i

@@ -184,3 +184,54 @@ def test_shard_bounds_and_packing_properties():
             order = np.lexsort((flat_i, -flat_s))[:k]
             np.testing.assert_array_equal(a_i[j], flat_i[order])
     merge_is_order_independent()
+
+
+def _selfknn_worker(rank, world, port, n, d, k, block, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sharded = importlib.import_module(PKG + ".sharded")
+    synth = importlib.import_module(PKG + ".synth")
+    oracle = importlib.import_module("oracle.oracle")
+    vecs, _ = synth.ties(n, 1, d=d, n_distinct=n // 3)          # every row has two exact duplicates: the self-first rule matters
+    bounds = sharded.shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    shard = np.ascontiguousarray(vecs[:, lo:hi])
+
+    def local_search(queries, kk):
+        ids, sims = oracle.topk_ip(shard, queries.numpy().T, kk)
+        packed = torch.zeros((sharded.packed_bytes(ids.shape[0], kk),), dtype=torch.uint8)
+        pi, ps, _ = sharded.unpack(packed, ids.shape[0], kk)
+        pi.copy_(torch.from_numpy(ids + lo)); ps.copy_(torch.from_numpy(sims))
+        return packed
+
+    def merge(packed_all, world_, nq_, kk):
+        pb = sharded.packed_bytes(nq_, kk)
+        parts = [sharded.unpack(packed_all[g * pb:(g + 1) * pb], nq_, kk) for g in range(world_)]
+        i, s = oracle.merge_parts(np.stack([p[0].numpy() for p in parts]), np.stack([p[1].numpy() for p in parts]), kk)
+        return torch.from_numpy(i), torch.from_numpy(s), torch.zeros(nq_, dtype=torch.int32)
+
+    searcher = sharded.ShardedSearcher(local_search, merge)
+    rows_local = torch.from_numpy(np.ascontiguousarray(shard.T))
+    sims, ids = sharded.self_knn_rowsharded(searcher, rows_local, bounds, k, rank, block=block)
+    np.savez(os.path.join(out_dir, f"self{rank}.npz"), ids=ids.numpy(), sims=sims.numpy(), lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+def test_rowsharded_self_knn(tmp_path, synth, oracle):
+    """The N x N self-kNN over a row-sharded database: blocks of query rows broadcast by their owner, searched by every
+    shard, merged, kept by the owner; a row's own id first even among exact duplicates (diffusion.py:108)."""
+    n, d, k, world = 150, 24, 7, 2
+    port = 31000 + (os.getpid() % 2000)
+    mp.spawn(_selfknn_worker, args=(world, port, n, d, k, 32, str(tmp_path)), nprocs=world, join=True)
+    vecs, _ = synth.ties(n, 1, d=d, n_distinct=n // 3)
+    ref_s, ref_i = oracle.knn_search(np.ascontiguousarray(vecs.T), np.ascontiguousarray(vecs.T), k)
+    for r in range(world):
+        o = np.load(os.path.join(tmp_path, f"self{r}.npz"))
+        lo, hi = int(o["lo"]), int(o["hi"])
+        assert (o["ids"][:, 0] == np.arange(lo, hi)).all()
+        np.testing.assert_allclose(o["sims"], ref_s[lo:hi], rtol=1e-6, atol=1e-7)
+        # same neighbour SETS up to exact ties (the duplicates): compare by score multiset and by membership of non-tied ids
+        for j in range(hi - lo):
+            assert len(set(o["ids"][j].tolist())) == k
