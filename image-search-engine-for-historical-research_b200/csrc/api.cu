@@ -83,7 +83,7 @@ struct xs_index {
     int eps_mode = 0;                             // certificate: 0 = statistical band (8 sigma, random rotation, model check), 1 = worst-case band
     int inline_boot = 1;                          // small batches: threshold bootstrap inside the GEMM launch (0: separate sample pass)
     bool rotate = true; uint32_t rot_seed = 0;    // random rotation applied before bf16 rounding (fixed at build time)
-    uint32_t boot_arrived = 0, boot_epoch = 0;    // host mirrors of the in-kernel bootstrap's arrival counter / epoch
+    uint32_t boot_arrived = 0, boot_published = 0, boot_epoch = 0;    // host mirrors of the in-kernel bootstrap's counters / epoch
     int self_lanes = 1;                           // xs_self_knn: 2 = batches alternate between this index and an internal clone
                                                   // (measured: 1.03 s either way at 500k x 500k -- the loop is tensor/power bound)
     xs_index* self_lane = nullptr;                // that clone (created on first use, freed with the index)
@@ -572,13 +572,16 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 if (!ix->boot_sync.p) {
                     XS_TRY(ix->boot_sync.ensure(16 + GEMM_BM * sizeof(uint64_t)));
                     CU_TRY(cudaMemsetAsync(ix->boot_sync.p, 0, ix->boot_sync.cap, ix->cur));
-                    ix->boot_arrived = 0; ix->boot_epoch = 0;
+                    ix->boot_arrived = 0; ix->boot_published = 0; ix->boot_epoch = 0;
                 }
                 boot.samp = ix->boot_samp.as<float>();
                 boot.arrive = ix->boot_sync.as<uint32_t>();
                 boot.thr_pub = reinterpret_cast<uint64_t*>(static_cast<char*>(ix->boot_sync.p) + 16);
                 ix->boot_arrived += (uint32_t)plan.grid;
                 boot.arrive_target = ix->boot_arrived;
+                boot.published = ix->boot_sync.as<uint32_t>() + 1;
+                ix->boot_published += (uint32_t)c;
+                boot.published_target = ix->boot_published;
                 boot.epoch = ++ix->boot_epoch;
             }
             const int64_t slots = (int64_t)((plan.m_tiles + 1) & ~1) * plan.splits * GEMM_BM;

@@ -177,10 +177,15 @@ void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int 
 // zero rows [nq, nq_pad) of the bf16 copy (GEMM tile padding) and the per-query band eps.
 //
 // eps[q] bounds |coarse score - exact score| of query q against ANY database row.
-//   mode 0 (statistical, default): both operands are rounded to bf16 (unit roundoff u = 2^-9 relative to the binade
-//     centre); over a row the error is a sum of d independent zero-mean terms with standard deviation
-//     <= u sqrt(2/3) ||v'||_4 ||q'||_4 (primes: rotated vectors) -- independence is what the random rotation buys --
-//     and eps = sigmas * that + a small absolute term for fp32 accumulation and the rotation's own rounding.
+//   mode 0 (statistical, default): both operands are rounded to bf16.  The relative rounding error of one element is
+//     uniform in +-2^-8/m (m = its mantissa in [1,2)): standard deviation 2^-8 sqrt(E[1/m^2]/12) = 0.85 * 2^-9 for
+//     log-uniform mantissas.  A product v'_i q'_i carries the sum of two such errors -- independent for unrelated
+//     vectors, IDENTICAL when the row is a copy of the query -- so its standard deviation is at most 1.7 * 2^-9 |v'_i q'_i|,
+//     and over a row (independent across coordinates: that is what the random rotation buys)
+//         sigma <= 1.7 * 2^-9 * sqrt(sum (v'_i q'_i)^2) <= 1.7 * 2^-9 ||v'||_4 ||q'||_4      (Cauchy-Schwarz; primes = rotated).
+//     eps = sigmas * that + a small absolute term for fp32 accumulation and the rotation's own rounding.  For unrelated
+//     unit vectors the true sigma is ~3x smaller than the bound (the default 8 "sigmas" are ~24 of theirs); the bound is
+//     attained by near-duplicates of the query.
 //   mode 1 (worst case): |<v16,q16> - <v',q'>| <= rho_v ||q16|| + ||v'|| rho_q by Cauchy-Schwarz with the stored
 //     residual norms rho = ||x' - bf16(x')||, plus d_pad 2^-22 ||v|| ||q|| for ANY order of fp32 accumulation and
 //     1e-5 ||v|| ||q|| for the rotation arithmetic.  No assumption at all, ~3x the candidates.
@@ -221,7 +226,7 @@ prep_queries_kernel(const float* __restrict__ raw, int raw_pitch, int d, float* 
             const float q16n = (float)sqrt(r2) * 1.000001f, qrho = (float)sqrt(res2) * 1.000001f;
             e = vrho * q16n + vn * qrho + ((float)d_pad * 2.3841858e-7f + 1e-5f) * qn * vn;
         } else {
-            e = eps_sigmas * (1.0f / 512.0f) * 0.8165f * q4 * v4 + 2e-5f * qn * vn;
+            e = eps_sigmas * (1.0f / 512.0f) * 1.7f * q4 * v4 + 2e-5f * qn * vn;
         }
         eps[r] = e;
     }

@@ -481,19 +481,28 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                 // the main pass keeps scores strictly above the threshold: k-th best of the sample, minus the band
                                 t_pub = nextafterf(key_score(prefix) - 2.f * eps[qq], -INFINITY);
                             }
-                            if (lane == 0)
+                            if (lane == 0) {
                                 st_release_gpu_u64(boot.thr_pub + qq, ((uint64_t)boot.epoch << 32) | (uint64_t)__float_as_uint(t_pub));
+                                __threadfence();
+                                atomicAdd(boot.published, 1u);
+                            }
                         }
                     }
-                }
-                // (C)
-                if (active) {
-                    const long long w0 = clock64();
-                    uint64_t w;
-                    while ((uint32_t)((w = ld_acquire_gpu_u64(boot.thr_pub + q)) >> 32) != boot.epoch) {
-                        __nanosleep(40);
-                        if (clock64() - w0 > 8000000000ll) { printf("xs gemm_topk: bootstrap threshold timeout (block %d)\n", blockIdx.x); __trap(); }
+                    // (C) ONE thread per CTA waits until every query's threshold is out (ten thousand threads polling their
+                    // own words would swamp the L2 that the operand stream needs), the named barrier releases the rest
+                    if (lane == 0) {
+                        const long long w0 = clock64();
+                        while ((int32_t)(ld_acquire_gpu_u32(boot.published) - boot.published_target) < 0) {
+                            __nanosleep(100);
+                            if (clock64() - w0 > 8000000000ll) { printf("xs gemm_topk: bootstrap threshold timeout (block %d)\n", blockIdx.x); __trap(); }
+                        }
                     }
+                    __syncwarp();
+                }
+                asm volatile("bar.sync 1, %0;" :: "r"(n_warps_on * 32) : "memory");
+                if (active) {
+                    const uint64_t w = __ldcg(reinterpret_cast<const unsigned long long*>(boot.thr_pub + q));
+                    if ((uint32_t)(w >> 32) != boot.epoch) { printf("xs gemm_topk: stale bootstrap threshold (block %d)\n", blockIdx.x); __trap(); }
                     thr = __uint_as_float((uint32_t)w);
                 }
                 __syncwarp();

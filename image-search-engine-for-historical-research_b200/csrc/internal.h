@@ -88,6 +88,8 @@ struct InlineBoot {
     float* samp;                  // [128 queries][grid][8] best scores of every CTA's first tile
     uint32_t* arrive;             // CTA arrival counter (monotonic across launches)
     uint32_t arrive_target;       // counter value once every CTA of THIS launch has arrived
+    uint32_t* published;          // thresholds published so far (monotonic across launches)
+    uint32_t published_target;    // its value once every query of THIS launch has its threshold
     uint64_t* thr_pub;            // [128] (epoch << 32 | threshold bits), written by the CTA that owns the query
     uint32_t epoch;               // distinguishes this launch's thresholds from the previous launch's
 };

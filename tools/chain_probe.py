@@ -1,0 +1,51 @@
+"""Where the 70-query step goes: per-step device time and coarse-kernel time with the in-kernel threshold bootstrap on
+and off, at the full database and at the 8-GPU shard size.
+
+    python tools/chain_probe.py [steps]
+"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("image-search-engine-for-historical-research_b200")
+bench = importlib.import_module("bench")
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+dev = torch.device("cuda", 0)
+queries = bench.synth_rows_device(torch, 70, 2048, dev, 1)
+ids = torch.empty((70, 100), dtype=torch.int64, device=dev)
+sims = torch.empty((70, 100), dtype=torch.float32, device=dev)
+status = torch.zeros((70,), dtype=torch.int32, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for n in (1_007_000, 125_875):
+    rows = bench.synth_rows_device(torch, n, 2048, dev, 0)
+    ix = pkg.ExactIndex.from_device(rows.data_ptr(), n, 2048, 0)
+    for nq in (70, 1):
+        for inline in ((1, 0) if nq > 1 else (1,)):
+            ix.set_param("inline_boot", inline)
+            q = queries[:nq].contiguous()
+            for _ in range(20):
+                ix.search_device(q.data_ptr(), nq, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                ix.search_device(q.data_ptr(), nq, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            step_ms = e0.elapsed_time(e1) / steps
+            ix.set_param("timing", 1)
+            ks, ts = [], []
+            for _ in range(20):
+                ix.search_device(q.data_ptr(), nq, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+                st = ix.stats()
+                ks.append(st["ms_coarse"]); ts.append(st["ms_total"])
+            ix.set_param("timing", 0)
+            print(f"rows {n:8d} nq {nq:3d} inline_boot {inline}: step {step_ms*1e3:7.1f} us back to back; one call {sum(ts)/20*1e3:7.1f} us, coarse kernel {sum(ks)/20*1e3:7.1f} us, "
+                  f"launches {st['gpu_launches']}, candidates/query {st['n_candidates']/nq:.0f}, uncertified {int(status[:nq].sum())}", flush=True)
+    ix.close()
+    del rows
+    torch.cuda.empty_cache()
