@@ -636,9 +636,9 @@ finalise_fused_kernel(FinaliseArgs a, int cand_max, int item_cap) {
 // Candidates per query the rescoring stage can hold: the band of the statistical certificate is a few dozen rows wide
 // on top of k; the worst-case band (mode 1) is ~8x wider.
 int finalise_cand_max(int k, int mode) {
-    int m = 256;
+    int m = 512;
     while (m < 2 * k) m <<= 1;
-    if (mode == 1) m *= 4;
+    if (mode == 1) m *= 2;
     return m;
 }
 size_t finalise_work_bytes(int64_t nq, int k, int cand_max) {
