@@ -88,7 +88,8 @@ struct xs_index {
                                                   // (measured: 1.03 s either way at 500k x 500k -- the loop is tensor/power bound)
     xs_index* self_lane = nullptr;                // that clone (created on first use, freed with the index)
     // workspace
-    Buf boot_samp, boot_sync, q32r;
+    Buf boot_samp, boot_sync, boot_trace, q32r;
+    int boot_trace_on = 0, boot_trace_grid = 0;
     Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     PinnedBuf h_aqe;                              // pinned staging of xs_aqe_search's id lists
@@ -200,7 +201,7 @@ static void index_free(xs_index* ix) {
     if (ix->self_lane) { index_free(ix->self_lane); ix->self_lane = nullptr; }
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->q32r, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->boot_trace, &ix->q32r, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release(); ix->h_aqe.release();
     if (ix->share) {
@@ -384,8 +385,24 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "timing")) ix->timing = (int)value;
     else if (!strcmp(name, "certificate")) ix->eps_mode = ((int)value == 1) ? 1 : 0;
     else if (!strcmp(name, "inline_boot")) ix->inline_boot = (int)value != 0;
+    else if (!strcmp(name, "boot_trace")) ix->boot_trace_on = (int)value != 0;
     else if (!strcmp(name, "self_lanes")) ix->self_lanes = ((int)value >= 2) ? 2 : 1;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
+    return XS_OK;
+}
+
+// Debugging aid: the globaltimer stamps of the last bootstrap-inside-the-GEMM launch, [grid][8] nanoseconds
+// (0 job start, 1 first tile accumulated, 2 arrival posted, 3 all arrived (owners), 4 thresholds out, 5 first accumulator released, 6 job done).
+extern "C" int xs_debug_boot_trace(xs_index* ix, unsigned long long* out, int max_ctas, int* grid) {
+    if (!ix || !out || !grid) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *grid = 0;
+    if (!ix->boot_trace.p || !ix->boot_trace_grid) return XS_OK;
+    CU_TRY(cudaSetDevice(ix->device));
+    CU_TRY(cudaDeviceSynchronize());
+    const int g = ix->boot_trace_grid < max_ctas ? ix->boot_trace_grid : max_ctas;
+    CU_TRY(cudaMemcpy(out, ix->boot_trace.p, (size_t)g * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *grid = g;
     return XS_OK;
 }
 
@@ -583,6 +600,12 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 ix->boot_published += (uint32_t)c;
                 boot.published_target = ix->boot_published;
                 boot.epoch = ++ix->boot_epoch;
+                if (ix->boot_trace_on) {
+                    XS_TRY(ix->boot_trace.ensure((size_t)BOOT_MAX_GRID * 8 * sizeof(unsigned long long)));
+                    CU_TRY(cudaMemsetAsync(ix->boot_trace.p, 0, (size_t)BOOT_MAX_GRID * 8 * sizeof(unsigned long long), ix->cur));
+                    boot.trace = ix->boot_trace.as<unsigned long long>();
+                    ix->boot_trace_grid = plan.grid;
+                }
             }
             const int64_t slots = (int64_t)((plan.m_tiles + 1) & ~1) * plan.splits * GEMM_BM;
             XS_TRY(ix->pool_items.ensure((size_t)slots * plan.cap * 8));
@@ -1235,6 +1258,125 @@ extern "C" int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t*
     if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "xs_diffusion_cg: %s", cudaGetErrorString(e)); }
     if (bad) return fail(XS_ERR_ARG, "trunc_ids holds an id outside [0, n)");
+    return XS_OK;
+}
+
+// ---- diffusion graph + gallery-side solves, device resident (src/utils/diffusion.py:52-116) ---------------------------
+extern "C" int xs_diffusion_laplacian(int device, const float* sims, const int64_t* ids, int64_t n, int kd, double alpha, double gamma,
+                                      int32_t* out_cols, float* out_vals, int32_t* out_cnt, float* out_affinity) {
+    if (!sims || !ids || !out_cols || !out_vals || !out_cnt) return fail(XS_ERR_ARG, "null pointer");
+    if (n <= 0 || kd <= 0 || n > 0x7FFFFFFF) return fail(XS_ERR_ARG, "bad sizes (n=%lld, kd=%d)", (long long)n, kd);
+    CU_TRY(cudaSetDevice(device));
+    const size_t count = (size_t)n * kd;
+    DevMem d_ids64, d_ids32, d_sims, d_mut, d_aff, d_dinv, d_cols, d_vals, d_cnt;
+    cudaError_t e = d_ids64.alloc(count * 8);
+    if (e == cudaSuccess) e = d_ids32.alloc(count * 4);
+    if (e == cudaSuccess) e = d_sims.alloc(count * 4);
+    if (e == cudaSuccess) e = d_mut.alloc(count);
+    if (e == cudaSuccess) e = d_aff.alloc(count * 4);
+    if (e == cudaSuccess) e = d_dinv.alloc((size_t)n * 4);
+    if (e == cudaSuccess) e = d_cols.alloc(count * 4);
+    if (e == cudaSuccess) e = d_vals.alloc(count * 4);
+    if (e == cudaSuccess) e = d_cnt.alloc((size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ids64.p, ids, count * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_sims.p, sims, count * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_ids_to_i32(d_ids64.as<int64_t>(), d_ids32.as<int32_t>(), (int64_t)count, nullptr);
+        launch_diffusion_graph(d_ids32.as<int32_t>(), kd, d_sims.as<float>(), kd, n, kd, alpha, gamma, d_mut.as<uint8_t>(), d_aff.as<float>(),
+                               d_dinv.as<float>(), d_cols.as<int32_t>(), d_vals.as<float>(), d_cnt.as<int32_t>(), nullptr, nullptr);
+        e = cudaMemcpy(out_cols, d_cols.p, count * 4, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_vals, d_vals.p, count * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out_cnt, d_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_affinity) e = cudaMemcpy(out_affinity, d_aff.p, count * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "xs_diffusion_laplacian: %s", cudaGetErrorString(e)); }
+    return XS_OK;
+}
+
+// The whole gallery side without leaving the device: N x N self-kNN truncated at n_trunc -> mutual-kNN graph of the first
+// kd neighbours -> Laplacian -> one truncated CG per row.  The host receives only the final (ids, scores) arrays.
+extern "C" int xs_diffusion_offline(xs_index* ix, int n_trunc, int kd, double alpha, double gamma, int maxiter, double tol,
+                                    int64_t* out_ids, float* out_sims, float* out_scores) {
+    if (!ix) return fail(XS_ERR_ARG, "null index");
+    if (!out_ids || !out_scores) return fail(XS_ERR_ARG, "null pointer");
+    XS_TRY(check_search_args(ix, ix->n, n_trunc));
+    if (kd < 1 || kd > n_trunc) return fail(XS_ERR_ARG, "kd must be in [1, n_trunc] (got %d)", kd);
+    if (n_trunc > 4096 || ix->n > 0x7FFFFFFF) return fail(XS_ERR_ARG, "n_trunc <= 4096 and n < 2^31 required");
+    if (maxiter < 0 || !(tol >= 0.0)) return fail(XS_ERR_ARG, "bad maxiter/tol");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    ix->cur = ix->stream;
+    const int64_t n = ix->n;
+    const int T = n_trunc;
+    const int64_t batch = 8192;
+    DevMem d_ids32, d_sims, d_mut, d_aff, d_dinv, d_cols, d_vals, d_cnt, d_ptr, d_out, d_scols, d_svals, d_bad;
+    int grid = 0;
+    CU_TRY(diffusion_cg_grid(T, &grid));
+    const int stride = std::max(1, std::min(kd, T));
+    cudaError_t e = d_ids32.alloc((size_t)n * T * 4);
+    if (e == cudaSuccess) e = d_sims.alloc((size_t)n * T * 4);
+    if (e == cudaSuccess) e = d_mut.alloc((size_t)n * kd);
+    if (e == cudaSuccess) e = d_aff.alloc((size_t)n * kd * 4);
+    if (e == cudaSuccess) e = d_dinv.alloc((size_t)n * 4);
+    if (e == cudaSuccess) e = d_cols.alloc((size_t)n * kd * 4);
+    if (e == cudaSuccess) e = d_vals.alloc((size_t)n * kd * 4);
+    if (e == cudaSuccess) e = d_cnt.alloc((size_t)n * 4);
+    if (e == cudaSuccess) e = d_ptr.alloc((size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = d_out.alloc((size_t)n * T * 4);
+    if (e == cudaSuccess) e = d_scols.alloc((size_t)grid * T * stride * 2);
+    if (e == cudaSuccess) e = d_svals.alloc((size_t)grid * T * stride * 4);
+    if (e == cudaSuccess) e = d_bad.alloc(4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad.p, 0, 4, ix->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, "xs_diffusion_offline: %s", cudaGetErrorString(e)); }
+    // 1. self-kNN, batch by batch, results stay on the device (ids as local int32 for the graph kernels)
+    XS_TRY(ix->status.ensure((size_t)batch * sizeof(int)));
+    XS_TRY(ix->out_idx.ensure((size_t)batch * T * sizeof(int64_t)));
+    XS_TRY(ix->out_score.ensure((size_t)batch * T * sizeof(float)));
+    XS_TRY(ix->h_status.ensure((size_t)(batch + 1) * sizeof(int)));
+    xs_stats total{};
+    for (int64_t r0 = 0; r0 < n; r0 += batch) {
+        const int64_t c = (n - r0 < batch) ? n - r0 : batch;
+        CoreArgs a{};
+        a.q32 = ix->db32 + (size_t)r0 * ix->d_pad; a.nq = c; a.k = T; a.prep = true; a.prep_renorm = false;
+        a.path = choose_path(ix, c, T);
+        a.tmap_a = (a.path == PATH_GEMM) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
+        a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
+        XS_TRY(search_core(ix, a));
+        total.n_queries += c; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;
+        if (a.path != PATH_EXACT) {
+            int* hst = ix->h_status.as<int>();
+            CU_TRY(cudaMemcpyAsync(hst, a.status, (size_t)c * sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+            CU_TRY(cudaStreamSynchronize(ix->stream));
+            int launches = 0;
+            for (int64_t q = 0; q < c;) {
+                if (!(hst[q] & ST_UNCERTIFIED)) { ++q; continue; }
+                int64_t qe = q + 1;
+                while (qe < c && qe - q < 16 && (hst[qe] & ST_UNCERTIFIED)) ++qe;
+                XS_TRY(run_exact(ix, ix->db32 + (size_t)(r0 + q) * ix->d_pad, qe - q, T, r0 + q, a.out_idx + q * T, a.out_score + q * T, nullptr, &launches));
+                total.n_exact_rerun += qe - q;
+                q = qe;
+            }
+            total.gpu_launches += launches;
+        }
+        launch_ids_strided_to_i32(a.out_idx, T, d_ids32.as<int32_t>() + (size_t)r0 * T, T, c, T, ix->id_offset, ix->stream);
+        CU_TRY(cudaMemcpyAsync(d_sims.as<float>() + (size_t)r0 * T, a.out_score, (size_t)c * T * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+        CU_TRY(cudaMemcpyAsync(out_ids + (size_t)r0 * T, a.out_idx, (size_t)c * T * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+        if (out_sims) CU_TRY(cudaMemcpyAsync(out_sims + (size_t)r0 * T, a.out_score, (size_t)c * T * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+        CU_TRY(cudaStreamSynchronize(ix->stream));          // the batch buffers are reused
+    }
+    // 2. graph of the first kd neighbours, 3. CG per row -- consuming the lists where they are
+    launch_diffusion_graph(d_ids32.as<int32_t>(), T, d_sims.as<float>(), T, n, kd, alpha, gamma, d_mut.as<uint8_t>(), d_aff.as<float>(), d_dinv.as<float>(),
+                           d_cols.as<int32_t>(), d_vals.as<float>(), d_cnt.as<int32_t>(), d_ptr.as<int64_t>(), ix->stream);
+    e = launch_diffusion_cg(d_ptr.as<int64_t>(), d_cols.as<int32_t>(), d_vals.as<float>(), n, d_ids32.as<int32_t>(), n, T, stride, maxiter, tol,
+                            d_scols.as<uint16_t>(), d_svals.as<float>(), grid, d_out.as<float>(), d_bad.as<int>(), ix->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_out.p, (size_t)n * T * 4, cudaMemcpyDeviceToHost, ix->stream);
+    int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(XS_ERR_CUDA, "xs_diffusion_offline: %s", cudaGetErrorString(e)); }
+    if (bad) return fail(XS_ERR_CUDA, "xs_diffusion_offline: a neighbour id fell outside the database");
+    ix->stats = total;
+    ix->ev_valid = false;
     return XS_OK;
 }
 

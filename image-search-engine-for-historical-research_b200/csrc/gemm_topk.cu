@@ -148,6 +148,8 @@ __device__ __forceinline__ void st_release_gpu_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 constexpr int BOOT_PER_LANE = (BOOT_MAX_GRID * 8 + 31) / 32;      // sample scores per lane of the selecting warp
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define BOOT_STAMP(i) do { if (boot.trace && sub == 0 && lane == 0) boot.trace[(size_t)blockIdx.x * 8 + (i)] = globaltimer_ns(); } while (0)
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -398,8 +400,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 float top[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
+                BOOT_STAMP(0);                                   // job start
                 mbar_wait(smem_u32(&bars->tfull[0]), 0);
                 tc_fence_after();
+                BOOT_STAMP(1);                                   // first tile accumulated
                 {
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
 #pragma unroll 1
@@ -432,6 +436,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         __threadfence();
                         atomicAdd(boot.arrive, 1u);
                     }
+                    BOOT_STAMP(2);                               // sample written, arrival posted
                     if ((int64_t)blockIdx.x < nq) {
                         // (B) this CTA owns queries blockIdx.x, blockIdx.x + grid, ...
                         if (lane == 0) {
@@ -442,6 +447,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             }
                         }
                         __syncwarp();
+                        BOOT_STAMP(3);                           // (owners) every CTA has arrived
                         const int n_samp = (int)gridDim.x * 8;
                         for (int64_t qq = blockIdx.x; qq < nq; qq += gridDim.x) {
                             const float* src = boot.samp + (size_t)qq * gridDim.x * 8;
@@ -498,6 +504,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         }
                     }
                     __syncwarp();
+                    BOOT_STAMP(4);                               // every threshold is out
                 }
                 asm volatile("bar.sync 1, %0;" :: "r"(n_warps_on * 32) : "memory");
                 if (active) {
@@ -508,6 +515,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 __syncwarp();
                 filter_tile(0u, t0);
                 release_acc(0u);
+                BOOT_STAMP(5);                                   // first accumulator handed back
                 t_first = t0 + 1;
                 it = 1;
             }
@@ -535,6 +543,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             pool_count[slot] = cnt;
             pool_thr[slot] = thr_rec;
+            if (boot.on) BOOT_STAMP(6);                          // job done
         }
     }
     tc_fence_before();

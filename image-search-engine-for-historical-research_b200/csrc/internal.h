@@ -92,6 +92,7 @@ struct InlineBoot {
     uint32_t published_target;    // its value once every query of THIS launch has its threshold
     uint64_t* thr_pub;            // [128] (epoch << 32 | threshold bits), written by the CTA that owns the query
     uint32_t epoch;               // distinguishes this launch's thresholds from the previous launch's
+    unsigned long long* trace;    // optional [grid][8] globaltimer stamps (debugging: xs_set_param "boot_trace")
 };
 GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits, bool allow_pair);
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k);
@@ -170,6 +171,13 @@ void launch_rank_all(const float* scores, int64_t pitch, int c, int64_t n, int q
 // mutual[i][j] = 1 iff j >= 1 and i is among the kd neighbours of ids[i][j]  (diffusion.py:107-108)
 void launch_mutual_knn(const int64_t* ids64, int32_t* ids32_scratch, int64_t n, int kd, uint8_t* mutual, cudaStream_t st);
 void launch_ids_to_i32(const int64_t* ids64, int32_t* ids32, int64_t count, cudaStream_t st);
+
+// Diffusion graph on the device (diffusion.py:87-116): mutual test on the first kd columns of ids32 [n][id_pitch], affinity
+// max(sim,0)^gamma, degrees, and the Laplacian I - alpha D^-1/2 A D^-1/2 in ELL form (kd slots per row, diagonal first,
+// padding column INT32_MIN); indptr (optional) = i * kd so that the ELL arrays read as CSR for the CG kernel.
+void launch_diffusion_graph(const int32_t* ids32, int64_t id_pitch, const float* sims, int64_t sim_pitch, int64_t n, int kd, double alpha, double gamma,
+                            uint8_t* mutual, float* aff, float* dinv, int32_t* cols, float* vals, int32_t* cnt, int64_t* indptr, cudaStream_t st);
+void launch_ids_strided_to_i32(const int64_t* in, int64_t in_pitch, int32_t* out, int64_t out_pitch, int64_t rows, int cols, int64_t sub, cudaStream_t st);
 
 // diffusion.cu -- truncated CG solves (one CTA per database row)
 cudaError_t diffusion_cg_grid(int T, int* grid_out);

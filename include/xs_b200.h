@@ -222,6 +222,29 @@ XS_API int xs_exchange_destroy(xs_exchange* ex);
 XS_API int xs_mutual_knn(int device, const int64_t* ids, int64_t n, int kd, uint8_t* out_mutual);
 
 /*
+ * Diffusion graph on the device: mutual-kNN affinity and the normalised Laplacian from kNN lists.
+ *   replaces: Diffusion.get_affinity + get_laplacian (scipy on the host)              src/utils/diffusion.py:87-116
+ * sims / ids: HOST [n, kd] (slot 0 = the row itself, as xs_self_knn returns them; sims are not modified).
+ * A[i, ids[i][j]] = max(sims[i][j], 0)^gamma for mutual slots j >= 1; L = I - alpha D^-1/2 A D^-1/2 with float32
+ * entries computed in the reference's order.  Outputs (HOST, ELL form): out_cols int32 [n, kd], out_vals f32 [n, kd],
+ * out_cnt int32 [n] -- row i has out_cnt[i] entries, the diagonal first; out_affinity (may be NULL) f32 [n, kd], 0 at
+ * non-mutual slots.
+ */
+XS_API int xs_diffusion_laplacian(int device, const float* sims, const int64_t* ids, int64_t n, int kd, double alpha, double gamma,
+                                  int32_t* out_cols, float* out_vals, int32_t* out_cnt, float* out_affinity);
+
+/*
+ * The whole gallery side of the diffusion re-ranking without leaving the device.
+ *   replaces: Diffusion.get_offline_results up to the final csr_matrix merge           src/utils/diffusion.py:52-85
+ * N x N self-kNN truncated at n_trunc (row i's own id first) -> mutual-kNN graph of the first kd neighbours ->
+ * Laplacian -> one truncated CG per row on L[ids][:, ids] x = e_0 (see xs_diffusion_cg).  The lists never visit the
+ * host between the stages.  out_ids int64 [n, n_trunc], out_sims f32 [n, n_trunc] (may be NULL), out_scores f32
+ * [n, n_trunc]: HOST.  n_trunc <= 4096.
+ */
+XS_API int xs_diffusion_offline(xs_index* index, int n_trunc, int kd, double alpha, double gamma, int maxiter, double tol,
+                                int64_t* out_ids, float* out_sims, float* out_scores);
+
+/*
  * Gallery-side diffusion: one truncated conjugate-gradient solve per database row.
  *   replaces: get_offline_result (`lap_alpha[ids][:, ids]`, `linalg.cg(trunc_lap, trunc_init, tol=1e-6, maxiter=20)`)
  *             src/utils/diffusion.py:15-19 and the joblib loop over all rows :74-76
@@ -253,6 +276,10 @@ XS_API int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* ind
  *   "self_lanes"   int    2 = xs_self_knn alternates its batches between the index and an internal clone (1)
  */
 XS_API int xs_set_param(xs_index* index, const char* name, double value);
+
+/* Debugging aid (after xs_set_param "boot_trace" 1): per-CTA globaltimer stamps [grid][8] of the last GEMM launch that
+ * bootstrapped its threshold in-kernel; *grid receives the CTA count (0 if none was recorded). */
+XS_API int xs_debug_boot_trace(xs_index* index, unsigned long long* out, int max_ctas, int* grid);
 
 #ifdef __cplusplus
 }

@@ -49,3 +49,30 @@ for n in (1_007_000, 125_875):
     ix.close()
     del rows
     torch.cuda.empty_cache()
+
+# timeline of the in-kernel bootstrap at the shard size (per-CTA globaltimer stamps)
+import ctypes as C
+import numpy as np
+nat = importlib.import_module("image-search-engine-for-historical-research_b200._native")
+for n in (125_875, 1_007_000):
+    rows = bench.synth_rows_device(torch, n, 2048, dev, 0)
+    ix = pkg.ExactIndex.from_device(rows.data_ptr(), n, 2048, 0)
+    ix.set_param("boot_trace", 1)
+    for _ in range(5):
+        ix.search_device(queries.data_ptr(), 70, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
+    torch.cuda.synchronize()
+    buf = np.zeros((160, 8), dtype=np.uint64)
+    g = C.c_int(0)
+    nat.check(nat.load().xs_debug_boot_trace(ix._h, buf.ctypes.data, 160, C.byref(g)), "trace")
+    t = buf[: g.value].astype(np.int64)
+    t0 = t[:, 0].min()
+    rel = (t - t0) / 1e3
+    names = ["start", "tile1", "arrived", "all_arrived(owner)", "thr_out", "acc0_released", "done"]
+    print(f"bootstrap timeline, {n} rows, {g.value} CTAs (us after the first CTA's start): ", flush=True)
+    for j, nm in enumerate(names):
+        col = rel[:, j][t[:, j] > 0]
+        if col.size:
+            print(f"  {nm:20s} min {col.min():7.1f}  median {np.median(col):7.1f}  max {col.max():7.1f}   ({col.size} CTAs)")
+    ix.close()
+    del rows
+    torch.cuda.empty_cache()
