@@ -88,7 +88,7 @@ struct xs_index {
                                                   // (measured: 1.03 s either way at 500k x 500k -- the loop is tensor/power bound)
     xs_index* self_lane = nullptr;                // that clone (created on first use, freed with the index)
     // workspace
-    Buf boot_samp, boot_sync, boot_trace, q32r;
+    Buf boot_samp, boot_sync, boot_trace, q32r, sbound;
     int boot_trace_on = 0, boot_trace_grid = 0;
     Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
@@ -201,7 +201,7 @@ static void index_free(xs_index* ix) {
     if (ix->self_lane) { index_free(ix->self_lane); ix->self_lane = nullptr; }
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->boot_trace, &ix->q32r, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->boot_trace, &ix->q32r, &ix->sbound, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release(); ix->h_aqe.release();
     if (ix->share) {
@@ -458,6 +458,7 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
     const int64_t chunk_max = 16;
     XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
     XS_TRY(ix->ghist.ensure((size_t)chunk_max * HIST_BINS * sizeof(uint32_t)));
+    XS_TRY(ix->sbound.ensure(64 * sizeof(float)));
     const int64_t slots = round_up(chunk_max, 128) * P;
     XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
     XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
@@ -465,10 +466,10 @@ static int run_exact(xs_index* ix, const float* q32, int64_t nq, int k, int64_t 
     for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
         const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
         CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
-        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
+        launch_exact_scores(ix->db32, q32 + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->dstats, ix->sbound.as<float>(), ix->num_sms, ix->cur);
         *launches += (c + 3) / 4;
         if (self_base >= 0) { boost_self_kernel<<<(c + 127) / 128, 128, 0, ix->cur>>>(ix->scores.as<float>(), ix->n, c, self_base + q0); ++*launches; }
-        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, ix->ghist.as<uint32_t>(), true, ix->pool_items.as<uint64_t>(),
+        launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, nullptr, ix->ghist.as<uint32_t>(), ix->sbound.as<float>(), true, ix->pool_items.as<uint64_t>(),
                                ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->cur);
         FinaliseArgs fa{};
         fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
@@ -550,6 +551,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         const int64_t chunk_max = 8;
         XS_TRY(ix->scores.ensure((size_t)chunk_max * ix->n * sizeof(float)));
         XS_TRY(ix->ghist.ensure((size_t)chunk_max * HIST_BINS * sizeof(uint32_t)));
+        XS_TRY(ix->sbound.ensure(64 * sizeof(float)));
         const int64_t slots = round_up(chunk_max, 128) * P;
         XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
         XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
@@ -558,10 +560,10 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
             CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
-            launch_scan_scores(ix->db16, ix->q32r.as<float>() + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->num_sms, ix->cur);
+            launch_scan_scores(ix->db16, ix->q32r.as<float>() + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->dstats, ix->sbound.as<float>(), ix->num_sms, ix->cur);
             launches += (c + 1) / 2;
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
-            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), false, ix->pool_items.as<uint64_t>(),
+            launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), ix->sbound.as<float>(), false, ix->pool_items.as<uint64_t>(),
                                    ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(), P, cap, ix->cur);
             FinaliseArgs fa{};
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
@@ -969,6 +971,7 @@ extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, i
     XS_TRY(ix->scores.ensure((size_t)chunk * n * sizeof(float)));
     XS_TRY(ix->ghist.ensure((size_t)chunk * HIST_BINS * sizeof(uint32_t)));
     XS_TRY(ix->sort_work.ensure(rank_all_work_bytes(chunk, n)));
+    XS_TRY(ix->sbound.ensure(64 * sizeof(float)));
     const int64_t cb_max = nq < col_block ? nq : col_block;
     XS_TRY(ix->rank_out.ensure((size_t)n * cb_max * sizeof(int64_t)));
     if (out_scores_sorted) XS_TRY(ix->rank_scores.ensure((size_t)n * cb_max * sizeof(float)));
@@ -988,7 +991,7 @@ extern "C" int xs_rank_all(xs_index* ix, const void* q, int dtype, int64_t nq, i
             const int c = (int)((cb - q0 < chunk) ? cb - q0 : chunk);
             CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->stream));
             launch_exact_scores(ix->db32, ix->q32.as<float>() + (b0 + q0) * ix->d_pad, c, n, ix->d_pad, ix->scores.as<float>(), n,
-                                ix->ghist.as<uint32_t>(), ix->num_sms, ix->stream);
+                                ix->ghist.as<uint32_t>(), ix->dstats, ix->sbound.as<float>(), ix->num_sms, ix->stream);
             launch_rank_all(ix->scores.as<float>(), n, c, n, (int)q0, (int)cb, ix->id_offset, ix->sort_work.p,
                             ix->rank_out.as<int64_t>(), out_scores_sorted ? ix->rank_scores.as<float>() : nullptr, ix->stream);
             launches += (c + 3) / 4 + 13;

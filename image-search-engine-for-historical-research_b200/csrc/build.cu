@@ -164,13 +164,6 @@ finish_rows_kernel(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad
     }
 }
 
-void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm, bool rotate, uint32_t seed,
-                        DevStats* stats, cudaStream_t st) {
-    if (rows <= 0) return;
-    const size_t smem = (size_t)d_pad * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(finish_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    finish_rows_kernel<<<(unsigned)rows, ROW_THREADS, smem, st>>>(rows32, rows16, rows, d_pad, renorm ? 1 : 0, rotate ? 1 : 0, seed, stats);
-}
 
 // Query preparation, one launch: optional copy from the caller's raw fp32 rows (pitch d), optional normalisation
 // (nnsearch.py:693-697), the rotated copies the coarse kernels read (bf16 for the GEMM, fp32 for the batch-1 scan),
@@ -232,15 +225,216 @@ prep_queries_kernel(const float* __restrict__ raw, int raw_pitch, int d, float* 
     }
 }
 
+
+// ---- register / shuffle form of the same kernels for d_pad = 128 * J, J a power of two (128 .. 4096 columns) ---------
+// Thread t of the 128-thread CTA holds elements j * 128 + t (coalesced rows): the Walsh-Hadamard butterflies on the j bits
+// are register-to-register, those on the five lane bits are shuffles, and only the two warp bits go through shared memory
+// -- four barriers per round instead of one per butterfly stage, which is what the per-request latency of prep feels.
+template <int J>
+__device__ __forceinline__ void cta_rotate_regs(float (&v)[J], float* xch, uint32_t seed) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float scale = rsqrtf((float)(J * ROW_THREADS));
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] *= rot_sign(seed, (uint32_t)round, (uint32_t)(j * ROW_THREADS + tid));
+#pragma unroll
+        for (int m = 1; m < J; m <<= 1)
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (!(j & m)) { const float a = v[j], b = v[j | m]; v[j] = a + b; v[j | m] = a - b; }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float other = __shfl_xor_sync(0xffffffffu, v[j], o);
+                v[j] = (lane & o) ? other - v[j] : v[j] + other;
+            }
+#pragma unroll
+        for (int wb = 32; wb < ROW_THREADS; wb <<= 1) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < J; ++j) xch[j * ROW_THREADS + tid] = v[j];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float other = xch[j * ROW_THREADS + (tid ^ wb)];
+                v[j] = (tid & wb) ? other - v[j] : v[j] + other;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] *= scale;
+    }
+}
+
+__device__ __forceinline__ void block_sum4(double (&a)[4], double* red) {      // red: 4 * ROW_THREADS/32 doubles
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = warp_sum(a[i]);
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[i * (ROW_THREADS / 32) + warp] = a[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < ROW_THREADS / 32; ++w) t += red[i * (ROW_THREADS / 32) + w];
+        a[i] = t;
+    }
+}
+
+// Shared tail of the two fast kernels: v = the (normalised) row.  Rotates (optional), rounds to bf16 and returns
+// sums[0] = ||v'||^2, sums[1] = sum v'^4, sums[2] = ||v' - bf16(v')||^2, sums[3] = ||bf16(v')||^2.
+template <int J>
+__device__ __forceinline__ void rotate_round_reduce(float (&v)[J], float* xch, double* red, int rotate, uint32_t seed,
+                                                    __nv_bfloat16* dst16, float* dst32r, double (&sums)[4]) {
+    const int tid = threadIdx.x;
+    if (rotate) cta_rotate_regs<J>(v, xch, seed);
+    sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const float x = v[j];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const float w = __bfloat162float(h);
+        if (dst16) dst16[j * ROW_THREADS + tid] = h;
+        if (dst32r) dst32r[j * ROW_THREADS + tid] = x;
+        const double q = (double)x * x, e = (double)x - (double)w;
+        sums[0] += q; sums[1] += q * q; sums[2] += e * e; sums[3] += (double)w * w;
+    }
+    block_sum4(sums, red);
+}
+
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS)
+finish_rows_fast_kernel(float* rows32, __nv_bfloat16* rows16, int64_t rows, int renorm, int rotate, uint32_t seed, DevStats* stats) {
+    __shared__ float xch[J * ROW_THREADS];
+    __shared__ double red[4 * ROW_THREADS / 32];
+    constexpr int d_pad = J * ROW_THREADS;
+    const int tid = threadIdx.x;
+    const int64_t r = blockIdx.x;
+    float* row = rows32 + r * d_pad;
+    float v[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) v[j] = row[j * ROW_THREADS + tid];
+    double s2 = 0.0;
+    if (renorm) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) a += (double)v[j] * v[j];
+        block_sum2(a, b, red);
+        const float scale = (a > 0.0) ? (float)(1.0 / sqrt(a)) : 0.f;       // a zero row stays zero (the reference would produce NaNs, nnsearch.py:697)
+#pragma unroll
+        for (int j = 0; j < J; ++j) { v[j] *= scale; row[j * ROW_THREADS + tid] = v[j]; }
+    }
+    if (!rotate) { double a = 0.0, b = 0.0; for (int j = 0; j < J; ++j) a += (double)v[j] * v[j]; block_sum2(a, b, red); s2 = a; }
+    double sums[4];
+    rotate_round_reduce<J>(v, xch, red, rotate, seed, rows16 ? rows16 + r * d_pad : nullptr, nullptr, sums);
+    if (rotate) s2 = sums[0];
+    if (tid == 0) {
+        const float n4 = (float)sqrt(sqrt(sums[1])) * 1.000001f, n2 = (float)sqrt(s2) * 1.00001f, rho = (float)sqrt(sums[2]) * 1.000001f;
+        atomicMax(&stats->v4max_bits, __float_as_uint(n4));
+        atomicMax(&stats->vnmax_bits, __float_as_uint(n2));
+        atomicMax(&stats->rhomax_bits, __float_as_uint(rho));
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS)
+prep_queries_fast_kernel(const float* __restrict__ raw, int raw_pitch, int d, float* q32, __nv_bfloat16* q16, float* q32r,
+                         int64_t nq, int renorm, int rotate, uint32_t seed, const DevStats* stats,
+                         float eps_sigmas, int eps_mode, float* __restrict__ eps) {
+    __shared__ float xch[J * ROW_THREADS];
+    __shared__ double red[4 * ROW_THREADS / 32];
+    constexpr int d_pad = J * ROW_THREADS;
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const int64_t r = blockIdx.x;
+    if (r >= nq) {                                      // GEMM tile padding
+        if (q16) for (int c = tid * 8; c < d_pad; c += 8 * ROW_THREADS) *reinterpret_cast<uint4*>(q16 + r * d_pad + c) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    float v[J];
+    if (raw) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) { const int c = j * ROW_THREADS + tid; v[j] = (c < d) ? raw[r * raw_pitch + c] : 0.f; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] = q32[r * d_pad + j * ROW_THREADS + tid];
+    }
+    if (renorm) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) a += (double)v[j] * v[j];
+        block_sum2(a, b, red);
+        const float scale = (a > 0.0) ? (float)(1.0 / sqrt(a)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] *= scale;
+    }
+    if (raw || renorm) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) q32[r * d_pad + j * ROW_THREADS + tid] = v[j];
+    }
+    double sums[4];
+    rotate_round_reduce<J>(v, xch, red, rotate, seed, q16 ? q16 + r * d_pad : nullptr, q32r ? q32r + r * d_pad : nullptr, sums);
+    if (tid == 0) {
+        const float v4 = __uint_as_float(stats->v4max_bits), vn = __uint_as_float(stats->vnmax_bits), vrho = __uint_as_float(stats->rhomax_bits);
+        const float q4 = (float)sqrt(sqrt(sums[1])), qn = (float)sqrt(sums[0]) * 1.00001f;    // the rotation preserves the norm (to rounding)
+        float e;
+        if (eps_mode == 1) {
+            const float q16n = (float)sqrt(sums[3]) * 1.000001f, qrho = (float)sqrt(sums[2]) * 1.000001f;
+            e = vrho * q16n + vn * qrho + ((float)d_pad * 2.3841858e-7f + 1e-5f) * qn * vn;
+        } else {
+            e = eps_sigmas * (1.0f / 512.0f) * 1.7f * q4 * v4 + 2e-5f * qn * vn;
+        }
+        eps[r] = e;
+    }
+}
+
+template <int J>
+static void launch_prep_fast(const float* raw, int d, float* q32, __nv_bfloat16* q16, float* q32r, int64_t nq, int64_t rows,
+                             bool renorm, bool rotate, uint32_t seed, const DevStats* stats, float eps_sigmas, int eps_mode, float* eps, cudaStream_t st) {
+    launch_pdl(prep_queries_fast_kernel<J>, dim3((unsigned)rows), dim3(ROW_THREADS), 0, st,
+               raw, d, d, q32, q16, q32r, nq, renorm ? 1 : 0, rotate ? 1 : 0, seed, stats, eps_sigmas, eps_mode, eps);
+}
+
 void launch_prep_queries(const float* raw, int d, float* q32, __nv_bfloat16* q16, float* q32r, int64_t nq, int64_t nq_pad, int d_pad,
                          bool renorm, bool rotate, uint32_t seed, const DevStats* stats, float eps_sigmas, int eps_mode, float* eps,
                          cudaStream_t st) {
     if (nq <= 0) return;
     const int64_t rows = q16 ? nq_pad : nq;
+    switch (d_pad) {
+        case 128:  return launch_prep_fast<1>(raw, d, q32, q16, q32r, nq, rows, renorm, rotate, seed, stats, eps_sigmas, eps_mode, eps, st);
+        case 256:  return launch_prep_fast<2>(raw, d, q32, q16, q32r, nq, rows, renorm, rotate, seed, stats, eps_sigmas, eps_mode, eps, st);
+        case 512:  return launch_prep_fast<4>(raw, d, q32, q16, q32r, nq, rows, renorm, rotate, seed, stats, eps_sigmas, eps_mode, eps, st);
+        case 1024: return launch_prep_fast<8>(raw, d, q32, q16, q32r, nq, rows, renorm, rotate, seed, stats, eps_sigmas, eps_mode, eps, st);
+        case 2048: return launch_prep_fast<16>(raw, d, q32, q16, q32r, nq, rows, renorm, rotate, seed, stats, eps_sigmas, eps_mode, eps, st);
+        default: break;
+    }
     const size_t smem = (size_t)d_pad * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(prep_queries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_pdl(prep_queries_kernel, dim3((unsigned)rows), dim3(ROW_THREADS), smem, st,
                raw, d, d, q32, q16, q32r, nq, d_pad, renorm ? 1 : 0, rotate ? 1 : 0, seed, stats, eps_sigmas, eps_mode, eps);
+}
+
+void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int d_pad, bool renorm, bool rotate, uint32_t seed,
+                        DevStats* stats, cudaStream_t st) {
+    if (rows <= 0) return;
+    const unsigned g = (unsigned)rows;
+    const int rn = renorm ? 1 : 0, ro = rotate ? 1 : 0;
+    switch (d_pad) {
+        case 128:  finish_rows_fast_kernel<1><<<g, ROW_THREADS, 0, st>>>(rows32, rows16, rows, rn, ro, seed, stats); return;
+        case 256:  finish_rows_fast_kernel<2><<<g, ROW_THREADS, 0, st>>>(rows32, rows16, rows, rn, ro, seed, stats); return;
+        case 512:  finish_rows_fast_kernel<4><<<g, ROW_THREADS, 0, st>>>(rows32, rows16, rows, rn, ro, seed, stats); return;
+        case 1024: finish_rows_fast_kernel<8><<<g, ROW_THREADS, 0, st>>>(rows32, rows16, rows, rn, ro, seed, stats); return;
+        case 2048: finish_rows_fast_kernel<16><<<g, ROW_THREADS, 0, st>>>(rows32, rows16, rows, rn, ro, seed, stats); return;
+        default: break;
+    }
+    const size_t smem = (size_t)d_pad * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(finish_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    finish_rows_kernel<<<g, ROW_THREADS, smem, st>>>(rows32, rows16, rows, d_pad, rn, ro, seed, stats);
 }
 
 // ---- tiled bf16 copy ---------------------------------------------------------------------------------

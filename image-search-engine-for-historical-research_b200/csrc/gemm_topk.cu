@@ -316,9 +316,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 continue;
             }
             if (sample_mode) {
-                // Threshold bootstrap: only the 8 best scores of this lane's tile(s) are needed (the
-                // union of per-tile top-8 lists holds >= k items, and its k-th best is a valid lower
-                // bound of the database's k-th best).  Sorted in registers, no lists, no trims.
+                // Threshold bootstrap: per tile only 8 scores are kept -- the maxima of its 8 column groups (branch-free:
+                // one max per score).  They are real scores, so the k-th best of the union over all sampled tiles is a
+                // valid lower bound of the database's k-th best.  No lists, no trims.
                 float top[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
@@ -327,7 +327,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
-#pragma unroll 1
+#pragma unroll
                     for (int c = 0; c < TILE_N / 32; ++c) {
                         uint32_t v[32];
                         tc_ld32(taddr + c * 32, v);
@@ -335,11 +335,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         const int64_t lim = n_valid - ((int64_t)t * tile_stride * TILE_N + c * 32);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float s = __uint_as_float(v[i]);
-                            if (s > top[7] && i < lim) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { const float hi = fmaxf(top[j], s); s = fminf(top[j], s); top[j] = hi; }
-                            }
+                            const float s = (i < lim) ? __uint_as_float(v[i]) : -INFINITY;
+                            constexpr int G = TILE_N / 8;                      // columns per group
+                            top[(c * 32 + i) / G] = fmaxf(top[(c * 32 + i) / G], s);
                         }
                     }
                     release_acc(acc);
@@ -406,19 +404,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 BOOT_STAMP(1);                                   // first tile accumulated
                 {
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-#pragma unroll 1
-                    for (int c = 0; c < TILE_N / 32; ++c) {
+#pragma unroll
+                    for (int c = 0; c < TILE_N / 32; ++c) {                  // the maximum of every 32-column group: one max per score
                         uint32_t v[32];
                         tc_ld32(taddr + c * 32, v);
                         tc_ld_wait();
                         const int64_t lim = n_valid - ((int64_t)t0 * tile_stride * TILE_N + c * 32);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float s = __uint_as_float(v[i]);
-                            if (s > top[7] && i < lim) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { const float hi = fmaxf(top[j], s); s = fminf(top[j], s); top[j] = hi; }
-                            }
+                            const float s = (i < lim) ? __uint_as_float(v[i]) : -INFINITY;
+                            constexpr int G = TILE_N / 8;
+                            top[(c * 32 + i) / G] = fmaxf(top[(c * 32 + i) / G], s);
                         }
                     }
                 }
@@ -464,28 +460,29 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
                             float t_pub = -INFINITY;
                             if (valid_cnt >= k) {
-                                uint32_t prefix = 0, mask = 0, kk = (uint32_t)k;
-#pragma unroll 1
-                                for (int pass = 0; pass < 4; ++pass) {
-                                    const int shift = 24 - 8 * pass;
+                                // conservative k-th best: min / max of the keys, ONE pass into 256 bins spread over that range,
+                                // lower edge of the bin that holds the k-th largest -- never above it, at most one bin below
+                                uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) my_hist[lane * 8 + j] = 0;
-                                    __syncwarp();
+                                for (int j = 0; j < BOOT_PER_LANE; ++j) if (keys[j] != 0u) { kmin = min(kmin, keys[j]); kmax = max(kmax, keys[j]); }
 #pragma unroll
-                                    for (int j = 0; j < BOOT_PER_LANE; ++j) {
-                                        const bool in = keys[j] != 0u && ((keys[j] & mask) == prefix);
-                                        hist_add(my_hist, (keys[j] >> shift) & 255u, in);
-                                    }
-                                    __syncwarp();
-                                    uint32_t dg, kr;
-                                    warp_pick_digit(my_hist, kk, dg, kr);
-                                    kk = kr;
-                                    prefix |= dg << shift;
-                                    mask |= 255u << shift;
-                                    __syncwarp();
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
                                 }
-                                // the main pass keeps scores strictly above the threshold: k-th best of the sample, minus the band
-                                t_pub = nextafterf(key_score(prefix) - 2.f * eps[qq], -INFINITY);
+                                const uint32_t range = kmax - kmin;
+                                const int shift = (range >> 8) ? (32 - __clz(range) - 8) : 0;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) my_hist[lane * 8 + j] = 0;
+                                __syncwarp();
+#pragma unroll
+                                for (int j = 0; j < BOOT_PER_LANE; ++j) if (keys[j] != 0u) atomicAdd(&my_hist[(keys[j] - kmin) >> shift], 1u);
+                                __syncwarp();
+                                uint32_t dg, kr;
+                                warp_pick_digit(my_hist, (uint32_t)k, dg, kr);
+                                __syncwarp();
+                                // the main pass keeps scores strictly above the threshold: that edge, minus the band
+                                t_pub = nextafterf(key_score(kmin + (dg << shift)) - 2.f * eps[qq], -INFINITY);
                             }
                             if (lane == 0) {
                                 st_release_gpu_u64(boot.thr_pub + qq, ((uint64_t)boot.epoch << 32) | (uint64_t)__float_as_uint(t_pub));

@@ -15,8 +15,7 @@ constexpr int ROW_ALIGN = 256;    // database rows are padded to a multiple of t
 constexpr int COL_ALIGN = 64;     // descriptor length is padded to a multiple of this
 
 constexpr int SLICE_ROWS = 4096;
-constexpr int HIST_BINS = 4096;   // database-wide histogram of score keys (top 12 bits), filled by the scoring kernels
-constexpr int HIST_SHIFT = 20;  // rows per partial list in the score-matrix -> pools kernel
+constexpr int HIST_BINS = 4096;   // database-wide score histogram filled by the scoring kernels (linear bins, scan.cu)
 
 // status bits written by the finalise kernel (one int32 per query)
 constexpr int ST_UNCERTIFIED = 1;
@@ -53,17 +52,18 @@ void launch_tile_db16(const __nv_bfloat16* db16, __nv_bfloat16* db16t, int64_t n
 
 // ---- scan.cu ------------------------------------------------------------------------------------
 // Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  Both scoring kernels also
-// add every score to ghist[q][score_key >> HIST_SHIFT] (zeroed by the caller).
+// add every score to the linear histogram ghist[q][.] (zeroed by the caller).
+//   The histogram is linear over [-B, B], B = ||q|| max||v||; the kernels publish B per query in bounds[q] for scores_to_pools.
 void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
-                        float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st);
+                        float* scores, int64_t score_pitch, uint32_t* ghist, const DevStats* stats, float* bounds, int num_sms, cudaStream_t st);
 // Exact scoring: scores[q][row] = fp32( sum_fp64 db32[row][i] * q32[q][i] ).  Any nq (looped in 4s).
 void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n, int d_pad,
-                         float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st);
+                         float* scores, int64_t score_pitch, uint32_t* ghist, const DevStats* stats, float* bounds, int num_sms, cudaStream_t st);
 // Score matrix -> candidate pools (one partial list per SLICE_ROWS rows).
 //   exact = false: keep items within the eps band below the slice's k-th best
 //   exact = true : keep exactly the slice's k best (full 64-bit item order)
 void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                            const float* eps, const uint32_t* ghist, bool exact, uint64_t* pool_items, int* pool_count,
+                            const float* eps, const uint32_t* ghist, const float* bounds, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st);
 
 // ---- gemm_topk.cu -------------------------------------------------------------------------------

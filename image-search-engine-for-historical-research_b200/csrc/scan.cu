@@ -11,6 +11,45 @@
 
 namespace xs {
 
+// ---- database-wide score histogram ---------------------------------------------------------------------------------
+// Both scoring kernels count every score into HIST_BINS bins that are LINEAR over [-B, +B], B = ||q|| * max ||v|| (no score
+// can leave that interval): 4096 bins of width B / 2048 whatever the score level.  (Bins cut from the float's exponent
+// and leading mantissa bits are 0.06 wide around 0.6 -- un-whitened descriptors score 0.6..0.7 against everything, the
+// k-th best's bin then holds most of the database and the batch-1 path falls back to the exact scan on every query.)
+__device__ __forceinline__ int score_bin(float s, float inv_bound) {
+    const float t = fmaf(s, inv_bound, 1.0f) * (float)(HIST_BINS / 2);
+    const int b = (int)t;                               // NaN -> 0
+    return min(max(b, 0), HIST_BINS - 1);
+}
+__device__ __forceinline__ float bin_lower_edge(int b, float bound) {      // a score counted in bin b is >= this (minus rounding, see caller)
+    return ((float)b * (1.0f / (float)(HIST_BINS / 2)) - 1.0f) * bound;
+}
+// ||q|| * max||v|| (slightly inflated) for the QB query rows in shared memory; every CTA computes the same values, CTA 0
+// publishes them for scores_to_pools.  `red`: QB * 8 doubles.  Ends with a barrier.
+template <int QB>
+__device__ __forceinline__ void query_bounds(const float* qs, int d_pad, const DevStats* stats, double* red, float* bound_out, float (&inv)[QB]) {
+    double a[QB];
+#pragma unroll
+    for (int b = 0; b < QB; ++b) {
+        a[b] = 0.0;
+        for (int i = threadIdx.x; i < d_pad; i += blockDim.x) a[b] += (double)qs[b * d_pad + i] * qs[b * d_pad + i];
+        a[b] = warp_sum(a[b]);
+    }
+    if (lane_id() == 0)
+#pragma unroll
+        for (int b = 0; b < QB; ++b) red[b * 8 + (threadIdx.x >> 5)] = a[b];
+    __syncthreads();
+    const float vn = __uint_as_float(stats->vnmax_bits);
+#pragma unroll
+    for (int b = 0; b < QB; ++b) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[b * 8 + w];
+        const float bound = (float)sqrt(t) * vn * 1.0001f;
+        inv[b] = bound > 0.f ? 1.0f / bound : 0.f;
+        if (blockIdx.x == 0 && threadIdx.x == 0) bound_out[b] = bound;
+    }
+}
+
 // ---- scan_scores ---------------------------------------------------------------------------------
 // One warp owns groups of R consecutive rows (R * d_pad * 2 contiguous bytes).  Per step every
 // lane issues R 16-byte loads per 8-element chunk, two chunks in flight, so a warp keeps
@@ -18,13 +57,17 @@ namespace xs {
 template <int QB, int R>
 __global__ void __launch_bounds__(256, 2)
 scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32, int64_t n, int d_pad,
-                   float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist) {
-    extern __shared__ float qs[];                       // [QB][d_pad] query rows | [QB][HIST_BINS] score-key histogram
+                   float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist, const DevStats* __restrict__ stats,
+                   float* __restrict__ bounds) {
+    extern __shared__ float qs[];                       // [QB][d_pad] query rows | [QB][HIST_BINS] score histogram
+    __shared__ double red[QB * 8];
     pdl_wait();
     uint32_t* sh = reinterpret_cast<uint32_t*>(qs + QB * d_pad);
     for (int i = threadIdx.x; i < QB * d_pad; i += blockDim.x) qs[i] = q32[i];
     for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
+    float inv[QB];
+    query_bounds<QB>(qs, d_pad, stats, red, bounds, inv);
     const int chunks = d_pad >> 3;                      // 16-byte chunks per row
     const int lane = lane_id();
     const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -80,7 +123,7 @@ scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32
                 float s = warp_sum(acc[r][b]);
                 if (lane == 0 && row0 + r < n) {
                     scores[(int64_t)b * pitch + row0 + r] = s;
-                    atomicAdd(&sh[b * HIST_BINS + (score_key(s) >> HIST_SHIFT)], 1u);
+                    atomicAdd(&sh[b * HIST_BINS + score_bin(s, inv[b])], 1u);
                 }
             }
     }
@@ -90,7 +133,7 @@ scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32
 }
 
 void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
-                        float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st) {
+                        float* scores, int64_t score_pitch, uint32_t* ghist, const DevStats* stats, float* bounds, int num_sms, cudaStream_t st) {
     const int grid = num_sms * 2;
     const uint4* db = reinterpret_cast<const uint4*>(db16);
     const size_t per_q = (size_t)d_pad * sizeof(float) + HIST_BINS * sizeof(uint32_t);
@@ -102,10 +145,10 @@ void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int
         float* s = scores + (int64_t)q0 * score_pitch;
         uint32_t* h = ghist + (size_t)q0 * HIST_BINS;
         if (left >= 2) {
-            launch_pdl(scan_scores_kernel<2, 4>, dim3(grid), dim3(256), 2 * per_q, st, db, q, n, d_pad, s, score_pitch, h);
+            launch_pdl(scan_scores_kernel<2, 4>, dim3(grid), dim3(256), 2 * per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 2;
         } else {
-            launch_pdl(scan_scores_kernel<1, 4>, dim3(grid), dim3(256), per_q, st, db, q, n, d_pad, s, score_pitch, h);
+            launch_pdl(scan_scores_kernel<1, 4>, dim3(grid), dim3(256), per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 1;
         }
     }
@@ -115,12 +158,16 @@ void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int
 template <int QB, int R>
 __global__ void __launch_bounds__(256, 2)
 exact_scores_kernel(const float4* __restrict__ db32, const float* __restrict__ q32, int64_t n, int d_pad,
-                    float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist) {
+                    float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist, const DevStats* __restrict__ stats,
+                    float* __restrict__ bounds) {
     extern __shared__ float qs[];
+    __shared__ double red[QB * 8];
     uint32_t* sh = reinterpret_cast<uint32_t*>(qs + QB * d_pad);
     for (int i = threadIdx.x; i < QB * d_pad; i += blockDim.x) qs[i] = q32[i];
     for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
+    float inv[QB];
+    query_bounds<QB>(qs, d_pad, stats, red, bounds, inv);
     const int chunks = d_pad >> 2;                      // float4 per row
     const int lane = lane_id();
     const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -159,7 +206,7 @@ exact_scores_kernel(const float4* __restrict__ db32, const float* __restrict__ q
                 double s = warp_sum(acc[r][b]);
                 if (lane == 0 && row0 + r < n) {
                     scores[(int64_t)b * pitch + row0 + r] = (float)s;
-                    atomicAdd(&sh[b * HIST_BINS + (score_key((float)s) >> HIST_SHIFT)], 1u);
+                    atomicAdd(&sh[b * HIST_BINS + score_bin((float)s, inv[b])], 1u);
                 }
             }
     }
@@ -169,7 +216,7 @@ exact_scores_kernel(const float4* __restrict__ db32, const float* __restrict__ q
 }
 
 void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n, int d_pad,
-                         float* scores, int64_t score_pitch, uint32_t* ghist, int num_sms, cudaStream_t st) {
+                         float* scores, int64_t score_pitch, uint32_t* ghist, const DevStats* stats, float* bounds, int num_sms, cudaStream_t st) {
     const int grid = num_sms * 2;
     const float4* db = reinterpret_cast<const float4*>(db32);
     const size_t per_q = (size_t)d_pad * sizeof(float) + HIST_BINS * sizeof(uint32_t);
@@ -182,13 +229,13 @@ void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n,
         float* s = scores + (int64_t)q0 * score_pitch;
         uint32_t* h = ghist + (size_t)q0 * HIST_BINS;
         if (left >= 4) {
-            exact_scores_kernel<4, 2><<<grid, 256, 4 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
+            exact_scores_kernel<4, 2><<<grid, 256, 4 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 4;
         } else if (left >= 2) {
-            exact_scores_kernel<2, 2><<<grid, 256, 2 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
+            exact_scores_kernel<2, 2><<<grid, 256, 2 * per_q, st>>>(db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 2;
         } else {
-            exact_scores_kernel<1, 2><<<grid, 256, per_q, st>>>(db, q, n, d_pad, s, score_pitch, h);
+            exact_scores_kernel<1, 2><<<grid, 256, per_q, st>>>(db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 1;
         }
     }
@@ -202,7 +249,7 @@ void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n,
 //   exact scores : emit the slice's own k best that are not below the edge (bounded by k per slice)
 __global__ void __launch_bounds__(256)
 scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t n, int k,
-                       const float* __restrict__ eps, const uint32_t* __restrict__ ghist, int exact,
+                       const float* __restrict__ eps, const uint32_t* __restrict__ ghist, const float* __restrict__ bounds, int exact,
                        uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr,
                        int P, int cap) {
     __shared__ uint32_t keys[SLICE_ROWS];
@@ -238,7 +285,12 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
 #pragma unroll
             for (int j = PER - 1; j >= 0; --j) {
                 run += h[j];
-                if (run >= (uint32_t)k) { edge_key = (uint32_t)(threadIdx.x * PER + j) << HIST_SHIFT; break; }
+                if (run >= (uint32_t)k) {
+                    // lower edge of that bin, lowered by the rounding of the bin arithmetic: no score counted in it or above lies below
+                    const float b = bounds[q];
+                    edge_key = max(1u, score_key(bin_lower_edge(threadIdx.x * PER + j, b) - 1e-6f * b));
+                    break;
+                }
             }
         }
     }
@@ -282,10 +334,10 @@ scores_to_pools_kernel(const float* __restrict__ scores, int64_t pitch, int64_t 
 }
 
 void launch_scores_to_pools(const float* scores, int64_t score_pitch, int nq, int64_t n, int k,
-                            const float* eps, const uint32_t* ghist, bool exact, uint64_t* pool_items, int* pool_count,
+                            const float* eps, const uint32_t* ghist, const float* bounds, bool exact, uint64_t* pool_items, int* pool_count,
                             uint32_t* pool_thr, int P, int cap, cudaStream_t st) {
     dim3 grid((unsigned)P, (unsigned)nq);
-    launch_pdl(scores_to_pools_kernel, grid, dim3(256), 0, st, scores, score_pitch, n, k, eps, ghist, exact ? 1 : 0,
+    launch_pdl(scores_to_pools_kernel, grid, dim3(256), 0, st, scores, score_pitch, n, k, eps, ghist, bounds, exact ? 1 : 0,
                pool_items, pool_count, pool_thr, P, cap);
 }
 

@@ -2,11 +2,12 @@
 
 The reference builds the N x N kNN graph with faiss (``self.knn.search(self.features, n_trunc)``,
 src/utils/diffusion.py:67) and then decides mutual neighbourhood row by row in Python
-(``get_affinity``, :101-116).  Here the kNN lists come from ``KNN.self_search`` (tcgen05 GEMM + fused
-top-K, a row's own id first) and the mutual test runs as one CUDA kernel (xs_mutual_knn); the sparse
-assembly and the normalised Laplacian keep the reference's scipy formulation (:87-98).  The per-row
-truncated conjugate-gradient solves (:15-19, 74-76) run on the GPU as well, one CTA per database row
-(xs_diffusion_cg); ``Diffusion`` strings the three together like the reference class does.
+(``get_affinity``, :101-116).  Here the kNN lists come from the tcgen05 GEMM + fused top-K self search (a row's
+own id first); the mutual test, the affinity values, the degrees and the normalised Laplacian are CUDA kernels
+(xs_diffusion_laplacian) that round exactly where the reference's float32 scipy matrices do, and the per-row
+truncated conjugate-gradient solves (:15-19, 74-76) run one CTA per database row (xs_diffusion_cg).
+``Diffusion.get_offline_results`` strings the three together ON the device (xs_diffusion_offline): the kNN lists go
+from the search kernels to the graph kernels to the solver without visiting the host.
 """
 from __future__ import annotations
 
@@ -27,29 +28,49 @@ def mutual_mask(ids, device: int = 0) -> np.ndarray:
     return out.view(np.bool_)
 
 
+def _device_graph(sims, ids, alpha: float, gamma: float, device: int):
+    """xs_diffusion_laplacian: mutual test, affinity, degrees and Laplacian on the device; returns the ELL arrays
+    ``(cols int32 [n,kd], vals f32 [n,kd], cnt int32 [n], affinity f32 [n,kd])``."""
+    sims = np.ascontiguousarray(sims, dtype=np.float32)
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    n, kd = ids.shape
+    cols = np.empty((n, kd), dtype=np.int32)
+    vals = np.empty((n, kd), dtype=np.float32)
+    cnt = np.empty((n,), dtype=np.int32)
+    aff = np.empty((n, kd), dtype=np.float32)
+    nat.check(nat.load().xs_diffusion_laplacian(int(device), sims.ctypes.data, ids.ctypes.data, n, kd, float(alpha), float(gamma),
+                                                cols.ctypes.data, vals.ctypes.data, cnt.ctypes.data, aff.ctypes.data),
+              "xs_diffusion_laplacian")
+    return cols, vals, cnt, aff
+
+
 def get_affinity(sims, ids, gamma=3, device: int = 0):
-    """Drop-in for ``Diffusion.get_affinity(sims, ids, gamma=3)`` (diffusion.py:101-116): mutual-kNN
-    affinity ``csc_matrix`` with values ``max(sim, 0) ** gamma``.  Like the reference it clamps
-    negative similarities in the caller's ``sims`` array in place (:103)."""
+    """Drop-in for ``Diffusion.get_affinity(sims, ids, gamma=3)`` (diffusion.py:101-116): mutual-kNN affinity
+    ``csc_matrix`` with values ``max(sim, 0) ** gamma``, computed on the device.  Like the reference it clamps negative
+    similarities in the caller's ``sims`` array in place (:103)."""
     import scipy.sparse as sparse
     num = sims.shape[0]
     sims[sims < 0] = 0
-    powed = sims ** gamma
-    mask = mutual_mask(ids, device)
+    _, _, _, aff = _device_graph(sims, ids, 0.99, gamma, device)
+    mask = aff != 0
     rows = np.repeat(np.arange(num), mask.sum(axis=1))
-    return sparse.csc_matrix((powed[mask], (rows, np.asarray(ids)[mask])), shape=(num, num), dtype=np.float32)
+    return sparse.csc_matrix((aff[mask], (rows, np.asarray(ids)[mask])), shape=(num, num), dtype=np.float32)
 
 
 def get_laplacian(sims, ids, alpha=0.99, device: int = 0):
-    """``Diffusion.get_laplacian`` (diffusion.py:87-98): ``I - alpha * D^-1/2 A D^-1/2``."""
+    """``Diffusion.get_laplacian`` (diffusion.py:87-98): ``I - alpha * D^-1/2 A D^-1/2`` as a float32 ``csr_matrix``.
+    Every entry is computed on the device in the reference's order of float32 roundings (csrc/graph.cu); the host only
+    wraps the device's row lists into a scipy matrix."""
     import scipy.sparse as sparse
-    affinity = get_affinity(sims, ids, device=device)
-    num = affinity.shape[0]
-    degrees = affinity @ np.ones(num) + 1e-12
-    mat = sparse.dia_matrix((degrees ** (-0.5), [0]), shape=(num, num), dtype=np.float32)
-    stochastic = mat @ affinity @ mat
-    sparse_eye = sparse.dia_matrix((np.ones(num), [0]), shape=(num, num), dtype=np.float32)
-    return sparse_eye - alpha * stochastic
+    num = sims.shape[0]
+    sims[sims < 0] = 0                                       # the reference's get_affinity clamps in place (:103)
+    cols, vals, cnt, _ = _device_graph(sims, ids, alpha, 3, device)
+    keep = np.arange(cols.shape[1])[None, :] < cnt[:, None]
+    indptr = np.zeros(num + 1, dtype=np.int64)
+    np.cumsum(cnt, out=indptr[1:])
+    lap = sparse.csr_matrix((vals[keep], cols[keep], indptr), shape=(num, num), dtype=np.float32)
+    lap.sort_indices()
+    return lap
 
 
 def knn_graph(features, n_trunc: int, kd: int = 50, device: int = 0):
@@ -86,6 +107,21 @@ def offline_cg(lap, trunc_ids, tol: float = 1e-6, maxiter: int = 20, device: int
     return out
 
 
+def offline_device(index, n_trunc: int, kd: int = 50, alpha: float = 0.99, gamma: float = 3, tol: float = 1e-6, maxiter: int = 20,
+                   return_sims: bool = False):
+    """Steps 1-2 of ``get_offline_results`` (diffusion.py:52-76) in one device-resident pass over an ``ExactIndex``:
+    N x N self-kNN truncated at ``n_trunc``, Laplacian of the first ``kd`` neighbours, one truncated CG per row.
+    Returns ``(ids int64 (N, n_trunc), sims f32 or None, scores f32 (N, n_trunc))``."""
+    n = index.N
+    ids = np.empty((n, int(n_trunc)), dtype=np.int64)
+    sims = np.empty((n, int(n_trunc)), dtype=np.float32) if return_sims else None
+    scores = np.empty((n, int(n_trunc)), dtype=np.float32)
+    nat.check(index._lib.xs_diffusion_offline(index._h, int(n_trunc), int(kd), float(alpha), float(gamma), int(maxiter), float(tol),
+                                              ids.ctypes.data, sims.ctypes.data if return_sims else None, scores.ctypes.data),
+              "xs_diffusion_offline")
+    return ids, sims, scores
+
+
 class Diffusion(object):
     """Mirror of ``src/utils/diffusion.py:42-116`` (exact-kNN branch; the ANN branch for N >= 110 000 exists in
     the reference only because the exhaustive search was too slow -- here the exhaustive one is used at
@@ -108,9 +144,8 @@ class Diffusion(object):
         if path and os.path.exists(path):
             import joblib
             return joblib.load(path)
-        sims, ids = self.knn.self_search(n_trunc)
-        lap_alpha = self.get_laplacian(sims[:, :kd].copy(), ids[:, :kd])
-        all_scores = offline_cg(lap_alpha, ids, device=self.device)
+        # self-kNN -> graph -> CG without leaving the device (xs_diffusion_offline); the host sees the final arrays only
+        ids, _, all_scores = offline_device(self.knn.index, n_trunc, kd)
         rows = np.repeat(np.arange(self.N), n_trunc)
         offline = sparse.csr_matrix((all_scores.reshape(-1), (rows, ids.reshape(-1))), shape=(self.N, self.N),
                                     dtype=np.float32)
