@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "xs_index_destroy", "xs_index_clone", "xs_index_info", "xs_index_stats", "xs_search", "xs_search_dev", "xs_self_knn",
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
     "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
-    "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_boot_trace",
+    "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_trace",
 )
 
 
@@ -72,7 +72,7 @@ def load() -> C.CDLL:
         lib.xs_diffusion_laplacian.argtypes = [i32, p, p, i64, i32, C.c_double, C.c_double, p, p, p, p]
         lib.xs_diffusion_offline.argtypes = [p, i32, i32, C.c_double, C.c_double, i32, C.c_double, p, p, p]
         lib.xs_set_param.argtypes = [p, C.c_char_p, C.c_double]
-        lib.xs_debug_boot_trace.argtypes = [p, p, i32, C.POINTER(i32)]
+        lib.xs_debug_trace.argtypes = [p, i32, p, i32, C.POINTER(i32)]
         lib.xs_config_set.argtypes = [C.c_char_p, C.c_double]
         lib.xs_exchange_part_bytes.argtypes = [i64, i32]
         lib.xs_exchange_create.argtypes = [i32, i32, i32, i64, i32, C.POINTER(p), p]

@@ -90,6 +90,7 @@ struct xs_index {
     // workspace
     Buf boot_samp, boot_sync, boot_trace, q32r, sbound;
     int boot_trace_on = 0, boot_trace_grid = 0;
+    Buf fin_trace; int fin_trace_rows = 0;
     Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     PinnedBuf h_aqe;                              // pinned staging of xs_aqe_search's id lists
@@ -201,7 +202,7 @@ static void index_free(xs_index* ix) {
     if (ix->self_lane) { index_free(ix->self_lane); ix->self_lane = nullptr; }
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
-    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->boot_trace, &ix->q32r, &ix->sbound, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
+    for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->boot_trace, &ix->fin_trace, &ix->q32r, &ix->sbound, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
                    &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release(); ix->h_aqe.release();
     if (ix->share) {
@@ -391,18 +392,24 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     return XS_OK;
 }
 
-// Debugging aid: the globaltimer stamps of the last bootstrap-inside-the-GEMM launch, [grid][8] nanoseconds
-// (0 job start, 1 first tile accumulated, 2 arrival posted, 3 all arrived (owners), 4 thresholds out, 5 first accumulator released, 6 job done).
-extern "C" int xs_debug_boot_trace(xs_index* ix, unsigned long long* out, int max_ctas, int* grid) {
-    if (!ix || !out || !grid) return fail(XS_ERR_ARG, "null pointer");
+// Debugging aid (xs_set_param "boot_trace" 1): globaltimer stamps (ns) of the last small-batch search.
+//   which = 0: the GEMM launch with the in-kernel bootstrap, [grid][8] (0 job start, 1 first tile accumulated, 2 arrival posted,
+//              3 all arrived (owners), 4 thresholds out, 5 first accumulator released, 6 job done, 7 own threshold selected (owners))
+//   which = 1: the fused finalise launch, rows of 10 per (query, CTA) slot in launch order, unused slots zero (0 start, 1 sizes known,
+//              2 pools gathered, 3 cut known, 4 share collected, 5 share rescored, 6 ticket taken, 7 sorted (last CTA), 8 emitted)
+extern "C" int xs_debug_trace(xs_index* ix, int which, unsigned long long* out, int max_rows, int* rows) {
+    if (!ix || !out || !rows) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(ix->mu);
-    *grid = 0;
-    if (!ix->boot_trace.p || !ix->boot_trace_grid) return XS_OK;
+    *rows = 0;
+    Buf& b = which == 0 ? ix->boot_trace : ix->fin_trace;
+    const int have = which == 0 ? ix->boot_trace_grid : ix->fin_trace_rows;
+    const int width = which == 0 ? 8 : 10;
+    if (!b.p || !have) return XS_OK;
     CU_TRY(cudaSetDevice(ix->device));
     CU_TRY(cudaDeviceSynchronize());
-    const int g = ix->boot_trace_grid < max_ctas ? ix->boot_trace_grid : max_ctas;
-    CU_TRY(cudaMemcpy(out, ix->boot_trace.p, (size_t)g * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    *grid = g;
+    const int g = have < max_rows ? have : max_rows;
+    CU_TRY(cudaMemcpy(out, b.p, (size_t)g * width * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *rows = g;
     return XS_OK;
 }
 
@@ -514,6 +521,12 @@ static int fill_finalise(xs_index* ix, const CoreArgs& a, int64_t q0, int64_t c,
     XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k, fa->cand_max)));
     XS_TRY(ensure_tickets(ix, c));
     fa->work = ix->fin_work.p; fa->ticket = ix->fin_ticket.as<int>();
+    if (ix->boot_trace_on && c <= 128) {
+        XS_TRY(ix->fin_trace.ensure((size_t)128 * 16 * 10 * sizeof(unsigned long long)));
+        CU_TRY(cudaMemsetAsync(ix->fin_trace.p, 0, (size_t)128 * 16 * 10 * sizeof(unsigned long long), ix->cur));
+        fa->trace = ix->fin_trace.as<unsigned long long>();
+        ix->fin_trace_rows = (int)c * 16;
+    }
     if (a.push) {
         // the mailbox part holds ALL nq queries of the call: advance the per-query pointers to this batch
         fa->push = *a.push;

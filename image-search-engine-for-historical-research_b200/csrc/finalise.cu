@@ -6,6 +6,7 @@
 // stand-in for OpenBLAS' sgemm at src/main_retrieve.py:175), (4) sort by (score desc, id asc),
 // (5) emit the first k, plus a certificate bit when anything outside the band may have been lost.
 #include <cstdio>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "select.cuh"
 #include "internal.h"
@@ -487,109 +488,208 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
     }
 }
 
-// ---- fused form for small batches: select + rescore + emit in ONE launch ---------------------------------------
-// grid (nq, S).  Every one of a query's S CTAs repeats the cheap part (gather the pools, conservative k-th, band) and
-// gets the same answer; the candidates are then dealt by row id (row % S), each CTA rescores its share exactly and
-// appends the results to the query's global list; the last CTA to finish (ticket) sorts, emits and -- with the peer
-// exchange on -- stores the k results into every rank's mailbox.  One launch instead of two and no hand-over through
-// HBM between them: the per-step fixed cost that bounds strong scaling.
+// ---- fused form for small batches: select + rescore + emit in ONE launch, one thread-block CLUSTER per query ------------
+// grid (S, nq), cluster (S, 1, 1).  The S CTAs of a query split its partial lists between them and meet through
+// distributed shared memory:
+//   1. every CTA gathers ITS lists (p = rank, rank + S, ...) into shared memory, finds their min / max key;
+//   2. cluster barrier; the global min / max come from the S exchange blocks; every CTA fills a 4096-bin histogram of its
+//      items over that range; cluster barrier; every thread sums its 16 bins over the S CTAs (DSMEM reads) and the usual
+//      suffix scan gives the conservative k-th best and the cut of the band -- the same value in all CTAs;
+//   3. every CTA collects its items inside the band; cluster barrier; the band members are dealt evenly: warp w of CTA r
+//      takes global positions r * found / S + w, + 8, ..., fetches the item from whichever CTA holds it (DSMEM), rescores it
+//      exactly (the 8 KB fp32 row staged with cp.async) and stores the result into CTA 0's list (DSMEM);
+//   4. cluster barrier; CTA 0 ranks the <= cand_max results by counting, emits, and -- with the peer exchange on -- stores
+//      the k results straight into every rank's mailbox.
+// No redundant work, no global atomics or tickets between the phases, S times the shared-memory capacity for the lists.
+// It is what bounds the per-step fixed cost and with it strong scaling.
 constexpr int FF_THREADS = 256, FF_WARPS = FF_THREADS / 32;
+constexpr int FF_ITEMS = 2048;               // pooled items one CTA of the cluster can hold
+constexpr int FF_MAX_CLUSTER = 8;
+__device__ __forceinline__ unsigned long long ff_timer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define FF_STAMP(i) do { if (a.trace && threadIdx.x == 0) a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 10 + (i)] = ff_timer(); } while (0)
+
+struct FfExchange {              // one per CTA, read by the whole cluster
+    uint32_t kmin, kmax, total, thr, ncand, overflow, bad, pad;
+};
+
 __global__ void __launch_bounds__(FF_THREADS)
-finalise_fused_kernel(FinaliseArgs a, int cand_max, int item_cap) {
+finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ uint64_t ff_smem[];
-    uint64_t* mine = ff_smem;                           // [cand_max] this CTA's share of the band
-    uint64_t* items = ff_smem + cand_max;               // phase 1: [item_cap] gathered pool items | offsets | 4096 bins
-    const bool staged = a.P <= FIN_MAX_LISTS;
-    int* offs = reinterpret_cast<int*>(items + item_cap);
-    uint32_t* bins = reinterpret_cast<uint32_t*>(offs + (staged ? ((a.P + 4) & ~3) : 4));
-    float* rows = reinterpret_cast<float*>(ff_smem + cand_max);      // phase 2 (aliases phase 1): [FF_WARPS][d_pad] row staging
-    uint64_t* sorted = ff_smem + cand_max;              // phase 3 (aliases): the query's rescored candidates
-    __shared__ uint32_t edge_sh[4];
-    __shared__ uint32_t edge_wsum[FF_WARPS];
+    uint64_t* cands = ff_smem;                          // [cand_max] this CTA's band members
+    uint64_t* result = ff_smem + cand_max;              // [cand_max] (CTA 0's copy collects the cluster's rescored candidates)
+    uint64_t* items = ff_smem + 2 * cand_max;           // phase 1: [FF_ITEMS] gathered pool items | 4096 bins
+    uint32_t* bins = reinterpret_cast<uint32_t*>(items + FF_ITEMS);
+    float* rows = reinterpret_cast<float*>(ff_smem + 2 * cand_max);      // phase 3 (aliases phase 1): [FF_WARPS][d_pad] row staging
+    __shared__ FfExchange xch;
+    __shared__ int offs[FF_THREADS + 1];
     __shared__ int scan_scratch[33];
-    __shared__ uint32_t sh_found, sh_nmine, sh_flag, sh_tot, sh_selfkey, sh_last;
+    __shared__ uint32_t wsum[FF_WARPS];
+    __shared__ uint32_t sh_min, sh_max, sh_pick, sh_n, sh_selfkey;
     pdl_wait();
-    const int64_t q = blockIdx.x;
-    const uint32_t y = blockIdx.y, S = gridDim.y;
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    FF_STAMP(0);
+    const int64_t q = blockIdx.y;
+    const int S = (int)gridDim.x, r = (int)blockIdx.x;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
 
-    if (threadIdx.x == 0) { sh_found = 0; sh_nmine = 0; sh_flag = 0; sh_tot = 0; sh_selfkey = 0; }
-    __syncthreads();
-    uint32_t total = 0;
+    // ---- 1. my lists: p = r + t * S ------------------------------------------------------------------------------------
+    if (tid == 0) { sh_min = 0xFFFFFFFFu; sh_max = 0u; sh_pick = 0u; sh_n = 0u; sh_selfkey = 0u; }
+    const int n_lists = (a.P - r + S - 1) / S;          // <= FF_THREADS guaranteed by the launcher
+    uint32_t thr = 0;
     {
-        uint32_t thr = 0, t = 0;
-        for (int p = threadIdx.x; p < a.P; p += FF_THREADS) {
-            const int64_t slot = pool_slot(q, p, a.P);
-            const int c = a.pool_count[slot];
-            if (staged) offs[p] = c; else t += (uint32_t)c;
-            thr = max(thr, a.pool_thr[slot]);
+        int c = 0;
+        if (tid < n_lists) {
+            const int64_t slot = pool_slot(q, r + tid * S, a.P);
+            c = a.pool_count[slot];
+            thr = a.pool_thr[slot];
         }
-        if (thr) atomicMax(&sh_flag, thr);
-        if (!staged && t) atomicAdd(&sh_tot, t);
-        __syncthreads();
-        if (staged) { block_exclusive_scan(offs, a.P, scan_scratch); total = (uint32_t)offs[a.P]; }
-        else total = sh_tot;
+        offs[tid] = c;
     }
-    const uint32_t max_thr = sh_flag;
-    const bool in_smem = staged && total <= (uint32_t)item_cap;
-    if (in_smem) gather_pool(a.pool_items, q, a.P, a.cap, offs, (int)total, items);
-
-    auto each = [&](auto fn) {
-        if (in_smem) {
-            const int n_up = ((int)total + FF_THREADS - 1) / FF_THREADS * FF_THREADS;
-            for (int i = threadIdx.x; i < n_up; i += FF_THREADS) {
-                const bool valid = i < (int)total;
-                fn(valid ? items[i] : 0ull, valid);
-            }
-        } else {
-            for (int p = warp; p < a.P; p += FF_WARPS) {
-                const int64_t slot = pool_slot(q, p, a.P);
-                const int cnt = a.pool_count[slot];
-                const uint64_t* lst = a.pool_items + slot * a.cap;
-                for (int b = 0; b < cnt; b += 32) {
-                    const int i = b + lane;
-                    const bool valid = i < cnt;
-                    fn(valid ? lst[i] : 0ull, valid);
+    __syncthreads();
+    block_exclusive_scan(offs, FF_THREADS, scan_scratch);            // offs[FF_THREADS] = total
+    const int total_all = offs[FF_THREADS];
+    const int total_r = min(total_all, FF_ITEMS);                    // what does not fit voids the certificate below
+    {   // gather: warp per list round-robin would serialise on short lists; flat (list, position < 32) slots, 8 loads in flight
+        const int flat = n_lists * 32;
+        for (int base = tid; base < flat; base += FF_THREADS * 8) {
+            uint64_t v[8];
+            int dst[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * FF_THREADS;
+                dst[u] = -1;
+                if (i < flat) {
+                    const int l = i >> 5, jj = i & 31;
+                    const int o = offs[l], c = offs[l + 1] - o;
+                    if (jj < c && o + jj < FF_ITEMS) { dst[u] = o + jj; v[u] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj]; }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (dst[u] >= 0) items[dst[u]] = v[u];
         }
-    };
-
+        for (int l = warp; l < n_lists; l += FF_WARPS) {             // the rare list longer than 32
+            const int o = offs[l], c = offs[l + 1] - o;
+            for (int jj = 32 + lane; jj < c; jj += 32) if (o + jj < FF_ITEMS) items[o + jj] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj];
+        }
+    }
+    for (int i = tid; i < HIST_BINS; i += FF_THREADS) bins[i] = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) thr = max(thr, __shfl_xor_sync(0xffffffffu, thr, o));
+    if (lane == 0 && thr) atomicMax(&sh_pick, thr);                 // (sh_pick doubles as the max of pool_thr until step 2)
+    __syncthreads();
+    FF_STAMP(1);
+    {
+        uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+        for (int i = tid; i < total_r; i += FF_THREADS) { const uint32_t key = item_key(items[i]); kmin = min(kmin, key); kmax = max(kmax, key); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if (lane == 0) { atomicMin(&sh_min, kmin); atomicMax(&sh_max, kmax); }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        xch.kmin = sh_min; xch.kmax = sh_max; xch.total = (uint32_t)total_r; xch.thr = sh_pick;
+        xch.overflow = total_all > FF_ITEMS ? 1u : 0u; xch.ncand = 0; xch.bad = 0;
+        sh_pick = 0u;
+    }
+    cluster.sync();                                                  // ---- every CTA's exchange block is readable ----
+    FF_STAMP(2);
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u, total = 0, max_thr = 0, overflow = 0;
+    for (int g = 0; g < S; ++g) {
+        const FfExchange* x = cluster.map_shared_rank(&xch, g);
+        kmin = min(kmin, x->kmin); kmax = max(kmax, x->kmax); total += x->total; max_thr = max(max_thr, x->thr); overflow |= x->overflow;
+    }
+    // ---- 2. conservative k-th best of the query's pooled coarse scores --------------------------------------------------
     const uint32_t kk = min((uint32_t)a.k, total);
     uint64_t cut = 0;
     uint32_t cut_key = 0;
-    if (total > kk) {
-        const uint32_t edge = block_kth_edge<FF_THREADS>(each, kk, bins, edge_sh, edge_wsum);
+    if (total > kk) {                                                // (uniform across the cluster)
+        const uint32_t range = kmax - kmin;
+        const int shift = (range >> 12) ? (32 - __clz(range) - 12) : 0;
+        for (int i = tid; i < total_r; i += FF_THREADS) atomicAdd(&bins[(item_key(items[i]) - kmin) >> shift], 1u);
+        cluster.sync();                                              // ---- every CTA's histogram is complete ----
+        constexpr int PER = HIST_BINS / FF_THREADS;                  // 16 bins per thread, summed over the cluster
+        uint32_t h[PER];
+#pragma unroll
+        for (int jj = 0; jj < PER; ++jj) h[jj] = 0;
+        for (int g = 0; g < S; ++g) {
+            const uint4* rb = reinterpret_cast<const uint4*>(cluster.map_shared_rank(bins, g) + tid * PER);
+#pragma unroll
+            for (int jj = 0; jj < PER / 4; ++jj) {
+                const uint4 w = rb[jj];
+                h[4 * jj] += w.x; h[4 * jj + 1] += w.y; h[4 * jj + 2] += w.z; h[4 * jj + 3] += w.w;
+            }
+        }
+        uint32_t minesum = 0;
+#pragma unroll
+        for (int jj = 0; jj < PER; ++jj) minesum += h[jj];
+        uint32_t suf = minesum;                                      // suffix over lanes >= lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += t; }
+        if (lane == 0) wsum[warp] = suf;
+        __syncthreads();
+        uint32_t above = 0;
+        for (int w = warp + 1; w < FF_WARPS; ++w) above += wsum[w];
+        const uint32_t incl = above + suf, excl = incl - minesum;
+        if (incl >= kk && excl < kk) {                               // exactly one thread
+            uint32_t run = excl;
+#pragma unroll
+            for (int jj = PER - 1; jj >= 0; --jj) {
+                run += h[jj];
+                if (run >= kk) { sh_pick = (uint32_t)(tid * PER + jj); break; }
+            }
+        }
+        __syncthreads();
+        const uint32_t edge = kmin + (sh_pick << shift);
         cut_key = score_key(key_score(edge) - 2.f * a.eps[q]);
         cut = (uint64_t)cut_key << 32;
     }
-    __syncthreads();
-    each([&](uint64_t it, bool valid) {
-        const bool take = valid && it >= cut;
-        const bool take_mine = take && (item_row(it) % S == y);
-        const uint32_t m_all = __ballot_sync(0xffffffffu, take), m_mine = __ballot_sync(0xffffffffu, take_mine);
-        uint32_t base = 0;
-        if (lane == 0) {
-            if (m_all) atomicAdd(&sh_found, (uint32_t)__popc(m_all));
-            if (m_mine) base = atomicAdd(&sh_nmine, (uint32_t)__popc(m_mine));
+    FF_STAMP(3);
+    // ---- 3. my band members ------------------------------------------------------------------------------------------------
+    {
+        const int n_up = (total_r + FF_THREADS - 1) / FF_THREADS * FF_THREADS;
+        for (int i = tid; i < n_up; i += FF_THREADS) {
+            const uint64_t it = (i < total_r) ? items[i] : 0ull;
+            const bool take = (i < total_r) && it >= cut;
+            const uint32_t m = __ballot_sync(0xffffffffu, take);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(&sh_n, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t pos = base + __popc(m & lanemask_lt());
+            if (take && pos < (uint32_t)cand_max) cands[pos] = it;
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const uint32_t pos = base + __popc(m_mine & lanemask_lt());
-        if (take_mine && pos < (uint32_t)cand_max) mine[pos] = it;
-    });
-    __syncthreads();                                    // also: phase 1's shared memory is free from here on
-    const uint32_t found = sh_found;
-    const int nmine = (int)min(sh_nmine, (uint32_t)cand_max);
-    // certificate: nothing that could belong to the exact top-k was dropped upstream (every CTA of the query computes the same bit)
-    const bool uncertified = (found > (uint32_t)cand_max) || (max_thr != 0 && max_thr >= cut_key);
-
-    // ---- exact rescoring of this CTA's share: one warp per candidate, the 8 KB row staged with cp.async ----
+    }
+    __syncthreads();
+    if (tid == 0) xch.ncand = sh_n;                                  // may exceed cand_max: counted, not stored
+    cluster.sync();                                                  // ---- band members + counts readable; histograms no longer needed ----
+    FF_STAMP(4);
+    uint32_t off[FF_MAX_CLUSTER + 1];
+    off[0] = 0;
+    bool lost = false;
+    for (int g = 0; g < S; ++g) {
+        const uint32_t c = cluster.map_shared_rank(&xch, g)->ncand;
+        lost |= c > (uint32_t)cand_max;
+        off[g + 1] = off[g] + min(c, (uint32_t)cand_max);
+    }
+    const uint32_t found = off[S];
+    const int ncand = (int)min(found, (uint32_t)cand_max);
+    // certificate: nothing that could belong to the exact top-k was dropped upstream or does not fit
+    const bool uncertified = lost || found > (uint32_t)cand_max || overflow != 0 || (max_thr != 0 && max_thr >= cut_key);
+    // exact rescoring of an even share: global positions lo + warp, + 8, ... of the concatenated band lists
+    const int lo = (int)((int64_t)r * ncand / S), hi = (int)((int64_t)(r + 1) * ncand / S);
     const float* qrow = a.q32 + q * a.d_pad;
     const float band_check = MODEL_CHECK * a.eps[q];
     float* buf = rows + (size_t)warp * a.d_pad;
     const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
-    for (int c = warp; c < nmine; c += FF_WARPS) {
-        const uint64_t it = mine[c];
+    uint64_t* result0 = cluster.map_shared_rank(result, 0);
+    bool bad = false;
+    for (int c = lo + warp; c < hi; c += FF_WARPS) {
+        int g = 0;
+        while (g + 1 < S && (uint32_t)c >= off[g + 1]) ++g;
+        const uint64_t it = cluster.map_shared_rank(cands, g)[c - off[g]];
         const uint32_t row = item_row(it);
         const float* v = a.db32 + (int64_t)row * a.d_pad;
         for (int i = lane * 4; i < a.d_pad; i += 128)
@@ -608,43 +708,41 @@ finalise_fused_kernel(FinaliseArgs a, int cand_max, int item_cap) {
         acc = warp_sum(acc);
         if (lane == 0) {
             const float exact = (float)acc;
-            if (fabsf(key_score(item_key(it)) - exact) > band_check) atomicOr(&a.w_flag[q], ST_UNCERTIFIED);   // model check
-            const int pos = atomicAdd(&a.w_ncand[q], 1);
-            if (pos < cand_max) a.w_cand[q * cand_max + pos] = make_item(exact, row);
+            bad |= fabsf(key_score(item_key(it)) - exact) > band_check;      // model check
+            result0[c] = make_item(exact, row);
         }
         __syncwarp();
     }
-    // ---- completion ticket ----
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) sh_last = (atomicAdd(&a.w_ticket[q], 1) == (int)S - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!sh_last) return;
-    __threadfence();
-    // ---- sort + emit (the query's last CTA only) ----
-    const int ncand = min(__ldcg(&a.w_ncand[q]), cand_max);
-    const int flags = __ldcg(&a.w_flag[q]) | (uncertified ? ST_UNCERTIFIED : 0);
-    int m = 1;
-    while (m < ncand) m <<= 1;
-    if (m < 2) m = 2;
-    for (int c = threadIdx.x; c < m; c += FF_THREADS) sorted[c] = (c < ncand) ? __ldcg(a.w_cand + q * cand_max + c) : 0ull;
-    __syncthreads();
+    if (lane == 0 && bad) cluster.map_shared_rank(&xch, 0)->bad = 1u;      // (CTA 0's block: the others have exited by the time it is read)
+    FF_STAMP(5);
+    cluster.sync();                                                  // ---- CTA 0 holds every rescored candidate ----
+    FF_STAMP(6);
+    if (r != 0) return;
+    // ---- 4. rank by counting (items are distinct 64-bit words), emit ---------------------------------------------------------
+    const int flags = (uncertified || xch.bad) ? ST_UNCERTIFIED : 0;
+    uint64_t* sorted = cands;                                        // CTA 0's own band list is no longer needed ... by CTA 0
     if (a.self_base >= 0) {
         const uint32_t self_row = (uint32_t)(a.self_base + q);
-        for (int c = threadIdx.x; c < ncand; c += FF_THREADS)
-            if (item_row(sorted[c]) == self_row)
-                sorted[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
-        if (threadIdx.x < 32) {
-            const double s = exact_dot1(a.db32 + (int64_t)self_row * a.d_pad, qrow, a.d_pad);
-            if (threadIdx.x == 0) sh_selfkey = score_key((float)s);
+        for (int c = tid; c < ncand; c += FF_THREADS)
+            if (item_row(result[c]) == self_row)
+                result[c] = (0xFFFFFFFFull << 32) | (uint64_t)(0xFFFFFFFFu - self_row);
+        if (tid < 32) {
+            const double sd = exact_dot1(a.db32 + (int64_t)self_row * a.d_pad, qrow, a.d_pad);
+            if (tid == 0) sh_selfkey = score_key((float)sd);
         }
+        __syncthreads();
     }
-    block_sort_desc(sorted, m);
+    for (int c = tid; c < ncand; c += FF_THREADS) {
+        const uint64_t me = result[c];
+        int rank = 0;
+        for (int o = 0; o < ncand; ++o) rank += result[o] > me ? 1 : 0;
+        sorted[rank] = me;
+    }
+    __syncthreads();
+    FF_STAMP(7);
     emit_topk(a, q, sorted, ncand, sh_selfkey, flags);
-    if (threadIdx.x == 0) {
-        a.w_ncand[q] = 0; a.w_flag[q] = 0; a.w_ticket[q] = 0;       // ready for the next call
-        if (a.n_cand) atomicAdd(a.n_cand, ncand);
-    }
+    FF_STAMP(8);
+    if (tid == 0 && a.n_cand) atomicAdd(a.n_cand, ncand);
 }
 
 // Candidates per query the rescoring stage can hold: the band of the statistical certificate is a few dozen rows wide
@@ -670,7 +768,8 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     if (nq <= 0) return;
     FinaliseArgs a = a_in;
     const int cand_max = a.cand_max > 0 ? a.cand_max : finalise_cand_max(a.k, 0);
-    const int form = finalise_form(a, nq);
+    int form = finalise_form(a, nq);
+    int form_fallback = 0;
     if (form) {
         a.w_cand = static_cast<uint64_t*>(a.work);
         a.w_ticket = a.ticket;                       // zero-initialised once by the owner, self-resetting
@@ -679,26 +778,36 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     }
     const size_t offs_bytes = ((a.P <= FIN_MAX_LISTS) ? (size_t)((a.P + 4) & ~3) : 4) * sizeof(int);
     if (form == 2) {
-        // phase 1 (items + offsets + bins) and phase 2 (row staging) share one region; 64 KB keeps three CTAs on an SM
+        // phase 1 (items + bins) and phase 3 (row staging) share one region; 72 KB per CTA keeps three CTAs on an SM
         size_t region = (size_t)FF_WARPS * a.d_pad * sizeof(float);
-        if (region < (size_t)cand_max * sizeof(uint64_t)) region = (size_t)cand_max * sizeof(uint64_t);
-        const size_t fixed1 = offs_bytes + 4096 * sizeof(uint32_t);
-        if (region < fixed1 + 2048 * sizeof(uint64_t)) region = fixed1 + 2048 * sizeof(uint64_t);
-        size_t want_items = (size_t)a.P * (size_t)a.cap;
-        size_t room = (region - fixed1) / sizeof(uint64_t);
-        if (want_items > room && region < 64 * 1024) { region = 64 * 1024; room = (region - fixed1) / sizeof(uint64_t); }
-        int item_cap = (int)(want_items < room ? want_items : room) & ~1;
-        if (a.P > FIN_MAX_LISTS) item_cap = 0;
-        const size_t smem = (size_t)cand_max * sizeof(uint64_t) + region;
+        const size_t phase1 = (size_t)FF_ITEMS * sizeof(uint64_t) + HIST_BINS * sizeof(uint32_t);
+        if (region < phase1) region = phase1;
+        const size_t smem = (size_t)2 * cand_max * sizeof(uint64_t) + region;
         static int num_sms = 0;
         if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
-        // CTAs per query: as many as fit in ONE wave at three CTAs per SM, at most 16
-        int S = (int)((int64_t)3 * num_sms / nq);
-        S = S < 1 ? 1 : (S > 16 ? 16 : S);
-        cudaFuncSetAttribute(finalise_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024));
-        launch_pdl(finalise_fused_kernel, dim3((unsigned)nq, (unsigned)S), dim3(FF_THREADS), smem, st, a, cand_max, item_cap);
-        return;
+        // CTAs per query (= cluster size): as many as fit in ONE wave at three CTAs per SM, and enough that every CTA's lists fit
+        static const int sizes[] = {1, 2, 3, 4, 6, 8};
+        const int want = (int)((int64_t)3 * num_sms / nq);
+        int S = 0;
+        for (int cand : sizes) {
+            if ((a.P + cand - 1) / cand > FF_THREADS) continue;    // every CTA must be able to take its share of the lists
+            if (S == 0 || cand <= want) S = cand;
+        }                                                         // S == 0: more lists than a cluster can take -> the two-kernel form below
+        if (S) {
+            cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)S, (unsigned)nq); cfg.blockDim = dim3(FF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 2;
+            cudaLaunchKernelEx(&cfg, finalise_cluster_kernel, a, cand_max);
+            return;
+        }
     }
+    if (form == 2) form_fallback = 1;
     const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float) + 4096 * sizeof(uint32_t);
     // room for the gathered pool items: what the pools can hold, capped by the shared-memory budget
     size_t want_items = (size_t)a.P * (size_t)a.cap;
@@ -708,6 +817,7 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     item_cap = (item_cap + 1) & ~1;                  // keeps the fp32 query row behind it 16-byte aligned
     if (a.P > FIN_MAX_LISTS) item_cap = 0;
     const size_t smem = fixed + (size_t)item_cap * sizeof(uint64_t);
+    if (form_fallback) form = 1;
     if (form == 1) {
         cudaFuncSetAttribute(finalise_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<true>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);

@@ -58,7 +58,8 @@ struct __align__(8) GemmBarriers {
     uint32_t pad;
 };
 // both shapes stage 192 KB of operands
-constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t);
+constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t)
+                             + 16 + (size_t)BOOT_MAX_GRID * 8 * sizeof(float);
 static_assert(Shape<MODE_PAIR>::STAGES * Shape<MODE_PAIR>::STAGE_BYTES == Shape<MODE_FULL>::STAGES * Shape<MODE_FULL>::STAGE_BYTES, "ring sizes differ");
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in the pair's leader CTA
 
@@ -147,7 +148,6 @@ __device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const uint64_t* p) {
 __device__ __forceinline__ void st_release_gpu_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-constexpr int BOOT_PER_LANE = (BOOT_MAX_GRID * 8 + 31) / 32;      // sample scores per lane of the selecting warp
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define BOOT_STAMP(i) do { if (boot.trace && sub == 0 && lane == 0) boot.trace[(size_t)blockIdx.x * 8 + (i)] = globaltimer_ns(); } while (0)
 
@@ -175,6 +175,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint8_t* sB = smem + STAGES * A_BYTES;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + STAGES * STAGE_BYTES);
     uint32_t* whist = reinterpret_cast<uint32_t*>(bars + 1);          // [4 warps][256]
+    // [BOOT_MAX_GRID * 8] one query's threshold sample (in-kernel bootstrap), 16-byte aligned for cp.async
+    float* bsamp = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(whist + 4 * 256) + 15) & ~(uintptr_t)15);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -318,33 +320,28 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (sample_mode) {
                 // Threshold bootstrap: per tile only 8 scores are kept -- the maxima of its 8 column groups (branch-free:
                 // one max per score).  They are real scores, so the k-th best of the union over all sampled tiles is a
-                // valid lower bound of the database's k-th best.  No lists, no trims.
-                float top[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
+                // valid lower bound of the database's k-th best.  No lists, no trims.  (One tile per job.)
                 for (int t = t0; t < t1; ++t, ++it) {
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                     mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
-#pragma unroll
+#pragma unroll 1
                     for (int c = 0; c < TILE_N / 32; ++c) {
                         uint32_t v[32];
                         tc_ld32(taddr + c * 32, v);
                         tc_ld_wait();
                         const int64_t lim = n_valid - ((int64_t)t * tile_stride * TILE_N + c * 32);
+                        constexpr int G = TILE_N / 8;                          // columns per group: 32 (256-row tiles) or 16
+                        float gmax[32 / G];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float s = (i < lim) ? __uint_as_float(v[i]) : -INFINITY;
-                            constexpr int G = TILE_N / 8;                      // columns per group
-                            top[(c * 32 + i) / G] = fmaxf(top[(c * 32 + i) / G], s);
-                        }
+                        for (int g = 0; g < 32 / G; ++g) gmax[g] = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) gmax[i / G] = fmaxf(gmax[i / G], (i < lim) ? __uint_as_float(v[i]) : -INFINITY);
+#pragma unroll
+                        for (int g = 0; g < 32 / G; ++g) if (active && gmax[g] > -INFINITY && cnt < 8) list[cnt++] = make_item(gmax[g], 0u);
                     }
                     release_acc(acc);
-                }
-                if (active) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (top[j] > -INFINITY) list[cnt++] = make_item(top[j], 0u);
                 }
                 pool_count[slot] = cnt;
                 pool_thr[slot] = 0u;
@@ -395,35 +392,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 // and only then filters the tile, which has been waiting in its TMEM accumulator.  Meanwhile TMA and MMA
                 // run ahead into the ring and the second accumulator, so the exchange hides behind the second tile's
                 // HBM stream.  Replaces the separate bootstrap GEMM + threshold-select launches.
-                float top[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
                 BOOT_STAMP(0);                                   // job start
                 mbar_wait(smem_u32(&bars->tfull[0]), 0);
                 tc_fence_after();
                 BOOT_STAMP(1);                                   // first tile accumulated
                 {
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-#pragma unroll
+                    float* dst = boot.samp + ((size_t)q * gridDim.x + blockIdx.x) * 8;
+#pragma unroll 1
                     for (int c = 0; c < TILE_N / 32; ++c) {                  // the maximum of every 32-column group: one max per score
                         uint32_t v[32];
                         tc_ld32(taddr + c * 32, v);
                         tc_ld_wait();
                         const int64_t lim = n_valid - ((int64_t)t0 * tile_stride * TILE_N + c * 32);
+                        float gmax = -INFINITY;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float s = (i < lim) ? __uint_as_float(v[i]) : -INFINITY;
-                            constexpr int G = TILE_N / 8;
-                            top[(c * 32 + i) / G] = fmaxf(top[(c * 32 + i) / G], s);
-                        }
+                        for (int i = 0; i < 32; ++i) gmax = fmaxf(gmax, (i < lim) ? __uint_as_float(v[i]) : -INFINITY);
+                        if (active) dst[c] = gmax;
                     }
                 }
-                if (active) {
-                    float4* dst = reinterpret_cast<float4*>(boot.samp + ((size_t)q * gridDim.x + blockIdx.x) * 8);
-                    dst[0] = make_float4(top[0], top[1], top[2], top[3]);
-                    dst[1] = make_float4(top[4], top[5], top[6], top[7]);
-                }
-                __threadfence();
+                // (no fence per thread: the barrier orders these stores before the leader's fence + atomic below)
                 // warps that hold queries are those with sub < n_warps_on (a query's tile row is sub * 32 + lane); only they get here
                 const int n_warps_on = (int)((min(nq, (int64_t)GEMM_BM) + 31) >> 5);
                 asm volatile("bar.sync 1, %0;" :: "r"(n_warps_on * 32) : "memory");
@@ -446,37 +434,40 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         BOOT_STAMP(3);                           // (owners) every CTA has arrived
                         const int n_samp = (int)gridDim.x * 8;
                         for (int64_t qq = blockIdx.x; qq < nq; qq += gridDim.x) {
+                            // the query's sample (grid x 8 scores, ~5 KB) comes in with ONE round trip: cp.async straight
+                            // from L2 into shared memory (forty dependent register loads per lane took 20 us here)
                             const float* src = boot.samp + (size_t)qq * gridDim.x * 8;
-                            uint32_t keys[BOOT_PER_LANE];
+                            const uint32_t sdst = smem_u32(bsamp);
+                            for (int i = lane * 4; i < n_samp; i += 128)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sdst + (uint32_t)i * 4u), "l"(src + i) : "memory");
+                            asm volatile("cp.async.commit_group;" ::: "memory");
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            __syncwarp();
                             int valid_cnt = 0;
-#pragma unroll
-                            for (int j = 0; j < BOOT_PER_LANE; ++j) {
-                                const int i = j * 32 + lane;
-                                const float s = (i < n_samp) ? __ldcg(src + i) : -INFINITY;
-                                keys[j] = (s > -INFINITY) ? score_key(s) : 0u;
-                                valid_cnt += (s > -INFINITY) ? 1 : 0;
+                            uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+                            for (int i = lane; i < n_samp; i += 32) {
+                                const float s = bsamp[i];
+                                if (s > -INFINITY) { const uint32_t key = score_key(s); kmin = min(kmin, key); kmax = max(kmax, key); ++valid_cnt; }
                             }
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
+                            for (int o = 16; o > 0; o >>= 1) {
+                                valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
+                                kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                                kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+                            }
                             float t_pub = -INFINITY;
                             if (valid_cnt >= k) {
-                                // conservative k-th best: min / max of the keys, ONE pass into 256 bins spread over that range,
-                                // lower edge of the bin that holds the k-th largest -- never above it, at most one bin below
-                                uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-#pragma unroll
-                                for (int j = 0; j < BOOT_PER_LANE; ++j) if (keys[j] != 0u) { kmin = min(kmin, keys[j]); kmax = max(kmax, keys[j]); }
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) {
-                                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-                                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-                                }
+                                // conservative k-th best: ONE pass into 256 bins spread over [min, max] of the keys, lower edge of
+                                // the bin that holds the k-th largest -- never above it, at most one bin below
                                 const uint32_t range = kmax - kmin;
                                 const int shift = (range >> 8) ? (32 - __clz(range) - 8) : 0;
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) my_hist[lane * 8 + j] = 0;
                                 __syncwarp();
-#pragma unroll
-                                for (int j = 0; j < BOOT_PER_LANE; ++j) if (keys[j] != 0u) atomicAdd(&my_hist[(keys[j] - kmin) >> shift], 1u);
+                                for (int i = lane; i < n_samp; i += 32) {
+                                    const float s = bsamp[i];
+                                    if (s > -INFINITY) atomicAdd(&my_hist[(score_key(s) - kmin) >> shift], 1u);
+                                }
                                 __syncwarp();
                                 uint32_t dg, kr;
                                 warp_pick_digit(my_hist, (uint32_t)k, dg, kr);
@@ -484,6 +475,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                                 // the main pass keeps scores strictly above the threshold: that edge, minus the band
                                 t_pub = nextafterf(key_score(kmin + (dg << shift)) - 2.f * eps[qq], -INFINITY);
                             }
+                            BOOT_STAMP(7);                       // (owners) own threshold selected
                             if (lane == 0) {
                                 st_release_gpu_u64(boot.thr_pub + qq, ((uint64_t)boot.epoch << 32) | (uint64_t)__float_as_uint(t_pub));
                                 __threadfence();

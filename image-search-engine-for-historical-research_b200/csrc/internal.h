@@ -130,6 +130,7 @@ struct FinaliseArgs {
     int cand_max;               // candidates per query that can be rescored (power of two); 0 = default for k
     uint64_t* w_cand; int* w_ncand; int* w_flag; int* w_ticket;   // carved out by launch_finalise
     PushTarget push;
+    unsigned long long* trace;  // optional [nq * ctas_per_query][10] globaltimer stamps of the fused form (debugging)
 };
 int  finalise_cand_max(int k, int mode);                  // mode 0: statistical band, 1: worst-case band (more candidates)
 size_t finalise_work_bytes(int64_t nq, int k, int cand_max);

@@ -277,9 +277,10 @@ XS_API int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* ind
  */
 XS_API int xs_set_param(xs_index* index, const char* name, double value);
 
-/* Debugging aid (after xs_set_param "boot_trace" 1): per-CTA globaltimer stamps [grid][8] of the last GEMM launch that
- * bootstrapped its threshold in-kernel; *grid receives the CTA count (0 if none was recorded). */
-XS_API int xs_debug_boot_trace(xs_index* index, unsigned long long* out, int max_ctas, int* grid);
+/* Debugging aid (after xs_set_param "boot_trace" 1): per-CTA globaltimer stamps of the last small-batch search --
+ * which = 0: the GEMM launch that bootstrapped its threshold in-kernel, rows of 8; which = 1: the fused finalise
+ * launch, rows of 10.  *rows receives the number of rows copied (0 if nothing was recorded). */
+XS_API int xs_debug_trace(xs_index* index, int which, unsigned long long* out, int max_rows, int* rows);
 
 #ifdef __cplusplus
 }

@@ -61,18 +61,22 @@ for n in (125_875, 1_007_000):
     for _ in range(5):
         ix.search_device(queries.data_ptr(), 70, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
     torch.cuda.synchronize()
-    buf = np.zeros((160, 8), dtype=np.uint64)
-    g = C.c_int(0)
-    nat.check(nat.load().xs_debug_boot_trace(ix._h, buf.ctypes.data, 160, C.byref(g)), "trace")
-    t = buf[: g.value].astype(np.int64)
-    t0 = t[:, 0].min()
-    rel = (t - t0) / 1e3
-    names = ["start", "tile1", "arrived", "all_arrived(owner)", "thr_out", "acc0_released", "done"]
-    print(f"bootstrap timeline, {n} rows, {g.value} CTAs (us after the first CTA's start): ", flush=True)
-    for j, nm in enumerate(names):
-        col = rel[:, j][t[:, j] > 0]
-        if col.size:
-            print(f"  {nm:20s} min {col.min():7.1f}  median {np.median(col):7.1f}  max {col.max():7.1f}   ({col.size} CTAs)")
+    for which, width, names in ((0, 8, ["start", "tile1", "arrived", "all_arrived(owner)", "thr_out", "acc0_released", "done", "own_thr_selected(owner)"]),
+                                (1, 10, ["start", "sizes", "gathered", "cut", "collected", "rescored", "ticket", "sorted(last)", "emitted(last)"])):
+        buf = np.zeros((2048, width), dtype=np.uint64)
+        g = C.c_int(0)
+        nat.check(nat.load().xs_debug_trace(ix._h, which, buf.ctypes.data, 2048, C.byref(g)), "trace")
+        t = buf[: g.value].astype(np.int64)
+        t = t[t[:, 0] > 0]
+        if not len(t):
+            continue
+        t0 = t[:, 0].min()
+        rel = (t - t0) / 1e3
+        print(f"{'bootstrap GEMM' if which == 0 else 'fused finalise'} timeline, {n} rows, {len(t)} CTAs (us after the first CTA's start): ", flush=True)
+        for j, nm in enumerate(names):
+            col = rel[:, j][t[:, j] > 0]
+            if col.size:
+                print(f"  {nm:24s} min {col.min():7.1f}  median {np.median(col):7.1f}  max {col.max():7.1f}   ({col.size} CTAs)")
     ix.close()
     del rows
     torch.cuda.empty_cache()
