@@ -492,8 +492,8 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
 // grid (S, nq), cluster (S, 1, 1).  The S CTAs of a query split its partial lists between them and meet through
 // distributed shared memory:
 //   1. every CTA gathers ITS lists (p = rank, rank + S, ...) into shared memory, finds their min / max key;
-//   2. cluster barrier; the global min / max come from the S exchange blocks; every CTA fills a 4096-bin histogram of its
-//      items over that range; cluster barrier; every thread sums its 16 bins over the S CTAs (DSMEM reads) and the usual
+//   2. cluster barrier; the global min / max come from the S exchange blocks; every CTA fills a 1024-bin histogram of its
+//      items over that range; cluster barrier; every thread sums its 4 bins over the S CTAs (DSMEM reads) and the usual
 //      suffix scan gives the conservative k-th best and the cut of the band -- the same value in all CTAs;
 //   3. every CTA collects its items inside the band; cluster barrier; the band members are dealt evenly: warp w of CTA r
 //      takes global positions r * found / S + w, + 8, ..., fetches the item from whichever CTA holds it (DSMEM), rescores it
@@ -505,6 +505,10 @@ finalise_rescore_emit_kernel(FinaliseArgs a, int cand_max) {
 constexpr int FF_THREADS = 256, FF_WARPS = FF_THREADS / 32;
 constexpr int FF_ITEMS = 2048;               // pooled items one CTA of the cluster can hold
 constexpr int FF_MAX_CLUSTER = 8;
+// Histogram of the cluster form: 1024 bins over [min, max] of the query's pooled keys.  The pooled scores span a few
+// hundredths, so a bin is ~5e-5 wide -- far inside the band -- and a CTA's histogram is 4 KB: distributed shared memory
+// moves ~20 bytes per cycle and SM, and every CTA reads every other CTA's histogram (4096 bins cost 30 us here).
+constexpr int FF_BIN_BITS = 10, FF_BINS = 1 << FF_BIN_BITS;
 __device__ __forceinline__ unsigned long long ff_timer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define FF_STAMP(i) do { if (a.trace && threadIdx.x == 0) a.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 10 + (i)] = ff_timer(); } while (0)
 
@@ -519,7 +523,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
     extern __shared__ uint64_t ff_smem[];
     uint64_t* cands = ff_smem;                          // [cand_max] this CTA's band members
     uint64_t* result = ff_smem + cand_max;              // [cand_max] (CTA 0's copy collects the cluster's rescored candidates)
-    uint64_t* items = ff_smem + 2 * cand_max;           // phase 1: [FF_ITEMS] gathered pool items | 4096 bins
+    uint64_t* items = ff_smem + 2 * cand_max;           // phase 1: [FF_ITEMS] gathered pool items | FF_BINS bins
     uint32_t* bins = reinterpret_cast<uint32_t*>(items + FF_ITEMS);
     float* rows = reinterpret_cast<float*>(ff_smem + 2 * cand_max);      // phase 3 (aliases phase 1): [FF_WARPS][d_pad] row staging
     __shared__ FfExchange xch;
@@ -573,7 +577,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
             for (int jj = 32 + lane; jj < c; jj += 32) if (o + jj < FF_ITEMS) items[o + jj] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj];
         }
     }
-    for (int i = tid; i < HIST_BINS; i += FF_THREADS) bins[i] = 0;
+    for (int i = tid; i < FF_BINS; i += FF_THREADS) bins[i] = 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) thr = max(thr, __shfl_xor_sync(0xffffffffu, thr, o));
     if (lane == 0 && thr) atomicMax(&sh_pick, thr);                 // (sh_pick doubles as the max of pool_thr until step 2)
@@ -608,10 +612,10 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
     uint32_t cut_key = 0;
     if (total > kk) {                                                // (uniform across the cluster)
         const uint32_t range = kmax - kmin;
-        const int shift = (range >> 12) ? (32 - __clz(range) - 12) : 0;
+        const int shift = (range >> FF_BIN_BITS) ? (32 - __clz(range) - FF_BIN_BITS) : 0;
         for (int i = tid; i < total_r; i += FF_THREADS) atomicAdd(&bins[(item_key(items[i]) - kmin) >> shift], 1u);
         cluster.sync();                                              // ---- every CTA's histogram is complete ----
-        constexpr int PER = HIST_BINS / FF_THREADS;                  // 16 bins per thread, summed over the cluster
+        constexpr int PER = FF_BINS / FF_THREADS;                    // 4 bins per thread (one 16-byte DSMEM read per CTA), summed over the cluster
         uint32_t h[PER];
 #pragma unroll
         for (int jj = 0; jj < PER; ++jj) h[jj] = 0;
@@ -780,7 +784,7 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     if (form == 2) {
         // phase 1 (items + bins) and phase 3 (row staging) share one region; 72 KB per CTA keeps three CTAs on an SM
         size_t region = (size_t)FF_WARPS * a.d_pad * sizeof(float);
-        const size_t phase1 = (size_t)FF_ITEMS * sizeof(uint64_t) + HIST_BINS * sizeof(uint32_t);
+        const size_t phase1 = (size_t)FF_ITEMS * sizeof(uint64_t) + FF_BINS * sizeof(uint32_t);
         if (region < phase1) region = phase1;
         const size_t smem = (size_t)2 * cand_max * sizeof(uint64_t) + region;
         static int num_sms = 0;

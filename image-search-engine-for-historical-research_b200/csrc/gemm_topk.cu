@@ -145,8 +145,13 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 __device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const uint64_t* p) {
     uint64_t v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ void st_release_gpu_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_gpu_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// counter += v with release semantics: everything this thread wrote (and observed through a CTA barrier) before it is
+// visible to whoever acquires the new count -- one operation instead of fence + atomic
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define BOOT_STAMP(i) do { if (boot.trace && sub == 0 && lane == 0) boot.trace[(size_t)blockIdx.x * 8 + (i)] = globaltimer_ns(); } while (0)
@@ -416,10 +421,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 const int n_warps_on = (int)((min(nq, (int64_t)GEMM_BM) + 31) >> 5);
                 asm volatile("bar.sync 1, %0;" :: "r"(n_warps_on * 32) : "memory");
                 if (sub == 0) {                                  // the warp that holds queries 0..31 (TMEM sub-partition 0): always populated
-                    if (lane == 0) {
-                        __threadfence();
-                        atomicAdd(boot.arrive, 1u);
-                    }
+                    if (lane == 0) red_release_gpu_add(boot.arrive, 1u);
                     BOOT_STAMP(2);                               // sample written, arrival posted
                     if ((int64_t)blockIdx.x < nq) {
                         // (B) this CTA owns queries blockIdx.x, blockIdx.x + grid, ...
@@ -477,9 +479,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             }
                             BOOT_STAMP(7);                       // (owners) own threshold selected
                             if (lane == 0) {
-                                st_release_gpu_u64(boot.thr_pub + qq, ((uint64_t)boot.epoch << 32) | (uint64_t)__float_as_uint(t_pub));
-                                __threadfence();
-                                atomicAdd(boot.published, 1u);
+                                st_relaxed_gpu_u64(boot.thr_pub + qq, ((uint64_t)boot.epoch << 32) | (uint64_t)__float_as_uint(t_pub));
+                                red_release_gpu_add(boot.published, 1u);
                             }
                         }
                     }
