@@ -406,6 +406,8 @@ def run_ours(args):
             exchange = sharded.PeerExchange(local, N_QUERIES, TOPK)
         except RuntimeError as e:
             print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
+    if args.lanes == 0:
+        args.lanes = 2 if (world > 1 and not replicas) else 1
     shard, searcher = sharded.make_searcher(index, local, lanes=args.lanes, exchange=exchange)
     if replicas:
         searcher.world = 1                                     # no exchange step at all
@@ -604,9 +606,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="N=1: skip the cfg3 (batch-1) and 4096-query sub-records")
-    ap.add_argument("--lanes", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--lanes", type=int, default=0, choices=[0, 1, 2],
                     help="search lanes per GPU in the pipelined (value) loop: 2 = consecutive batches alternate between the index "
-                         "and a workspace clone on two streams, so one batch's selection/rescoring overlaps the next batch's scan")
+                         "and a workspace clone on two streams, so one batch's tail and exchange overlap the next batch's scan; "
+                         "0 (default) = 1 lane on one GPU (the scan holds every SM: nothing to overlap with), 2 lanes when sharded")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1, row sharding: how the per-shard lists meet -- peer (= auto): the search's last kernel stores them into "
                          "every rank's mailbox and the merge kernel waits on per-query flags; nccl: all-gather + merge kernel")

@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "xs_index_destroy", "xs_index_clone", "xs_index_info", "xs_index_stats", "xs_search", "xs_search_dev", "xs_self_knn",
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
     "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
-    "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_trace",
+    "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_trace", "xs_index_save", "xs_index_load",
 )
 
 
@@ -57,6 +57,8 @@ def load() -> C.CDLL:
         lib.xs_index_create.argtypes = [p, i32, i64, i32, i64, i64, i32, i32, i64, C.POINTER(p)]
         lib.xs_index_create_dev.argtypes = [p, i64, i32, i32, i32, i64, C.POINTER(p)]
         lib.xs_index_destroy.argtypes = [p]
+        lib.xs_index_save.argtypes = [p, C.c_char_p]
+        lib.xs_index_load.argtypes = [C.c_char_p, i32, i64, C.POINTER(p)]
         lib.xs_index_clone.argtypes = [p, C.POINTER(p)]
         lib.xs_index_info.argtypes = [p, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
         lib.xs_index_stats.argtypes = [p, C.POINTER(XsStats)]

@@ -12,7 +12,10 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/xs_b200.h"
 #include "common.cuh"
@@ -320,6 +323,159 @@ extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int de
     cudaError_t e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); index_free(ix); return rc; }
     rc = build_tiled_twin(ix);
+    if (rc != XS_OK) { index_free(ix); return rc; }
+    *out = ix;
+    return XS_OK;
+}
+
+// ---- on-disk image of an index: what lives in HBM, byte for byte -------------------------------------------------------
+// File = 4 KB header | db32 [n][d_pad] fp32 | db16 [n_pad][d_pad] bf16 | db16t (same bytes, tiled) -- sections 4 KB
+// aligned.  Loading is then a straight upload: reader threads pread() slices of the file into a ring of pinned buffers and
+// every slice goes out with its own cudaMemcpyAsync as soon as it is staged; no transpose, no conversion, no tiling kernel
+// (the reference unpickles, concatenates and transposes on every start, src/online.py:93-102).
+namespace {
+struct IndexFileHeader {
+    char magic[8];               // "XSB200\0\1"
+    uint32_t version, flags;     // flags: 1 rotate, 2 has tiled twin
+    int64_t n, n_pad;
+    int32_t d, d_pad;
+    uint32_t rot_seed, pad0;
+    DevStats stats; uint32_t pad1;
+    uint64_t off32, off16, off16t, bytes32, bytes16;
+};
+constexpr size_t FILE_ALIGN = 4096;
+constexpr size_t STAGE_BYTES_IO = (size_t)32 << 20;
+constexpr int STAGE_RING = 4, IO_THREADS = 8;
+
+struct StageRing {               // pinned staging shared by save / load (one transfer at a time)
+    std::mutex mu;
+    void* buf[STAGE_RING] = {};
+    cudaEvent_t ev[STAGE_RING] = {};
+    bool ready = false;
+    int ensure() {
+        if (ready) return XS_OK;
+        for (int i = 0; i < STAGE_RING; ++i) {
+            CU_TRY(cudaMallocHost(&buf[i], STAGE_BYTES_IO));
+            CU_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return XS_OK;
+    }
+};
+StageRing g_ring;
+
+// fn(part_offset, part_bytes, dst/src pointer inside the pinned buffer) on IO_THREADS threads
+template <typename F>
+bool parallel_parts(size_t bytes, char* pinned, F fn) {
+    std::vector<std::thread> th;
+    std::vector<int> ok(IO_THREADS, 1);
+    const size_t part = ((bytes + IO_THREADS - 1) / IO_THREADS + 4095) & ~(size_t)4095;
+    for (int t = 0; t < IO_THREADS; ++t) {
+        const size_t lo = (size_t)t * part;
+        if (lo >= bytes) break;
+        const size_t nb = std::min(part, bytes - lo);
+        th.emplace_back([&, t, lo, nb] { ok[t] = fn(lo, nb, pinned + lo) ? 1 : 0; });
+    }
+    for (auto& x : th) x.join();
+    for (int v : ok) if (!v) return false;
+    return true;
+}
+
+bool pread_all(int fd, void* dst, size_t nb, off_t off) {
+    char* p = static_cast<char*>(dst);
+    while (nb) { const ssize_t r = pread(fd, p, nb, off); if (r <= 0) return false; p += r; off += r; nb -= (size_t)r; }
+    return true;
+}
+bool pwrite_all(int fd, const void* src, size_t nb, off_t off) {
+    const char* p = static_cast<const char*>(src);
+    while (nb) { const ssize_t r = pwrite(fd, p, nb, off); if (r <= 0) return false; p += r; off += r; nb -= (size_t)r; }
+    return true;
+}
+
+// file section -> device array
+int upload_section(int fd, uint64_t off, void* dev, size_t bytes, cudaStream_t st) {
+    for (size_t done = 0, i = 0; done < bytes; done += STAGE_BYTES_IO, ++i) {
+        const int slot = (int)(i % STAGE_RING);
+        const size_t nb = std::min(STAGE_BYTES_IO, bytes - done);
+        CU_TRY(cudaEventSynchronize(g_ring.ev[slot]));               // the copy that last used this buffer has left it
+        if (!parallel_parts(nb, static_cast<char*>(g_ring.buf[slot]), [&](size_t lo, size_t n2, char* dst) { return pread_all(fd, dst, n2, (off_t)(off + done + lo)); }))
+            return fail(XS_ERR_ARG, "short read from the index file");
+        CU_TRY(cudaMemcpyAsync(static_cast<char*>(dev) + done, g_ring.buf[slot], nb, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaEventRecord(g_ring.ev[slot], st));
+    }
+    return XS_OK;
+}
+// device array -> file section
+int download_section(int fd, uint64_t off, const void* dev, size_t bytes, cudaStream_t st) {
+    for (size_t done = 0; done < bytes; done += STAGE_BYTES_IO) {
+        const size_t nb = std::min(STAGE_BYTES_IO, bytes - done);
+        CU_TRY(cudaMemcpyAsync(g_ring.buf[0], static_cast<const char*>(dev) + done, nb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if (!parallel_parts(nb, static_cast<char*>(g_ring.buf[0]), [&](size_t lo, size_t n2, char* src) { return pwrite_all(fd, src, n2, (off_t)(off + done + lo)); }))
+            return fail(XS_ERR_ARG, "short write to the index file");
+    }
+    return XS_OK;
+}
+}  // namespace
+
+extern "C" int xs_index_save(xs_index* ix, const char* path) {
+    if (!ix || !path) return fail(XS_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> lk2(g_ring.mu);
+    CU_TRY(cudaSetDevice(ix->device));
+    XS_TRY(g_ring.ensure());
+    IndexFileHeader h{};
+    memcpy(h.magic, "XSB200\0\1", 8);
+    h.version = 1; h.flags = (ix->rotate ? 1u : 0u) | (ix->db16t ? 2u : 0u);
+    h.n = ix->n; h.n_pad = ix->n_pad; h.d = ix->d; h.d_pad = ix->d_pad; h.rot_seed = ix->rot_seed;
+    CU_TRY(cudaMemcpy(&h.stats, ix->dstats, sizeof(DevStats), cudaMemcpyDeviceToHost));
+    h.bytes32 = (uint64_t)ix->n * ix->d_pad * 4; h.bytes16 = (uint64_t)ix->n_pad * ix->d_pad * 2;
+    h.off32 = FILE_ALIGN;
+    h.off16 = (h.off32 + h.bytes32 + FILE_ALIGN - 1) / FILE_ALIGN * FILE_ALIGN;
+    h.off16t = (h.off16 + h.bytes16 + FILE_ALIGN - 1) / FILE_ALIGN * FILE_ALIGN;
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(XS_ERR_ARG, "cannot create %s", path);
+    char page[FILE_ALIGN] = {};
+    memcpy(page, &h, sizeof h);
+    int rc = pwrite_all(fd, page, FILE_ALIGN, 0) ? XS_OK : fail(XS_ERR_ARG, "cannot write %s", path);
+    if (rc == XS_OK) rc = download_section(fd, h.off32, ix->db32, h.bytes32, ix->stream);
+    if (rc == XS_OK) rc = download_section(fd, h.off16, ix->db16, h.bytes16, ix->stream);
+    if (rc == XS_OK && ix->db16t) rc = download_section(fd, h.off16t, ix->db16t, h.bytes16, ix->stream);
+    close(fd);
+    return rc;
+}
+
+extern "C" int xs_index_load(const char* path, int device, int64_t id_offset, xs_index** out) {
+    if (!path || !out) return fail(XS_ERR_ARG, "null pointer");
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(XS_ERR_ARG, "cannot open %s", path);
+    IndexFileHeader h{};
+    if (!pread_all(fd, &h, sizeof h, 0) || memcmp(h.magic, "XSB200\0\1", 8) != 0 || h.version != 1) { close(fd); return fail(XS_ERR_ARG, "%s is not an index file of this library", path); }
+    std::lock_guard<std::mutex> lk2(g_ring.mu);
+    xs_index* ix = new xs_index();
+    int rc = index_alloc(ix, h.n, h.d, device, id_offset);
+    if (rc == XS_OK && (ix->d_pad != h.d_pad || ix->n_pad != h.n_pad)) rc = fail(XS_ERR_ARG, "%s was written with another padding", path);
+    if (rc == XS_OK) rc = g_ring.ensure();
+    if (rc == XS_OK) {
+        ix->rotate = (h.flags & 1u) != 0; ix->rot_seed = h.rot_seed;
+        cudaError_t e = cudaMemcpyAsync(ix->dstats, &h.stats, sizeof(DevStats), cudaMemcpyHostToDevice, ix->stream);
+        if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "xs_index_load: %s", cudaGetErrorString(e));
+    }
+    if (rc == XS_OK) rc = upload_section(fd, h.off32, ix->db32, h.bytes32, ix->stream);
+    if (rc == XS_OK) rc = upload_section(fd, h.off16, ix->db16, h.bytes16, ix->stream);
+    if (rc == XS_OK && (h.flags & 2u)) {
+        const char* e = getenv("XS_NO_TILED");
+        if (!(e && atoi(e)) && cudaMalloc(&ix->db16t, h.bytes16) == cudaSuccess) {
+            ix->share->db16t = ix->db16t;
+            rc = upload_section(fd, h.off16t, ix->db16t, h.bytes16, ix->stream);
+            if (rc == XS_OK) rc = make_tmap_tiled(&ix->tmap_dbt_b, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BN);
+            if (rc == XS_OK) rc = make_tmap_tiled(&ix->tmap_dbt_h, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BM);
+            if (rc == XS_OK) ix->bytes += (int64_t)h.bytes16;
+        } else { cudaGetLastError(); ix->db16t = nullptr; }
+    }
+    close(fd);
+    if (rc == XS_OK) { cudaError_t e = cudaStreamSynchronize(ix->stream); if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "xs_index_load: %s", cudaGetErrorString(e)); }
+    if (rc == XS_OK && !(h.flags & 2u)) rc = build_tiled_twin(ix);
     if (rc != XS_OK) { index_free(ix); return rc; }
     *out = ix;
     return XS_OK;

@@ -41,6 +41,22 @@ class ExactIndex:
                   "xs_index_create_dev")
         return self
 
+    def save(self, path: str):
+        """Write the device arrays as they are (xs_index_save); ``ExactIndex.load`` brings them back with plain copies."""
+        nat.check(self._lib.xs_index_save(self._h, str(path).encode()), "xs_index_save")
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, id_offset: int = 0):
+        """An index from its on-disk image (xs_index_load): pinned, multi-threaded, double-buffered upload; no kernels."""
+        self = cls.__new__(cls)
+        self._lib = nat.load()
+        self._h = C.c_void_p()
+        nat.check(self._lib.xs_index_load(str(path).encode(), int(device), int(id_offset), C.byref(self._h)), "xs_index_load")
+        n, d = C.c_int64(), C.c_int()
+        nat.check(self._lib.xs_index_info(self._h, C.byref(n), C.byref(d), None, None), "xs_index_info")
+        self.N, self.D, self.device, self.renormalised = int(n.value), int(d.value), int(device), False
+        return self
+
     def clone(self) -> "ExactIndex":
         """A second search lane over the same device-resident database (xs_index_clone): shares the database
         arrays, owns its workspaces -- searches on ``self`` and on the clone may overlap on two streams."""

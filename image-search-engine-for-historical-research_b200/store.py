@@ -19,6 +19,7 @@ import numpy as np
 
 ROWS_FILE = "rows.npy"
 PATHS_FILE = "paths.json"
+INDEX_FILE = "index.xsb"          # device image: fp32 rows + bf16 rows + tiled twin, as they live in HBM (xs_index_save)
 
 
 def save_store(directory: str, vecs, paths=None, chunk: int = 65536) -> str:
@@ -98,8 +99,20 @@ def append_store(directory: str, vecs, paths=None, chunk: int = 65536) -> str:
     return directory
 
 
-def index_from_store(directory: str, renormalise: bool = False, device: int = 0):
-    """Device index straight from the mapped rows (uploaded in 8k-row tiles by xs_index_create)."""
+def index_from_store(directory: str, renormalise: bool = False, device: int = 0, image: bool = True):
+    """Device index of a store.  The first call builds it from the mapped rows and (``image=True``) writes the device
+    image next to them; later calls upload that image as it is -- no layout / convert / tile kernels, pinned
+    double-buffered copies at PCIe speed (xs_index_load).  The image is tied to ``renormalise`` and to the rows file's
+    modification time."""
     from .index import ExactIndex
     rows, paths = open_store(directory)
-    return ExactIndex(rows, renormalise=renormalise, device=device), paths
+    img = os.path.join(directory, INDEX_FILE + (".n" if renormalise else ""))
+    rows_path = os.path.join(directory, ROWS_FILE)
+    if image and os.path.exists(img) and os.path.getmtime(img) >= os.path.getmtime(rows_path):
+        ix = ExactIndex.load(img, device=device)
+        ix.renormalised = bool(renormalise)
+        return ix, paths
+    ix = ExactIndex(rows, renormalise=renormalise, device=device)
+    if image:
+        ix.save(img)
+    return ix, paths

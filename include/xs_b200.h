@@ -95,6 +95,17 @@ XS_API int xs_index_create_dev(const float* db_dev, int64_t n, int d,
 XS_API int xs_index_destroy(xs_index* index);
 
 /*
+ * On-disk image of an index: the arrays exactly as they live in HBM (fp32 rows, bf16 rows of the rotated vectors and their
+ * tiled twin, the statistics behind the error band, the rotation seed).
+ *   replaces: save_path_feature / load_path_features pickles and the .pt distractor file      src/utils/general.py:67-92
+ *             + the unpickle / concatenate / transpose of every start-up                       src/online.py:93-102
+ * xs_index_load is a straight upload -- reader threads fill a ring of pinned buffers, one cudaMemcpyAsync per 32 MB slice,
+ * no layout, conversion or tiling kernel -- and yields an index indistinguishable from the one that was saved.
+ */
+XS_API int xs_index_save(xs_index* index, const char* path);
+XS_API int xs_index_load(const char* path, int device, int64_t id_offset, xs_index** out);
+
+/*
  * A second search lane over the same database (no reference counterpart).  The clone shares the read-only
  * database arrays of `src` (they are freed when the last of the index and its clones is destroyed, in any
  * order) and owns its workspaces, stream, tunables and statistics, so searches on the index and on the clone
