@@ -408,8 +408,11 @@ def run_ours(args):
             print(f"rank {rank}: {e}; falling back to the NCCL all-gather", file=sys.stderr)
     if args.lanes == 0:
         args.lanes = 2 if (world > 1 and not replicas) else 1
-    shard, searcher = sharded.make_searcher(index, local, lanes=args.lanes, exchange=exchange)
-    if replicas:
+    # the hot loop goes through the native two-slot pipeline (one C call per step) unless the NCCL exchange was asked for
+    native = (world == 1 or replicas or exchange is not None) and not args.python_loop
+    shard, searcher = sharded.make_searcher(index, local, lanes=args.lanes, exchange=exchange,
+                                            pipeline=(N_QUERIES, TOPK) if native else None)
+    if replicas and not native:
         searcher.world = 1                                     # no exchange step at all
 
     def barrier():
@@ -561,7 +564,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg2: 1,007,000 x 2048 DB (unit-norm Gaussian, seed 0), 70-query batch, exact top-100",
                    "rows_per_gpu": shard_rows, "lanes": args.lanes, "sharding": how,
-                   "value_loop": "two 70-query batches in flight (two lanes per GPU); every result's certificate words are read back and flagged queries re-run before it counts",
+                   "value_loop": ("native two-slot pipeline (xs_pipeline_submit / _collect: one C call enqueues search + exchange + merge + certificate read-back)" if native else "Python-driven ShardedSearcher")
+                                 + f", two 70-query batches in flight on {args.lanes} lane(s); every result's certificate words are read back and flagged queries re-run before it counts",
                    "l2": "inputs larger than L2 (4.1 GB bf16 database per pass vs 126 MB L2)",
                    "arithmetic": "bf16 operands / fp32 accumulate (tcgen05) for the coarse pass, then fp32 operands / fp64 accumulate exact rescoring of ~120 candidates per query",
                    "path": {1: "scan", 2: "tcgen05 GEMM + fused top-K", 3: "exact"}.get(stats["path"], "?"),
@@ -605,6 +609,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--python-loop", action="store_true", help="drive the value loop call by call from Python (ShardedSearcher) instead of xs_pipeline_*")
     ap.add_argument("--no-extra-configs", action="store_true", help="N=1: skip the cfg3 (batch-1) and 4096-query sub-records")
     ap.add_argument("--lanes", type=int, default=0, choices=[0, 1, 2],
                     help="search lanes per GPU in the pipelined (value) loop: 2 = consecutive batches alternate between the index "

@@ -24,6 +24,7 @@ ABI_SYMBOLS = (
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
     "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
     "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_trace", "xs_index_save", "xs_index_load",
+    "xs_pipeline_create", "xs_pipeline_submit", "xs_pipeline_collect", "xs_pipeline_destroy",
 )
 
 
@@ -83,6 +84,10 @@ def load() -> C.CDLL:
         lib.xs_exchange_push.argtypes = [p, p, i64, i32, i32, p]
         lib.xs_exchange_merge.argtypes = [p, i32, i64, i32, p, p, p, p]
         lib.xs_exchange_destroy.argtypes = [p]
+        lib.xs_pipeline_create.argtypes = [p, p, i64, i32, i32, C.POINTER(p)]
+        lib.xs_pipeline_submit.argtypes = [p, p, i64, i32, p, C.POINTER(i32)]
+        lib.xs_pipeline_collect.argtypes = [p, i32, p, C.POINTER(p), C.POINTER(p), C.POINTER(i64), p]
+        lib.xs_pipeline_destroy.argtypes = [p]
         for name in ABI_SYMBOLS:
             if name not in ("xs_last_error", "xs_exchange_part_bytes"):
                 getattr(lib, name).restype = i32

@@ -225,6 +225,22 @@ XS_API int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64
 XS_API int xs_exchange_destroy(xs_exchange* ex);
 
 /*
+ * Two-slot pipeline for the sharded (or single-shard) search: ONE host call enqueues a whole step -- local search with the
+ * exchange's sending end fused in, merge, copy of the merged certificate words to pinned memory -- on one of two lane
+ * streams (lanes = 2: the second lane is an internal clone of the index); a second call waits for the step and returns
+ * device pointers to the merged [nq, k] result (valid until the slot's next submit) and the uncertified queries, which
+ * the caller re-runs (collectively when sharded: every rank sees the same merged certificate words).  At most two steps
+ * in flight; with an exchange every rank submits and collects in the same order.  ex may be NULL (no exchange step).
+ * (No reference counterpart: it exists because at eight GPUs a step is shorter than the host work of driving it.)
+ */
+typedef struct xs_pipeline xs_pipeline;
+XS_API int xs_pipeline_create(xs_index* index, xs_exchange* ex, int64_t nq_max, int k_max, int lanes, xs_pipeline** out);
+XS_API int xs_pipeline_submit(xs_pipeline* p, const float* q_dev, int64_t nq, int k, void* caller_stream, int* slot_out);
+XS_API int xs_pipeline_collect(xs_pipeline* p, int slot, void* caller_stream, int64_t** out_idx_dev, float** out_score_dev,
+                               int64_t* n_flagged, int32_t* flagged);
+XS_API int xs_pipeline_destroy(xs_pipeline* p);
+
+/*
  * Mutual-kNN test of the diffusion affinity graph.
  *   replaces: the per-row loop `np.isin(ids[ids[i]], i).any(axis=1)` of get_affinity   src/utils/diffusion.py:106-108
  * ids: HOST [n, kd] int64, the kNN lists of every row (slot 0 = the row itself, as xs_self_knn returns them).

@@ -76,6 +76,27 @@ def main():
     for h in (h1, h2, h3):
         assert np.array_equal(h.result()[0].cpu().numpy(), want_i)
     assert peer.n_rerun == 0
+    # the native two-slot pipeline (xs_pipeline_*: one C call per step) over its own mailboxes: same answers
+    ex_p = sharded.PeerExchange(local, 70, 100)
+    _, pipe = sharded.make_searcher(index, local, lanes=2, exchange=ex_p, pipeline=(70, 100))
+    for nq, k in ((70, 100), (1, 100), (33, 7)):
+        gi, gs = [t.cpu().numpy().copy() for t in pipe.search(q_all[:nq].contiguous(), k)]
+        wi, ws = [t.cpu().numpy().copy() for t in peer.search(q_all[:nq].contiguous(), k)]
+        assert np.array_equal(gi, wi) and np.array_equal(gs, ws), f"rank {rank}: pipeline != searcher at nq={nq} k={k}"
+    pending = None
+    for it in range(30):
+        if it % 5 == rank:
+            torch.cuda._sleep(10_000_000)
+        nxt = pipe.search_async(q, 100)
+        if pending is not None:
+            assert np.array_equal(pending.result()[0].cpu().numpy(), want_i), f"rank {rank}: native pipeline step {it}"
+        pending = nxt
+    assert np.array_equal(pending.result()[0].cpu().numpy(), want_i)
+    h1, h2, h3 = pipe.search_async(q, 100), pipe.search_async(q, 100), pipe.search_async(q, 100)     # the third collects the first itself
+    for h in (h1, h2, h3):
+        assert np.array_equal(h.result()[0].cpu().numpy(), want_i)
+    pipe.close()
+    ex_p.close()
     index.close()
 
     # families where shards cannot certify every query: the certificate words travel with the lists and the flagged
@@ -86,7 +107,7 @@ def main():
         b2 = sharded.shard_bounds(n2, world)
         ix2 = pkg.ExactIndex(np.ascontiguousarray(v2.T[b2[rank]:b2[rank + 1]]), device=local, id_offset=b2[rank])
         ex2 = sharded.PeerExchange(local, q2.shape[1], k)
-        _, s2 = sharded.make_searcher(ix2, local, exchange=ex2)
+        _, s2 = sharded.make_searcher(ix2, local, exchange=ex2, pipeline=(q2.shape[1], k) if name == "crowded" else None)
         qd = torch.from_numpy(np.ascontiguousarray(q2.T)).to(dev)
         for _ in range(2):
             gi, gs = [t.cpu().numpy().copy() for t in s2.search(qd, k)]

@@ -36,6 +36,17 @@ def test_exchange_single_rank(pkg, synth, oracle):
         np.testing.assert_allclose(sims, ref_s[:nq, :k], rtol=1e-5, atol=1e-7)
     a, b = searcher.search_async(qd, 50), searcher.search_async(qd, 50)
     np.testing.assert_array_equal(a.result()[0].cpu().numpy(), b.result()[0].cpu().numpy())
+    # the native pipeline without an exchange (single shard) and with one
+    for ex_p in (None, sharded.PeerExchange(0, 40, 50)):
+        _, pipe = sharded.make_searcher(index, 0, lanes=2, exchange=ex_p, pipeline=(40, 50))
+        hs = [pipe.search_async(qd, 50), pipe.search_async(qd[:7].contiguous(), 9)]
+        np.testing.assert_array_equal(hs[0].result()[0].cpu().numpy(), a.result()[0].cpu().numpy())
+        np.testing.assert_array_equal(hs[1].result()[0].cpu().numpy(), a.result()[0].cpu().numpy()[:7, :9])
+        with pytest.raises(ValueError):
+            pipe.search(torch.zeros((41, 128), device="cuda"), 50)      # larger than the pipeline was sized for
+        pipe.close()
+        if ex_p is not None:
+            ex_p.close()
     # protocol errors are refused at the ABI, not left to hang a kernel
     with pytest.raises(ValueError):
         ex.push(torch.empty(sharded.packed_bytes(41, 50), dtype=torch.uint8, device="cuda"), 41, 50, 0)   # more queries than the mailbox holds
