@@ -259,7 +259,8 @@ __device__ void emit_topk(const FinaliseArgs& a, int64_t q, const uint64_t* item
         for (int g = 0; g < p.world; ++g) p.status[g][q] = status;
     }
     if (p.world > 0) {
-        __threadfence_system();
+        // the barrier orders every thread's stores before the releasing threads' system-scope fence (cumulative), so one
+        // fence per destination is enough -- a __threadfence_system() in all 256 threads first cost another NVLink round trip
         __syncthreads();
         if ((int)threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + q, p.epoch);
     }
@@ -898,6 +899,7 @@ merge_parts_kernel(const char* in_idx, const char* in_score, const char* in_stat
     __shared__ int s_last;
     const int64_t q = blockIdx.x;
     const int total = parts * k;
+    pdl_wait();                                         // launched early (programmatic dependent launch): the local search ahead of it has finished
     if (sync.flags) {
         if ((int)threadIdx.x < parts) wait_word_sys(sync.flags + (int64_t)threadIdx.x * sync.flag_stride + q, sync.epoch);
         __syncthreads();
@@ -956,9 +958,9 @@ void launch_merge_parts(const void* in_idx, const void* in_score, const void* in
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     MergeSync none{};
-    merge_parts_kernel<<<(unsigned)nq, 512, smem, st>>>(static_cast<const char*>(in_idx), static_cast<const char*>(in_score), static_cast<const char*>(in_status),
-                                                      idx_stride, score_stride, status_stride, parts, nq, k, out_idx, out_score, out_status, m,
-                                                      sync ? *sync : none);
+    launch_pdl(merge_parts_kernel, dim3((unsigned)nq), dim3(512), smem, st, static_cast<const char*>(in_idx), static_cast<const char*>(in_score),
+               static_cast<const char*>(in_status), idx_stride, score_stride, status_stride, parts, nq, k, out_idx, out_score, out_status, m,
+               sync ? *sync : none);
 }
 
 // Sending end of the peer exchange as a kernel of its own (for payloads that were not produced by an emit step with
