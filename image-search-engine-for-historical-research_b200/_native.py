@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
     "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
     "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_trace", "xs_index_save", "xs_index_load",
-    "xs_pipeline_create", "xs_pipeline_submit", "xs_pipeline_collect", "xs_pipeline_destroy",
+    "xs_search_dev_exchange", "xs_pipeline_create", "xs_pipeline_submit", "xs_pipeline_collect", "xs_pipeline_destroy",
 )
 
 
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
         lib.xs_exchange_create.argtypes = [i32, i32, i32, i64, i32, C.POINTER(p), p]
         lib.xs_exchange_connect.argtypes = [p, p]
         lib.xs_search_dev_push.argtypes = [p, p, i64, i32, i32, p, i32, p]
+        lib.xs_search_dev_exchange.argtypes = [p, p, i64, i32, i32, p, i32, p, p, p, p]
         lib.xs_exchange_push.argtypes = [p, p, i64, i32, i32, p]
         lib.xs_exchange_merge.argtypes = [p, i32, i64, i32, p, p, p, p]
         lib.xs_exchange_destroy.argtypes = [p]

@@ -602,6 +602,8 @@ struct CoreArgs {
     int* ncand;                 // device counter of rescored candidates (nullptr: the index's own)
     int path;                   // PATH_*
     const PushTarget* push;     // non-null: results also go straight into the peer-exchange mailboxes (out_idx etc. may be null)
+    const MergeTarget* merge;   // non-null (with push): try to merge the world's lists in the same launch
+    bool* merged;               // out: the merge did ride along (else the caller launches the merge kernel)
 };
 
 __global__ void boost_self_kernel(float* scores, int64_t pitch, int nq, int64_t self_base) {
@@ -689,6 +691,7 @@ static int fill_finalise(xs_index* ix, const CoreArgs& a, int64_t q0, int64_t c,
         for (int g = 0; g < fa->push.world; ++g) {
             fa->push.ids[g] += q0 * k; fa->push.scores[g] += q0 * k; fa->push.status[g] += q0; fa->push.flags[g] += q0;
         }
+        if (a.merge && c == a.nq) { fa->merge = *a.merge; fa->merge.on = 1; fa->merge.q0 = 0; }     // single-batch calls only
     }
     return XS_OK;
 }
@@ -738,7 +741,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
             fa.P = P; fa.cap = cap;
             XS_TRY(fill_finalise(ix, a, q0, c, &fa, ncand));
-            launch_finalise(fa, c, ix->cur);
+            const bool mg = launch_finalise(fa, c, ix->cur);
+            if (a.merged) *a.merged = mg;
             launches += 1 + finalise_launches(fa, c);
         }
     } else {
@@ -818,7 +822,8 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             fa.pool_items = ix->pool_items.as<uint64_t>(); fa.pool_count = ix->pool_count.as<int>(); fa.pool_thr = ix->pool_thr.as<uint32_t>();
             fa.P = plan.splits; fa.cap = plan.cap;
             XS_TRY(fill_finalise(ix, a, q0, c, &fa, ncand));
-            launch_finalise(fa, c, ix->cur);
+            const bool mg = launch_finalise(fa, c, ix->cur);
+            if (a.merged) *a.merged = mg;
             launches += 1 + finalise_launches(fa, c);
         }
     }
@@ -1281,17 +1286,21 @@ static int exchange_check_use(xs_exchange* ex, int slot, int64_t nq, int k) {
     return XS_OK;
 }
 
-// The search with the sending end of the exchange fused into its last kernel: the emit step of every query stores the
-// k results into all mailboxes and releases that query's flag -- no packed local result, no push kernel, no collective.
-extern "C" int xs_search_dev_push(xs_index* ix, const float* q_dev, int64_t nq, int renormalise_q, int k,
-                                  xs_exchange* ex, int slot, void* stream) {
+// The search with the exchange fused into its last kernel.  Sending end: the emit step of every query stores the k results
+// into all mailboxes and releases that query's flag -- no packed local result, no push kernel, no collective.  Receiving end
+// (merge_out != null): the same CTA then waits for the other ranks' lists of its query and merges; when that is not possible
+// (large batches, huge k) the merge kernel is launched behind the search instead.
+static int search_exchange(xs_index* ix, const float* q_dev, int64_t nq, int renormalise_q, int k, xs_exchange* ex, int slot,
+                           int64_t* out_idx, float* out_score, int32_t* out_status, bool want_merge, void* stream) {
     XS_TRY(check_search_args(ix, nq, k));
     if (!q_dev || !ex) return fail(XS_ERR_ARG, "null pointer");
+    if (want_merge && !out_idx) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(ix->mu);
-    std::lock_guard<std::mutex> lk2(ex->mu);
+    std::unique_lock<std::mutex> lk2(ex->mu);
     XS_TRY(exchange_check_use(ex, slot, nq, k));
     if (ex->device != ix->device) return fail(XS_ERR_ARG, "index and exchange live on different devices");
     if (ex->push_epoch[slot] != ex->merge_epoch[slot]) return fail(XS_ERR_ARG, "search into slot %d before its previous result was merged", slot);
+    if (want_merge && (int64_t)ex->world * k > 16384) return fail(XS_ERR_UNSUPPORTED, "world*k = %lld > 16384", (long long)ex->world * k);
     CU_TRY(cudaSetDevice(ix->device));
     ix->cur = static_cast<cudaStream_t>(stream);
     XS_TRY(ix->q32.ensure((size_t)nq * ix->d_pad * sizeof(float)));
@@ -1307,15 +1316,46 @@ extern "C" int xs_search_dev_push(xs_index* ix, const float* q_dev, int64_t nq, 
     }
     pt.my_acks = reinterpret_cast<const uint32_t*>(ex->local + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD;
     pt.epoch = ex->push_epoch[slot] + 1;
+    MergeTarget mt{};
+    if (want_merge) {
+        mt.base = ex->part(ex->rank, slot, 0); mt.part_bytes = ex->part_bytes;
+        mt.flags = ex->flags(ex->rank, slot, 0); mt.flag_stride = ex->max_q;
+        mt.nq_total = nq;
+        mt.ticket = reinterpret_cast<uint32_t*>(ex->local + xs_exchange::TICKET_OFF) + slot;
+        for (int g = 0; g < ex->world; ++g)
+            mt.ack[g] = reinterpret_cast<uint32_t*>(ex->peer[g] + xs_exchange::ACKS_OFF) + slot * XCHG_MAX_WORLD + ex->rank;
+        mt.out_idx = out_idx; mt.out_score = out_score; mt.out_status = out_status;
+    }
+    bool merged = false;
     CoreArgs a{};
     a.raw = q_dev;
     a.q32 = ix->q32.as<float>(); a.nq = nq; a.k = k; a.prep = true; a.prep_renorm = renormalise_q != 0; a.tmap_a = nullptr; a.a_row0 = 0;
     a.self_base = -1; a.out_idx = nullptr; a.out_score = nullptr; a.status = ix->status.as<int>();
     a.path = choose_path(ix, nq, k);
     a.push = &pt;
+    a.merge = want_merge ? &mt : nullptr;
+    a.merged = &merged;
     XS_TRY(search_core(ix, a));
     ++ex->push_epoch[slot];
+    if (want_merge) {
+        if (merged) { ++ex->merge_epoch[slot]; ix->stats.gpu_launches += 0; }
+        else {
+            lk2.unlock();
+            XS_TRY(xs_exchange_merge(ex, slot, nq, k, out_idx, out_score, out_status, stream));
+            ix->stats.gpu_launches += 1;
+        }
+    }
     return XS_OK;
+}
+
+extern "C" int xs_search_dev_push(xs_index* ix, const float* q_dev, int64_t nq, int renormalise_q, int k,
+                                  xs_exchange* ex, int slot, void* stream) {
+    return search_exchange(ix, q_dev, nq, renormalise_q, k, ex, slot, nullptr, nullptr, nullptr, false, stream);
+}
+
+extern "C" int xs_search_dev_exchange(xs_index* ix, const float* q_dev, int64_t nq, int renormalise_q, int k, xs_exchange* ex, int slot,
+                                      int64_t* out_idx_dev, float* out_score_dev, int32_t* out_status_dev, void* stream) {
+    return search_exchange(ix, q_dev, nq, renormalise_q, k, ex, slot, out_idx_dev, out_score_dev, out_status_dev, true, stream);
 }
 
 extern "C" int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t nq, int k, int slot, void* stream) {
@@ -1448,8 +1488,7 @@ extern "C" int xs_pipeline_submit(xs_pipeline* p, const float* q_dev, int64_t nq
     CU_TRY(cudaStreamWaitEvent(st, p->in_ev, 0));
     int64_t* oi = p->out_idx[slot].as<int64_t>(); float* os = p->out_score[slot].as<float>(); int32_t* ost = p->out_status[slot].as<int32_t>();
     if (p->ex) {
-        XS_TRY(xs_search_dev_push(ix, q_dev, nq, 0, k, p->ex, slot, st));
-        XS_TRY(xs_exchange_merge(p->ex, slot, nq, k, oi, os, ost, st));
+        XS_TRY(xs_search_dev_exchange(ix, q_dev, nq, 0, k, p->ex, slot, oi, os, ost, st));
     } else {
         XS_TRY(xs_search_dev(ix, q_dev, nq, 0, k, oi, os, ost, st));
     }

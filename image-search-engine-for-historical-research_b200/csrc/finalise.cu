@@ -748,6 +748,71 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
     emit_topk(a, q, sorted, ncand, sh_selfkey, flags);
     FF_STAMP(8);
     if (tid == 0 && a.n_cand) atomicAdd(a.n_cand, ncand);
+    if (!a.merge.on) return;
+    // ---- 5. receiving end of the exchange, same kernel: this query's lists from every rank -> the final k ----------------
+    // (the other clusters keep working; the only thing waited for here is another GPU)
+    const MergeTarget& mg = a.merge;
+    const int world = a.push.world, k = a.k;
+    const int64_t qg = mg.q0 + q;                                    // query index within the whole call
+    if (tid < world) wait_word_sys(mg.flags + (int64_t)tid * mg.flag_stride + qg, a.push.epoch);
+    __syncthreads();
+    uint64_t* mitems = reinterpret_cast<uint64_t*>(rows);            // [world * k] (the staging region is free now)
+    uint64_t* mrank = mitems + world * k;
+    const int mtotal = world * k;
+    for (int i = tid; i < mtotal; i += FF_THREADS) {
+        const int g = i / k, rr = i - g * k;
+        const char* part = mg.base + (int64_t)g * mg.part_bytes;
+        const int64_t id = reinterpret_cast<const int64_t*>(part)[qg * k + rr];
+        const float sc = reinterpret_cast<const float*>(part + mg.nq_total * k * 8)[qg * k + rr];
+        // position i orders equal scores by ascending id: parts own increasing id ranges and are sorted inside
+        mitems[i] = id >= 0 ? make_item(sc, (uint32_t)i) : 0ull;
+    }
+    __syncthreads();
+    for (int i = tid; i < mtotal; i += FF_THREADS) {
+        const uint64_t me = mitems[i];
+        if (me == 0ull) continue;
+        int rank = 0;
+        for (int o = 0; o < mtotal; ++o) rank += mitems[o] > me ? 1 : 0;
+        if (rank < k) mrank[rank] = me;
+    }
+    __syncthreads();
+    int valid = 0;
+    for (int i = tid; i < mtotal; i += FF_THREADS) valid += mitems[i] != 0ull ? 1 : 0;
+    __shared__ int sh_valid;
+    if (tid == 0) sh_valid = 0;
+    __syncthreads();
+    if (valid) atomicAdd(&sh_valid, valid);
+    __syncthreads();
+    const int nvalid = min(sh_valid, k);
+    for (int rr = tid; rr < k; rr += FF_THREADS) {
+        int64_t id = -1;
+        float sc = -INFINITY;
+        if (rr < nvalid) {
+            const int i = (int)item_row(mrank[rr]);
+            const int g = i / k, r2 = i - g * k;
+            const char* part = mg.base + (int64_t)g * mg.part_bytes;
+            id = reinterpret_cast<const int64_t*>(part)[qg * k + r2];
+            sc = reinterpret_cast<const float*>(part + mg.nq_total * k * 8)[qg * k + r2];
+        }
+        mg.out_idx[qg * k + rr] = id;
+        if (mg.out_score) mg.out_score[qg * k + rr] = sc;
+    }
+    if (tid == 0 && mg.out_status) {                                 // certified only if every shard certified its list
+        int32_t stw = 0;
+        for (int g = 0; g < world; ++g) stw |= reinterpret_cast<const int32_t*>(mg.base + (int64_t)g * mg.part_bytes + mg.nq_total * k * 12)[qg];
+        mg.out_status[qg] = stw;
+    }
+    __syncthreads();                                                 // every read of the mailbox by this CTA has completed
+    __shared__ int sh_lastq;
+    if (tid == 0) {
+        __threadfence();
+        sh_lastq = (atomicAdd(mg.ticket, 1u) == (uint32_t)(mg.nq_total - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_lastq) {                                                  // the whole call has been merged here: the slot may be overwritten
+        if (tid == 0) *mg.ticket = 0;
+        if (tid < world) st_release_sys(mg.ack[tid], a.push.epoch);
+    }
 }
 
 // Candidates per query the rescoring stage can hold: the band of the statistical certificate is a few dozen rows wide
@@ -768,9 +833,18 @@ static int finalise_form(const FinaliseArgs& a, int64_t nq) {     // 0: one CTA 
     return nq <= FIN_FUSED_MAX_Q ? 2 : 1;
 }
 int finalise_launches(const FinaliseArgs& a, int64_t nq) { return finalise_form(a, nq) == 1 ? 2 : 1; }
+// The receiving end of the exchange can ride in the same launch when the cluster form is used (one emitting CTA per query)
+// and the world's lists of a query fit its staging region twice over (items + ranks).
+bool finalise_can_merge(int64_t nq, int k, int world, int P, int d_pad) {
+    if (nq > FIN_FUSED_MAX_Q || (P + FF_MAX_CLUSTER - 1) / FF_MAX_CLUSTER > FF_THREADS) return false;
+    size_t region = (size_t)FF_WARPS * d_pad * sizeof(float);
+    const size_t phase1 = (size_t)FF_ITEMS * sizeof(uint64_t) + FF_BINS * sizeof(uint32_t);
+    if (region < phase1) region = phase1;
+    return (size_t)world * k * 16 + 64 <= region && (int64_t)world * k <= 2048;
+}
 
-void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
-    if (nq <= 0) return;
+bool launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
+    if (nq <= 0) return false;
     FinaliseArgs a = a_in;
     const int cand_max = a.cand_max > 0 ? a.cand_max : finalise_cand_max(a.k, 0);
     int form = finalise_form(a, nq);
@@ -808,10 +882,12 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
             attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 2;
+            if (a.merge.on && !(a.push.world > 0 && finalise_can_merge(nq, a.k, a.push.world, a.P, a.d_pad))) a.merge.on = 0;
             cudaLaunchKernelEx(&cfg, finalise_cluster_kernel, a, cand_max);
-            return;
+            return a.merge.on != 0;
         }
     }
+    a.merge.on = 0;                                   // the other forms emit (and push) only: the caller launches the merge kernel
     if (form == 2) form_fallback = 1;
     const size_t fixed = (size_t)cand_max * sizeof(uint64_t) + offs_bytes + (size_t)a.d_pad * sizeof(float) + 4096 * sizeof(uint32_t);
     // room for the gathered pool items: what the pools can hold, capped by the shared-memory budget
@@ -835,6 +911,7 @@ void launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
         cudaFuncSetAttribute(finalise_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIN_SMEM_BUDGET + 1024));
         launch_pdl(finalise_kernel<false>, dim3((unsigned)nq), dim3(FIN_THREADS), smem, st, a, cand_max, item_cap);
     }
+    return false;
 }
 
 // ---- threshold bootstrap ---------------------------------------------------------------------------

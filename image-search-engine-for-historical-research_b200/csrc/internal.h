@@ -115,6 +115,20 @@ struct PushTarget {
     const uint32_t* my_acks;             // local acknowledgement words of this slot, one per receiving rank
     uint32_t epoch;
 };
+// Receiving end of the peer exchange fused into the same kernel (cluster form only): after a query's own results have gone
+// out, its emitting CTA waits for the other ranks' lists of THAT query, merges world x k -> k and writes the final answer.
+struct MergeTarget {
+    int on;
+    const char* base;                    // this rank's mailbox, slot base: part g at base + g * part_bytes (ids | scores | status)
+    int64_t part_bytes;
+    const uint32_t* flags;               // local per-query arrival flags of this slot: flags[g * flag_stride + q]
+    int64_t flag_stride;
+    int64_t nq_total;                    // queries of the whole call (layout of a part)
+    int64_t q0;                          // first query of this launch within the call
+    uint32_t* ticket;                    // local counter of merged queries (the last one acknowledges the slot)
+    uint32_t* ack[XCHG_MAX_WORLD];       // rank g's acknowledgement word for (slot, this rank)
+    int64_t* out_idx; float* out_score; int32_t* out_status;    // [nq_total][k] / [nq_total]
+};
 struct FinaliseArgs {
     const uint64_t* pool_items; const int* pool_count; const uint32_t* pool_thr;
     int P, cap;
@@ -130,12 +144,14 @@ struct FinaliseArgs {
     int cand_max;               // candidates per query that can be rescored (power of two); 0 = default for k
     uint64_t* w_cand; int* w_ncand; int* w_flag; int* w_ticket;   // carved out by launch_finalise
     PushTarget push;
+    MergeTarget merge;          // merge.on requires push.world > 0
     unsigned long long* trace;  // optional [nq * ctas_per_query][10] globaltimer stamps of the fused form (debugging)
 };
 int  finalise_cand_max(int k, int mode);                  // mode 0: statistical band, 1: worst-case band (more candidates)
 size_t finalise_work_bytes(int64_t nq, int k, int cand_max);
 int  finalise_launches(const FinaliseArgs& a, int64_t nq);
-void launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);
+bool finalise_can_merge(int64_t nq, int k, int world, int P, int d_pad);
+bool launch_finalise(const FinaliseArgs& a, int64_t nq, cudaStream_t st);     // true: the exchange's merge rode in the same launch (a.merge)
 // thr0[q] = (k-th best pooled coarse score) - 2 eps[q], one ulp lower; -inf when fewer than k items.
 void launch_sample_threshold(const uint64_t* pool_items, const int* pool_count, int P, int cap, int k,
                              const float* eps, float* thr0, int64_t nq, cudaStream_t st);

@@ -131,6 +131,14 @@ class ExactIndex:
         nat.check(self._lib.xs_search_dev_push(self._h, C.c_void_p(q_ptr), int(nq), int(bool(renormalise)), int(k),
                                                exchange_handle, int(slot), C.c_void_p(stream) if stream else None), "xs_search_dev_push")
 
+    def search_device_exchange(self, q_ptr: int, nq: int, k: int, exchange_handle, slot: int, out_idx_ptr: int, out_score_ptr: int,
+                               out_status_ptr: int, stream: int = 0, renormalise: bool = False):
+        """Search + exchange in one call (xs_search_dev_exchange): local search, results into every rank's mailbox, and the
+        merged ``[nq, k]`` answer (plus certificate words) into the given device buffers."""
+        nat.check(self._lib.xs_search_dev_exchange(self._h, C.c_void_p(q_ptr), int(nq), int(bool(renormalise)), int(k), exchange_handle, int(slot),
+                                                   C.c_void_p(out_idx_ptr), C.c_void_p(out_score_ptr), C.c_void_p(out_status_ptr),
+                                                   C.c_void_p(stream) if stream else None), "xs_search_dev_exchange")
+
     def self_knn(self, k: int, begin: int = 0, end: int | None = None):
         """Top-k neighbours of database rows ``[begin, end)`` among all rows; a row's own id is
         first (src/utils/diffusion.py:67,108).  Returns ``(sims, ids)`` like ``KNN.search``."""

@@ -136,8 +136,10 @@ class ShardedSearcher:
     def _enqueue(self, queries, k, nq, slot, lane):
         import torch
         if self.exchange is not None:
-            self.local_push(queries, k, self.exchange, slot)
-            return _Pending(self, "peer", None, None, queries, nq, k, slot, lane)
+            # `local_push` may hand back the merged outputs itself (xs_search_dev_exchange: the merge rides in the search's
+            # last kernel); None = only the sending end ran and result() enqueues the merge
+            merged = self.local_push(queries, k, self.exchange, slot)
+            return _Pending(self, "peer", None, merged, queries, nq, k, slot, lane)
         packed = self._local(queries, k, slot)
         if self.world == 1:
             return _Pending(self, "local", None, packed, queries, nq, k, slot, lane)
@@ -183,7 +185,11 @@ class _Pending:
         o = self.owner
         if self.kind == "peer":
             # the merge goes onto the stream of the push: the only flags it can ever wait for are other GPUs'
-            if self.lane is not None:
+            if self.buf is not None:                        # already merged by the search itself
+                ids, sims, status = self.buf
+                if self.lane is not None:
+                    torch.cuda.current_stream(self.lane.device).wait_stream(self.lane)
+            elif self.lane is not None:
                 with torch.cuda.stream(self.lane):
                     ids, sims, status = o.exchange.merge(self.nq, self.k, self.slot)
                 torch.cuda.current_stream(self.lane.device).wait_stream(self.lane)
@@ -261,14 +267,19 @@ class PeerExchange:
         nat.check(self.lib.xs_exchange_push(self._h, C.c_void_p(packed.data_ptr()), int(nq), int(k), int(slot),
                                             C.c_void_p(stream) if stream else None), "xs_exchange_push")
 
-    def merge(self, nq: int, k: int, slot: int):
+    def outputs(self, nq: int, k: int, slot: int):
+        """The merged-result buffers of ``slot`` (reused from step to step)."""
         torch = self.torch
         key = (nq, k, slot)
         if key not in self._out:
             dev = torch.device("cuda", self.device)
             self._out[key] = (torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
                               torch.empty((nq,), dtype=torch.int32, device=dev))
-        out_i, out_s, out_st = self._out[key]
+        return self._out[key]
+
+    def merge(self, nq: int, k: int, slot: int):
+        torch = self.torch
+        out_i, out_s, out_st = self.outputs(nq, k, slot)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         nat.check(self.lib.xs_exchange_merge(self._h, int(slot), int(nq), int(k), C.c_void_p(out_i.data_ptr()),
                                              C.c_void_p(out_s.data_ptr()), C.c_void_p(out_st.data_ptr()),
@@ -342,6 +353,15 @@ class CudaShard:
         nq = int(queries.shape[0])
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
         self.lanes[slot % len(self.lanes)].search_device_push(queries.data_ptr(), nq, k, exchange.handle, slot, stream=stream)
+
+    def local_exchange(self, queries, k, exchange, slot=0):
+        """Search + push + merge in one call (xs_search_dev_exchange): returns the merged ``(ids, sims, status)``."""
+        nq = int(queries.shape[0])
+        out_i, out_s, out_st = exchange.outputs(nq, k, slot)
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.lanes[slot % len(self.lanes)].search_device_exchange(queries.data_ptr(), nq, k, exchange.handle, slot, out_i.data_ptr(),
+                                                                  out_s.data_ptr(), out_st.data_ptr(), stream=stream)
+        return out_i, out_s, out_st
 
     def merge(self, packed_all, world, nq, k, slot=0):
         torch = self.torch
@@ -473,7 +493,7 @@ def make_searcher(index, device: int, lanes: int = 1, exchange: "PeerExchange | 
     default is the Python-driven ``ShardedSearcher`` (also the NCCL path and the exact re-run path)."""
     shard = CudaShard(index, device, lanes=1 if pipeline else lanes)
     searcher = ShardedSearcher(shard.local_search, shard.merge, group=group, exchange=exchange,
-                               local_push=shard.local_push if exchange is not None else None,
+                               local_push=shard.local_exchange if exchange is not None else None,
                                lane_stream=shard.lane_stream if (lanes > 1 and not pipeline) else None, check=check)
     if pipeline:
         return shard, PipelinedSearcher(index, device, pipeline[0], pipeline[1], lanes=lanes, exchange=exchange, fallback=searcher)

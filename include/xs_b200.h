@@ -219,6 +219,12 @@ XS_API int xs_exchange_create(int device, int world, int rank, int64_t max_queri
 XS_API int xs_exchange_connect(xs_exchange* ex, const unsigned char* handles /* world x 64 bytes, by rank */);
 XS_API int xs_search_dev_push(xs_index* index, const float* q_dev, int64_t nq, int renormalise_q, int k,
                               xs_exchange* ex, int slot, void* stream);
+/* search + push + merge in one call: equivalent to xs_search_dev_push followed by xs_exchange_merge on the same stream.  For
+ * batches of at most 128 queries the merge rides in the search's last kernel too: the CTA that emitted a query waits for
+ * the other ranks' lists of that query and merges them, so a sharded step is three launches and the only wait is on
+ * another GPU. */
+XS_API int xs_search_dev_exchange(xs_index* index, const float* q_dev, int64_t nq, int renormalise_q, int k, xs_exchange* ex, int slot,
+                                  int64_t* out_idx_dev, float* out_score_dev, int32_t* out_status_dev, void* stream);
 XS_API int xs_exchange_push(xs_exchange* ex, const void* packed_dev, int64_t nq, int k, int slot, void* stream);
 XS_API int xs_exchange_merge(xs_exchange* ex, int slot, int64_t nq, int k, int64_t* out_idx_dev, float* out_score_dev,
                              int32_t* out_status_dev, void* stream);
