@@ -1488,7 +1488,17 @@ extern "C" int xs_pipeline_submit(xs_pipeline* p, const float* q_dev, int64_t nq
     CU_TRY(cudaStreamWaitEvent(st, p->in_ev, 0));
     int64_t* oi = p->out_idx[slot].as<int64_t>(); float* os = p->out_score[slot].as<float>(); int32_t* ost = p->out_status[slot].as<int32_t>();
     if (p->ex) {
-        XS_TRY(xs_search_dev_exchange(ix, q_dev, nq, 0, k, p->ex, slot, oi, os, ost, st));
+        // fused merge (the finalise CTA of a query waits for the peers' lists): fewest launches, best latency.  With two lanes the
+        // merge is its own small kernel instead, so that the other lane's scan -- which needs every SM to itself -- is not held
+        // up behind finalise CTAs that are only waiting for another GPU.
+        static const int force = [] { const char* e = getenv("XS_PIPE_MERGE"); return e ? atoi(e) : 0; }();     // 1 fused, 2 separate
+        const bool separate = force == 2 || (force == 0 && p->n_lanes == 2);
+        if (separate) {
+            XS_TRY(xs_search_dev_push(ix, q_dev, nq, 0, k, p->ex, slot, st));
+            XS_TRY(xs_exchange_merge(p->ex, slot, nq, k, oi, os, ost, st));
+        } else {
+            XS_TRY(xs_search_dev_exchange(ix, q_dev, nq, 0, k, p->ex, slot, oi, os, ost, st));
+        }
     } else {
         XS_TRY(xs_search_dev(ix, q_dev, nq, 0, k, oi, os, ost, st));
     }
