@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "xs_rank_all", "xs_merge_candidates", "xs_set_param", "xs_aqe_search", "xs_merge_candidates_strided", "xs_mutual_knn", "xs_diffusion_cg",
     "xs_exchange_create", "xs_exchange_connect", "xs_exchange_push", "xs_exchange_merge", "xs_exchange_destroy",
     "xs_exchange_part_bytes", "xs_search_dev_push", "xs_config_set", "xs_diffusion_laplacian", "xs_diffusion_offline", "xs_debug_trace", "xs_index_save", "xs_index_load",
-    "xs_search_dev_exchange", "xs_pipeline_create", "xs_pipeline_submit", "xs_pipeline_collect", "xs_pipeline_destroy",
+    "xs_search_dev_exchange", "xs_pipeline_create", "xs_pipeline_submit", "xs_pipeline_collect", "xs_pipeline_destroy", "xs_pipeline_lane",
 )
 
 
@@ -89,8 +89,10 @@ def load() -> C.CDLL:
         lib.xs_pipeline_submit.argtypes = [p, p, i64, i32, p, C.POINTER(i32)]
         lib.xs_pipeline_collect.argtypes = [p, i32, p, C.POINTER(p), C.POINTER(p), C.POINTER(i64), p]
         lib.xs_pipeline_destroy.argtypes = [p]
+        lib.xs_pipeline_lane.argtypes = [p, i32]
+        lib.xs_pipeline_lane.restype = p
         for name in ABI_SYMBOLS:
-            if name not in ("xs_last_error", "xs_exchange_part_bytes"):
+            if name not in ("xs_last_error", "xs_exchange_part_bytes", "xs_pipeline_lane"):
                 getattr(lib, name).restype = i32
         lib.xs_exchange_part_bytes.restype = i64
         _lib = lib

@@ -85,6 +85,8 @@ struct xs_index {
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
     int eps_mode = 0;                             // certificate: 0 = statistical band (8 sigma, random rotation, model check), 1 = worst-case band
     int inline_boot = 1;                          // small batches: threshold bootstrap inside the GEMM launch (0: separate sample pass)
+    int gemm_stages = 4;                          // operand ring of the single-CTA GEMM shape: 4 stages, or 3 to leave room for a co-resident finalise CTA
+    int fin_per_sm = 0;                           // cluster finalise: 0 = latency mode (three CTAs per SM), 1 = one slim CTA per SM, resident next to a GEMM CTA
     bool rotate = true; uint32_t rot_seed = 0;    // random rotation applied before bf16 rounding (fixed at build time)
     uint32_t boot_arrived = 0, boot_published = 0, boot_epoch = 0;    // host mirrors of the in-kernel bootstrap's counters / epoch
     int self_lanes = 1;                           // xs_self_knn: 2 = batches alternate between this index and an internal clone
@@ -492,7 +494,7 @@ extern "C" int xs_index_destroy(xs_index* ix) {
 static void copy_tunables(xs_index* dst, const xs_index* src) {
     dst->eps_sigmas = src->eps_sigmas; dst->scan_max_q = src->scan_max_q; dst->force_path = src->force_path;
     dst->gemm_splits = src->gemm_splits; dst->sample_pass = src->sample_pass; dst->pair_mode = src->pair_mode;
-    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot;
+    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot; dst->gemm_stages = src->gemm_stages; dst->fin_per_sm = src->fin_per_sm;
 }
 
 // caller holds src->mu
@@ -543,6 +545,8 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "certificate")) ix->eps_mode = ((int)value == 1) ? 1 : 0;
     else if (!strcmp(name, "inline_boot")) ix->inline_boot = (int)value != 0;
     else if (!strcmp(name, "boot_trace")) ix->boot_trace_on = (int)value != 0;
+    else if (!strcmp(name, "gemm_stages")) ix->gemm_stages = ((int)value == 3) ? 3 : 4;
+    else if (!strcmp(name, "fin_per_sm")) ix->fin_per_sm = (int)value == 1 ? 1 : 0;
     else if (!strcmp(name, "self_lanes")) ix->self_lanes = ((int)value >= 2) ? 2 : 1;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
@@ -676,6 +680,7 @@ static int fill_finalise(xs_index* ix, const CoreArgs& a, int64_t q0, int64_t c,
     fa->out_idx = a.out_idx ? a.out_idx + q0 * k : nullptr; fa->out_score = a.out_score ? a.out_score + q0 * k : nullptr;
     fa->status = a.status ? a.status + q0 : nullptr; fa->n_cand = ncand; fa->out_pitch = k;
     fa->cand_max = finalise_cand_max(k, ix->eps_mode);
+    fa->per_sm = ix->fin_per_sm;
     XS_TRY(ix->fin_work.ensure(finalise_work_bytes(c, k, fa->cand_max)));
     XS_TRY(ensure_tickets(ix, c));
     fa->work = ix->fin_work.p; fa->ticket = ix->fin_ticket.as<int>();
@@ -757,6 +762,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const int64_t c = (nq - q0 < batch_max) ? nq - q0 : batch_max;
             GemmPlan plan = plan_gemm(c, ix->n_pad, k, ix->num_sms, ix->gemm_splits, ix->pair_mode != 0);
             if (!ix->inline_boot) plan.inline_boot = 0;
+            plan.stages3 = ix->gemm_stages == 3 ? 1 : 0;
             InlineBoot boot{};
             if (plan.inline_boot) {
                 // the CTAs of this launch meet once inside the kernel: sample lists, arrival counter, published thresholds
@@ -1418,7 +1424,8 @@ extern "C" int xs_exchange_destroy(xs_exchange* ex) {
 // memory -- on one of two lane streams and returns; xs_pipeline_collect waits for that slot's event and hands back device
 // pointers to the merged result plus the number of uncertified queries (the caller re-runs those collectively).
 struct xs_pipeline {
-    xs_index* lane[2] = {nullptr, nullptr};       // lane[1] is an internal clone (own workspaces, same database arrays)
+    xs_index* lane[2] = {nullptr, nullptr};       // one lane: the caller's index; two lanes: two internal clones (own workspaces, same database arrays)
+    bool owns_lanes = false;
     xs_exchange* ex = nullptr;                    // null: single shard, no exchange step
     int n_lanes = 1, device = 0;
     int64_t nq_max = 0; int k_max = 0;
@@ -1440,7 +1447,20 @@ extern "C" int xs_pipeline_create(xs_index* ix, xs_exchange* ex, int64_t nq_max,
     p->ex = ex; p->device = ix->device; p->nq_max = nq_max; p->k_max = k_max; p->n_lanes = lanes >= 2 ? 2 : 1;
     p->lane[0] = ix;
     int rc = XS_OK;
-    if (p->n_lanes == 2) { std::lock_guard<std::mutex> lk(ix->mu); rc = clone_locked(ix, &p->lane[1]); }
+    if (p->n_lanes == 2) {
+        // Two lanes overlap for real only if the previous batch's finalise CTAs can sit on the SMs that the next batch's scan
+        // occupies: 3-stage operand ring for the scan (158 KB), one slim finalise CTA per SM (64 KB).  Both lanes are clones
+        // (own workspaces and tunables, the caller's index keeps its latency-mode shapes).  XS_PIPE_OVERLAP=0 keeps the
+        // default shapes on the lanes as well (they then merely alternate).
+        const char* e = getenv("XS_PIPE_OVERLAP");
+        const bool overlap = !(e && !atoi(e));
+        std::lock_guard<std::mutex> lk(ix->mu);
+        for (int l = 0; l < 2 && rc == XS_OK; ++l) {
+            rc = clone_locked(ix, &p->lane[l]);
+            if (rc == XS_OK && overlap) { p->lane[l]->gemm_stages = 3; p->lane[l]->fin_per_sm = 1; }
+        }
+        p->owns_lanes = true;
+    }
     cudaError_t e = cudaSuccess;
     for (int s = 0; s < 2 && rc == XS_OK && e == cudaSuccess; ++s) {
         if (s < p->n_lanes) e = cudaStreamCreateWithFlags(&p->stream[s], cudaStreamNonBlocking);
@@ -1457,6 +1477,9 @@ extern "C" int xs_pipeline_create(xs_index* ix, xs_exchange* ex, int64_t nq_max,
     return XS_OK;
 }
 
+// Debugging aid: the index behind lane `lane` (lane 1 is the internal clone), e.g. for xs_set_param "boot_trace" / xs_debug_trace.
+extern "C" xs_index* xs_pipeline_lane(xs_pipeline* p, int lane) { return (p && lane >= 0 && lane < p->n_lanes) ? p->lane[lane] : nullptr; }
+
 extern "C" int xs_pipeline_destroy(xs_pipeline* p) {
     if (!p) return XS_OK;
     cudaSetDevice(p->device);
@@ -1466,7 +1489,7 @@ extern "C" int xs_pipeline_destroy(xs_pipeline* p) {
         p->out_idx[s].release(); p->out_score[s].release(); p->out_status[s].release(); p->h_status[s].release();
     }
     if (p->in_ev) cudaEventDestroy(p->in_ev);
-    if (p->lane[1]) index_free(p->lane[1]);
+    if (p->owns_lanes) for (int l = 0; l < 2; ++l) if (p->lane[l]) index_free(p->lane[l]);
     cudaGetLastError();
     delete p;
     return XS_OK;
@@ -1476,6 +1499,7 @@ extern "C" int xs_pipeline_destroy(xs_pipeline* p) {
 extern "C" int xs_pipeline_submit(xs_pipeline* p, const float* q_dev, int64_t nq, int k, void* caller_stream, int* slot_out) {
     if (!p || !q_dev || !slot_out) return fail(XS_ERR_ARG, "null pointer");
     std::lock_guard<std::mutex> lk(p->mu);
+    if (!p->lane[0]) return fail(XS_ERR_ARG, "pipeline without lanes");
     XS_TRY(check_search_args(p->lane[0], nq, k));
     if (nq > p->nq_max || k > p->k_max) return fail(XS_ERR_ARG, "step of %lld queries x %d exceeds the pipeline's %lld x %d", (long long)nq, k, (long long)p->nq_max, p->k_max);
     const int slot = p->next;
@@ -1491,8 +1515,10 @@ extern "C" int xs_pipeline_submit(xs_pipeline* p, const float* q_dev, int64_t nq
         // fused merge (the finalise CTA of a query waits for the peers' lists): fewest launches, best latency.  With two lanes the
         // merge is its own small kernel instead, so that the other lane's scan -- which needs every SM to itself -- is not held
         // up behind finalise CTAs that are only waiting for another GPU.
-        static const int force = [] { const char* e = getenv("XS_PIPE_MERGE"); return e ? atoi(e) : 0; }();     // 1 fused, 2 separate
-        const bool separate = force == 2 || (force == 0 && p->n_lanes == 2);
+        // Measured on 8 B200s (70 queries, 300 steps): separate merge 182 / 186 us per step (2 / 1 lanes), fused 254 / 224 us --
+        // with seven peers to wait for, the waiting CTAs delay the launch's completion by the slowest rank's skew.
+        static const int force = [] { const char* e = getenv("XS_PIPE_MERGE"); return e ? atoi(e) : 0; }();     // 1 fused, 2 separate (default)
+        const bool separate = force != 1;
         if (separate) {
             XS_TRY(xs_search_dev_push(ix, q_dev, nq, 0, k, p->ex, slot, st));
             XS_TRY(xs_exchange_merge(p->ex, slot, nq, k, oi, os, ost, st));

@@ -518,15 +518,15 @@ struct FfExchange {              // one per CTA, read by the whole cluster
 };
 
 __global__ void __launch_bounds__(FF_THREADS)
-finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
+finalise_cluster_kernel(FinaliseArgs a, int cand_max, int item_cap, int rs_warps) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ uint64_t ff_smem[];
     uint64_t* cands = ff_smem;                          // [cand_max] this CTA's band members
     uint64_t* result = ff_smem + cand_max;              // [cand_max] (CTA 0's copy collects the cluster's rescored candidates)
-    uint64_t* items = ff_smem + 2 * cand_max;           // phase 1: [FF_ITEMS] gathered pool items | FF_BINS bins
-    uint32_t* bins = reinterpret_cast<uint32_t*>(items + FF_ITEMS);
-    float* rows = reinterpret_cast<float*>(ff_smem + 2 * cand_max);      // phase 3 (aliases phase 1): [FF_WARPS][d_pad] row staging
+    uint64_t* items = ff_smem + 2 * cand_max;           // phase 1: [item_cap] gathered pool items | FF_BINS bins
+    uint32_t* bins = reinterpret_cast<uint32_t*>(items + item_cap);
+    float* rows = reinterpret_cast<float*>(ff_smem + 2 * cand_max);      // phase 3 (aliases phase 1): [rs_warps][d_pad] row staging
     __shared__ FfExchange xch;
     __shared__ int offs[FF_THREADS + 1];
     __shared__ int scan_scratch[33];
@@ -554,7 +554,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
     __syncthreads();
     block_exclusive_scan(offs, FF_THREADS, scan_scratch);            // offs[FF_THREADS] = total
     const int total_all = offs[FF_THREADS];
-    const int total_r = min(total_all, FF_ITEMS);                    // what does not fit voids the certificate below
+    const int total_r = min(total_all, item_cap);                    // what does not fit voids the certificate below
     {   // gather: warp per list round-robin would serialise on short lists; flat (list, position < 32) slots, 8 loads in flight
         const int flat = n_lists * 32;
         for (int base = tid; base < flat; base += FF_THREADS * 8) {
@@ -567,7 +567,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
                 if (i < flat) {
                     const int l = i >> 5, jj = i & 31;
                     const int o = offs[l], c = offs[l + 1] - o;
-                    if (jj < c && o + jj < FF_ITEMS) { dst[u] = o + jj; v[u] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj]; }
+                    if (jj < c && o + jj < item_cap) { dst[u] = o + jj; v[u] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj]; }
                 }
             }
 #pragma unroll
@@ -575,7 +575,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
         }
         for (int l = warp; l < n_lists; l += FF_WARPS) {             // the rare list longer than 32
             const int o = offs[l], c = offs[l + 1] - o;
-            for (int jj = 32 + lane; jj < c; jj += 32) if (o + jj < FF_ITEMS) items[o + jj] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj];
+            for (int jj = 32 + lane; jj < c; jj += 32) if (o + jj < item_cap) items[o + jj] = a.pool_items[pool_slot(q, r + l * S, a.P) * a.cap + jj];
         }
     }
     for (int i = tid; i < FF_BINS; i += FF_THREADS) bins[i] = 0;
@@ -597,7 +597,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
     __syncthreads();
     if (tid == 0) {
         xch.kmin = sh_min; xch.kmax = sh_max; xch.total = (uint32_t)total_r; xch.thr = sh_pick;
-        xch.overflow = total_all > FF_ITEMS ? 1u : 0u; xch.ncand = 0; xch.bad = 0;
+        xch.overflow = total_all > item_cap ? 1u : 0u; xch.ncand = 0; xch.bad = 0;
         sh_pick = 0u;
     }
     cluster.sync();                                                  // ---- every CTA's exchange block is readable ----
@@ -691,7 +691,7 @@ finalise_cluster_kernel(FinaliseArgs a, int cand_max) {
     const uint32_t sbuf = (uint32_t)__cvta_generic_to_shared(buf);
     uint64_t* result0 = cluster.map_shared_rank(result, 0);
     bool bad = false;
-    for (int c = lo + warp; c < hi; c += FF_WARPS) {
+    for (int c = lo + warp; c < hi && warp < rs_warps; c += rs_warps) {
         int g = 0;
         while (g + 1 < S && (uint32_t)c >= off[g + 1]) ++g;
         const uint64_t it = cluster.map_shared_rank(cands, g)[c - off[g]];
@@ -857,16 +857,22 @@ bool launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
     }
     const size_t offs_bytes = ((a.P <= FIN_MAX_LISTS) ? (size_t)((a.P + 4) & ~3) : 4) * sizeof(int);
     if (form == 2) {
-        // phase 1 (items + bins) and phase 3 (row staging) share one region; 72 KB per CTA keeps three CTAs on an SM
-        size_t region = (size_t)FF_WARPS * a.d_pad * sizeof(float);
+        // phase 1 (items + bins) and phase 3 (row staging) share one region.  Latency mode (default): 8 staging warps, 72 KB
+        // per CTA, three CTAs per SM, as many CTAs per query as fit ONE wave.  Throughput mode (a.per_sm == 1, set by the
+        // two-lane pipeline together with the 3-stage GEMM ring): 7 staging warps, 64 KB -- one such CTA fits on an SM NEXT
+        // to a scanning GEMM CTA of the other lane, so the previous batch is finalised underneath the next batch's scan.
+        const bool slim = a.per_sm == 1;
+        const int rs_warps = slim ? FF_WARPS - 1 : FF_WARPS;
+        size_t region = (size_t)rs_warps * a.d_pad * sizeof(float);
         const size_t phase1 = (size_t)FF_ITEMS * sizeof(uint64_t) + FF_BINS * sizeof(uint32_t);
         if (region < phase1) region = phase1;
+        const int item_cap = (int)((region - FF_BINS * sizeof(uint32_t)) / sizeof(uint64_t)) & ~1;
         const size_t smem = (size_t)2 * cand_max * sizeof(uint64_t) + region;
         static int num_sms = 0;
         if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); if (num_sms <= 0) num_sms = 148; }
-        // CTAs per query (= cluster size): as many as fit in ONE wave at three CTAs per SM, and enough that every CTA's lists fit
+        // CTAs per query (= cluster size): as many as fit in ONE wave, and enough that every CTA's lists fit
         static const int sizes[] = {1, 2, 3, 4, 6, 8};
-        const int want = (int)((int64_t)3 * num_sms / nq);
+        const int want = (int)((int64_t)(slim ? 1 : 3) * num_sms / nq);
         int S = 0;
         for (int cand : sizes) {
             if ((a.P + cand - 1) / cand > FF_THREADS) continue;    // every CTA must be able to take its share of the lists
@@ -883,7 +889,7 @@ bool launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 2;
             if (a.merge.on && !(a.push.world > 0 && finalise_can_merge(nq, a.k, a.push.world, a.P, a.d_pad))) a.merge.on = 0;
-            cudaLaunchKernelEx(&cfg, finalise_cluster_kernel, a, cand_max);
+            cudaLaunchKernelEx(&cfg, finalise_cluster_kernel, a, cand_max, item_cap, rs_warps);
             return a.merge.on != 0;
         }
     }

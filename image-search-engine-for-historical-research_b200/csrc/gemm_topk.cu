@@ -34,11 +34,13 @@ constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB
 //   HALF          one CTA per 128 x 128 tile (cta_group::1), 6 stages x 32 KB: the per-CTA staging of PAIR without
 //                 the pairing.  Used by the threshold-bootstrap pass, which is one tile per CTA and purely
 //                 latency-bound: a deeper ring of smaller stages finishes the 32 K-steps sooner.
-enum { MODE_FULL = 0, MODE_PAIR = 1, MODE_HALF = 2 };
+enum { MODE_FULL = 0, MODE_PAIR = 1, MODE_HALF = 2, MODE_FULL3 = 3 };
+//   FULL3         FULL with a 3-stage ring (144 KB): leaves 70 KB of the SM's shared memory free, so that the selection /
+//                 rescoring kernel of the PREVIOUS batch can be resident next to it and run under this batch's scan
 template <int MODE> struct Shape {
     static constexpr bool PAIR = MODE == MODE_PAIR;
-    static constexpr int STAGES = MODE == MODE_FULL ? 4 : 6;
-    static constexpr int B_ROWS = MODE == MODE_FULL ? GEMM_BN : GEMM_BN / 2;     // database rows this CTA stages per step
+    static constexpr int STAGES = MODE == MODE_FULL ? 4 : (MODE == MODE_FULL3 ? 3 : 6);
+    static constexpr int B_ROWS = (MODE == MODE_FULL || MODE == MODE_FULL3) ? GEMM_BN : GEMM_BN / 2;     // database rows this CTA stages per step
     static constexpr int TILE_N = MODE == MODE_HALF ? GEMM_BN / 2 : GEMM_BN;     // database rows per tile (UMMA N)
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -58,8 +60,9 @@ struct __align__(8) GemmBarriers {
     uint32_t pad;
 };
 // both shapes stage 192 KB of operands
-constexpr size_t GEMM_SMEM = 1024 /*alignment slack*/ + (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t)
-                             + 16 + (size_t)BOOT_MAX_GRID * 8 * sizeof(float);
+constexpr size_t GEMM_SMEM_EXTRA = 1024 /*alignment slack*/ + sizeof(GemmBarriers) + 4 * 256 * sizeof(uint32_t) + 16 + (size_t)BOOT_MAX_GRID * 8 * sizeof(float);
+constexpr size_t GEMM_SMEM = (size_t)4 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + GEMM_SMEM_EXTRA;
+constexpr size_t GEMM_SMEM3 = (size_t)3 * (A_BYTES + GEMM_BN * GEMM_BK * 2) + GEMM_SMEM_EXTRA;
 static_assert(Shape<MODE_PAIR>::STAGES * Shape<MODE_PAIR>::STAGE_BYTES == Shape<MODE_FULL>::STAGES * Shape<MODE_FULL>::STAGE_BYTES, "ring sizes differ");
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in the pair's leader CTA
 
@@ -611,8 +614,9 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
     p.n_tiles = s;
     p.tile_stride = all_tiles / s;
     p.splits = s;                                   // one tile per job
-    p.sample_mode = 1;                              // register top-8 per (query, tile)
+    p.sample_mode = 1;                              // 8 group maxima per (query, tile)
     p.inline_boot = 0;
+    p.stages3 = 0;
     const int64_t jobs = (int64_t)p.m_tiles * p.splits;
     p.grid = (int)(jobs < num_sms ? jobs : num_sms);
     return p;
@@ -622,13 +626,15 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
                              const float* thr0, const InlineBoot* boot, cudaStream_t st) {
-    auto kern = plan.pair ? gemm_topk_kernel<MODE_PAIR> : (plan.half ? gemm_topk_kernel<MODE_HALF> : gemm_topk_kernel<MODE_FULL>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    const bool three = plan.stages3 && !plan.pair && !plan.half;
+    auto kern = plan.pair ? gemm_topk_kernel<MODE_PAIR> : (plan.half ? gemm_topk_kernel<MODE_HALF> : (three ? gemm_topk_kernel<MODE_FULL3> : gemm_topk_kernel<MODE_FULL>));
+    const size_t smem_bytes = three ? GEMM_SMEM3 : GEMM_SMEM;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)plan.grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GEMM_SMEM;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -80,6 +80,7 @@ struct GemmPlan {
     int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)
     int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
     int inline_boot;  // 1: one job per CTA; the first tile of every CTA is the threshold sample (no separate bootstrap launch)
+    int stages3;      // 1: single-CTA shape with a 3-stage operand ring (leaves shared memory for a co-resident finalise CTA)
 };
 // In-kernel threshold bootstrap of gemm_topk_kernel (plan.inline_boot): the CTAs meet once through these words.
 constexpr int BOOT_MAX_GRID = 160;        // CTAs (= sample lists per query) the selecting warp holds in registers
@@ -142,6 +143,7 @@ struct FinaliseArgs {
     void* work;                 // finalise_work_bytes(nq, k, cand_max) of scratch for the multi-CTA-per-query forms
     int* ticket;                // [3 * nq] zero-initialised words (completion tickets, candidate counters, flags; self-resetting)
     int cand_max;               // candidates per query that can be rescored (power of two); 0 = default for k
+    int per_sm;                 // cluster form: 0 / 3 = latency mode (three CTAs per SM), 1 = throughput mode (one slim CTA per SM, next to a GEMM CTA)
     uint64_t* w_cand; int* w_ncand; int* w_flag; int* w_ticket;   // carved out by launch_finalise
     PushTarget push;
     MergeTarget merge;          // merge.on requires push.world > 0

@@ -493,7 +493,7 @@ def make_searcher(index, device: int, lanes: int = 1, exchange: "PeerExchange | 
     default is the Python-driven ``ShardedSearcher`` (also the NCCL path and the exact re-run path)."""
     shard = CudaShard(index, device, lanes=1 if pipeline else lanes)
     searcher = ShardedSearcher(shard.local_search, shard.merge, group=group, exchange=exchange,
-                               local_push=shard.local_exchange if exchange is not None else None,
+                               local_push=shard.local_push if exchange is not None else None,
                                lane_stream=shard.lane_stream if (lanes > 1 and not pipeline) else None, check=check)
     if pipeline:
         return shard, PipelinedSearcher(index, device, pipeline[0], pipeline[1], lanes=lanes, exchange=exchange, fallback=searcher)

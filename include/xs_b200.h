@@ -245,6 +245,8 @@ XS_API int xs_pipeline_submit(xs_pipeline* p, const float* q_dev, int64_t nq, in
 XS_API int xs_pipeline_collect(xs_pipeline* p, int slot, void* caller_stream, int64_t** out_idx_dev, float** out_score_dev,
                                int64_t* n_flagged, int32_t* flagged);
 XS_API int xs_pipeline_destroy(xs_pipeline* p);
+/* Debugging aid: the index behind a lane of the pipeline (lane 1 = the internal clone; owned by the pipeline). */
+XS_API xs_index* xs_pipeline_lane(xs_pipeline* p, int lane);
 
 /*
  * Mutual-kNN test of the diffusion affinity graph.

@@ -25,8 +25,9 @@ for n in (1_007_000, 125_875):
     rows = bench.synth_rows_device(torch, n, 2048, dev, 0)
     ix = pkg.ExactIndex.from_device(rows.data_ptr(), n, 2048, 0)
     for nq in (70, 1):
-        for inline in ((1, 0) if nq > 1 else (1,)):
+        for inline, stages in (((1, 4), (1, 3), (0, 4)) if nq > 1 else ((1, 4),)):
             ix.set_param("inline_boot", inline)
+            ix.set_param("gemm_stages", stages)
             q = queries[:nq].contiguous()
             for _ in range(20):
                 ix.search_device(q.data_ptr(), nq, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
@@ -44,7 +45,7 @@ for n in (1_007_000, 125_875):
                 st = ix.stats()
                 ks.append(st["ms_coarse"]); ts.append(st["ms_total"])
             ix.set_param("timing", 0)
-            print(f"rows {n:8d} nq {nq:3d} inline_boot {inline}: step {step_ms*1e3:7.1f} us back to back; one call {sum(ts)/20*1e3:7.1f} us, coarse kernel {sum(ks)/20*1e3:7.1f} us, "
+            print(f"rows {n:8d} nq {nq:3d} inline_boot {inline} ring {stages}: step {step_ms*1e3:7.1f} us back to back; one call {sum(ts)/20*1e3:7.1f} us, coarse kernel {sum(ks)/20*1e3:7.1f} us, "
                   f"launches {st['gpu_launches']}, candidates/query {st['n_candidates']/nq:.0f}, uncertified {int(status[:nq].sum())}", flush=True)
     ix.close()
     del rows
@@ -58,6 +59,7 @@ for n in (125_875, 1_007_000):
     rows = bench.synth_rows_device(torch, n, 2048, dev, 0)
     ix = pkg.ExactIndex.from_device(rows.data_ptr(), n, 2048, 0)
     ix.set_param("boot_trace", 1)
+    ix.set_param("gemm_stages", 4); ix.set_param("inline_boot", 1)
     for _ in range(5):
         ix.search_device(queries.data_ptr(), 70, 100, ids.data_ptr(), sims.data_ptr(), status_ptr=status.data_ptr())
     torch.cuda.synchronize()

@@ -94,6 +94,33 @@ if rank == 0:
         if col.size:
             print(f"  finalise+push {nm:24s} min {col.min():7.1f}  median {np.median(col):7.1f}  max {col.max():7.1f}   ({col.size} CTAs)")
 index.set_param("boot_trace", 0)
+# two consecutive pipelined steps on the device clock: when does each kernel of each lane start and end?
+lib = nat.load()
+lanes_h = [C.c_void_p(lib.xs_pipeline_lane(pipe._h, l)) for l in range(int(os.environ.get("XS_LANES", "1")))]
+for hnd in lanes_h:
+    nat.check(lib.xs_set_param(hnd, b"boot_trace", 1.0), "set")
+for _ in range(12):
+    piped()
+pend[0].result(); pend[0] = None
+torch.cuda.synchronize(); dist.barrier()
+if rank == 0:
+    ev = []
+    for l, hnd in enumerate(lanes_h):
+        for which, width, name, c_end in ((0, 8, "scan+select GEMM", 6), (1, 10, "finalise+push", 8)):
+            buf = np.zeros((2048, width), dtype=np.uint64)
+            g = C.c_int(0)
+            nat.check(lib.xs_debug_trace(hnd, which, buf.ctypes.data, 2048, C.byref(g)), "trace")
+            t = buf[: g.value].astype(np.int64)
+            t = t[t[:, 0] > 0]
+            if len(t):
+                ends = t[:, c_end][t[:, c_end] > 0]
+                ev.append((int(t[:, 0].min()), int(ends.max() if len(ends) else t.max()), f"lane {l} {name}"))
+    if ev:
+        t0 = min(e[0] for e in ev)
+        for a_, b_, nm in sorted(ev):
+            print(f"  pipelined timeline: {nm:28s} {(a_ - t0) / 1e3:8.1f} .. {(b_ - t0) / 1e3:8.1f} us")
+for hnd in lanes_h:
+    nat.check(lib.xs_set_param(hnd, b"boot_trace", 0.0), "set")
 if rank == 0:
     print(f"{world} GPUs, {hi - lo} rows/GPU: local search {t_local:.1f} us | search+push+merge back to back {t_pm:.1f} us | "
           f"the same, host-synchronised per step {t_pm_sync:.1f} us | native pipeline (2 in flight) {t_pipe:.1f} us | "
