@@ -880,6 +880,7 @@ bool launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
         }                                                         // S == 0: more lists than a cluster can take -> the two-kernel form below
         if (S) {
             cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024));
+            cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)S, (unsigned)nq); cfg.blockDim = dim3(FF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
             cudaLaunchAttribute attr[2];

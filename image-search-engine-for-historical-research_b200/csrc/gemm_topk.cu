@@ -631,6 +631,9 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     const size_t smem_bytes = three ? GEMM_SMEM3 : GEMM_SMEM;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
+    // the SM's whole 228 KB as shared memory whatever this kernel needs: with the 3-stage ring the 70 KB it leaves are for a
+    // finalise CTA of the other lane (the driver would otherwise carve out just enough for this kernel and nothing else fits)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)plan.grid);
     cfg.blockDim = dim3(GEMM_THREADS);
