@@ -752,7 +752,10 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         }
     } else {
         // tcgen05 GEMM with fused top-K, queries in batches that bound the pool workspace
-        const int64_t batch_max = 8192;
+        // at most 8192 queries per batch (bounds the pool workspace); several batches are made equal (10,000 queries = 2 x 5,120,
+        // not 8,192 + 1,808: the short tail batch would run the tensor pipe at a fraction of its rate)
+        int64_t batch_max = 8192;
+        if (nq > batch_max) { const int64_t nb = (nq + batch_max - 1) / batch_max; batch_max = round_up((nq + nb - 1) / nb, 2 * GEMM_BM); }
         const int64_t nq_pad = round_up(nq < batch_max ? nq : batch_max, GEMM_BM);
         CUtensorMap tmap_q;
         if (!a.tmap_a) XS_TRY(ix->q16.ensure((size_t)round_up(nq, GEMM_BM) * ix->d_pad * 2));
