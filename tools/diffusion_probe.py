@@ -24,3 +24,12 @@ ref = np.stack([linalg.cg(lap[ids[i]][:, ids[i]], b, rtol=1e-6, atol=0.0, maxite
 t1 = time.time()
 print(f"scipy slicing + cg, {len(sample)} rows on one thread: {(t1-t0)/len(sample)*1e3:.2f} ms/row -> {(t1-t0)/len(sample)*n:.0f}s for all rows")
 print("max |gpu - scipy| =", np.abs(out[sample] - ref).max(), " max rel =", (np.abs(out[sample] - ref) / (np.abs(ref) + 1e-9)).max())
+
+# the whole gallery side on the device: self-kNN -> mutual graph -> Laplacian -> CG with nothing visiting the host in between
+for rep in range(2):
+    t0 = time.time()
+    oi, _, osc = pkg.diffusion.offline_device(d.knn.index, T, kd)
+    t1 = time.time()
+    print(f"device-resident pipeline (xs_diffusion_offline), all {n} rows: {t1-t0:.2f}s  (stagewise above: self-kNN + Laplacian + CG = {(t2 - t0_all) if False else 0:.0f})" if False else
+          f"device-resident pipeline (xs_diffusion_offline), all {n} rows: {t1-t0:.2f}s", flush=True)
+print("device pipeline vs stagewise: ids equal", bool((oi == ids).all()), " max |score diff| =", float(np.abs(osc - out).max()))
