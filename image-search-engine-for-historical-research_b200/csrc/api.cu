@@ -85,6 +85,7 @@ struct xs_index {
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
     int eps_mode = 0;                             // certificate: 0 = statistical band (8 sigma, random rotation, model check), 1 = worst-case band
     int inline_boot = 1;                          // small batches: threshold bootstrap inside the GEMM launch (0: separate sample pass)
+    int half_units = 1;                           // single-CTA GEMM shapes: deal the database in half tiles (0: whole tiles)
     int gemm_stages = 4;                          // operand ring of the single-CTA GEMM shape: 4 stages, or 3 to leave room for a co-resident finalise CTA
     int fin_per_sm = 0;                           // cluster finalise: 0 = latency mode (three CTAs per SM), 1 = one slim CTA per SM, resident next to a GEMM CTA
     bool rotate = true; uint32_t rot_seed = 0;    // random rotation applied before bf16 rounding (fixed at build time)
@@ -494,7 +495,7 @@ extern "C" int xs_index_destroy(xs_index* ix) {
 static void copy_tunables(xs_index* dst, const xs_index* src) {
     dst->eps_sigmas = src->eps_sigmas; dst->scan_max_q = src->scan_max_q; dst->force_path = src->force_path;
     dst->gemm_splits = src->gemm_splits; dst->sample_pass = src->sample_pass; dst->pair_mode = src->pair_mode;
-    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot; dst->gemm_stages = src->gemm_stages; dst->fin_per_sm = src->fin_per_sm;
+    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot; dst->gemm_stages = src->gemm_stages; dst->half_units = src->half_units; dst->fin_per_sm = src->fin_per_sm;
 }
 
 // caller holds src->mu
@@ -546,6 +547,7 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "inline_boot")) ix->inline_boot = (int)value != 0;
     else if (!strcmp(name, "boot_trace")) ix->boot_trace_on = (int)value != 0;
     else if (!strcmp(name, "gemm_stages")) ix->gemm_stages = ((int)value == 3) ? 3 : 4;
+    else if (!strcmp(name, "half_units")) ix->half_units = (int)value != 0;
     else if (!strcmp(name, "fin_per_sm")) ix->fin_per_sm = (int)value == 1 ? 1 : 0;
     else if (!strcmp(name, "self_lanes")) ix->self_lanes = ((int)value >= 2) ? 2 : 1;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
@@ -811,7 +813,7 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
                 XS_TRY(ix->pool_count.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
                 XS_TRY(ix->pool_thr.ensure((size_t)(sslots > slots ? sslots : slots) * 4));
                 sp.db_tiled = ix->db16t ? 1 : 0;
-                cudaError_t es = launch_gemm_topk(*ta, ix->db16t ? ix->tmap_dbt_h : ix->tmap_db_a, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+                cudaError_t es = launch_gemm_topk(*ta, ix->db16t ? ix->tmap_dbt_h : ix->tmap_db_a, nullptr, sp, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                                   ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                                   (int)row0, nullptr, nullptr, ix->cur);
                 if (es != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk (sample) launch failed: %s", cudaGetErrorString(es));
@@ -822,7 +824,9 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             }
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
             plan.db_tiled = ix->db16t ? 1 : 0;
-            cudaError_t e = launch_gemm_topk(*ta, ix->db16t ? (plan.pair ? ix->tmap_dbt_h : ix->tmap_dbt_b) : (plan.pair ? ix->tmap_db_a : ix->tmap_db_b), plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
+            if (!ix->half_units) plan.half_units = 0;
+            cudaError_t e = launch_gemm_topk(*ta, ix->db16t ? (plan.pair ? ix->tmap_dbt_h : ix->tmap_dbt_b) : (plan.pair ? ix->tmap_db_a : ix->tmap_db_b),
+                                             ix->db16t ? &ix->tmap_dbt_h : &ix->tmap_db_a, plan, c, ix->n, ix->d_pad, k, ix->eps.as<float>() + q0,
                                              ix->pool_items.as<uint64_t>(), ix->pool_count.as<int>(), ix->pool_thr.as<uint32_t>(),
                                              (int)row0, thr0, plan.inline_boot ? &boot : nullptr, ix->cur);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, "gemm_topk launch failed: %s", cudaGetErrorString(e));

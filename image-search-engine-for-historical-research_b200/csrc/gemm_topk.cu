@@ -170,8 +170,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // ---- the kernel ------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db,
-                 int m_tiles, int n_tiles, int tile_stride, int splits, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db, const __grid_constant__ CUtensorMap tmap_db_h,
+                 int m_tiles, int n_tiles, int tile_stride, int splits, int half_units, int k_blocks, int a_row0, int64_t nq, int64_t n_valid,
                  int k, int k_keep, int cap, int sample_mode, int db_tiled, uint64_t hint_db, const float* __restrict__ eps, const float* __restrict__ thr0,
                  uint64_t* __restrict__ pool_items, int* __restrict__ pool_count, uint32_t* __restrict__ pool_thr, const InlineBoot boot) {
     extern __shared__ uint8_t smem_raw[];
@@ -195,10 +195,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
     const int n_jobs = m_units * splits;
+    // The database tiles of a job.  Default: whole tiles t0 .. t1.  half_units (single-CTA shapes, main pass): the database is
+    // dealt in HALF tiles of 128 rows so that the jobs differ by at most half a tile (3 or 4 tiles per CTA on an 8-GPU shard is a
+    // 33 % longer critical path, 3 or 3.5 is 17 %); a job is then [lone half] whole tiles ... [lone half], a lone half being a
+    // 128-row TMA box (second tensor map) and an N = 128 MMA into the same accumulator.
+    constexpr uint32_t IDESC_HALF = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((GEMM_BN / 2) >> 3) << 17) | ((uint32_t)(S::UMMA_M >> 4) << 24);
+    auto job_range = [&](int sp, int& u, int& u1) {
+        const int total = half_units ? 2 * n_tiles : n_tiles;
+        u = (int)((int64_t)sp * total / splits); u1 = (int)((int64_t)(sp + 1) * total / splits);
+    };
+    auto next_unit = [&](int& u, int u1, int& row0, int& ncols) {
+        if (half_units) {
+            const bool half = (u & 1) || (u + 2 > u1);
+            row0 = u * (GEMM_BN / 2); ncols = half ? GEMM_BN / 2 : GEMM_BN; u += half ? 1 : 2;
+        } else { row0 = u * tile_stride * TILE_N; ncols = TILE_N; u += 1; }
+    };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_db) : "memory");
+        if (half_units) asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_db_h) : "memory");
         // pair: the leader's `full` collects its own arrive(+expect_tx) and the peer's remote arrive; the
         // leader's `tempty` collects the 128 epilogue threads of BOTH CTAs
         for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), PAIR ? 2 : 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
@@ -230,14 +246,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int job = unit; job < n_jobs; job += n_units) {
                 const int sp = job / m_units, mu = job - sp * m_units;
                 const int mt = PAIR ? 2 * mu + (int)cta_rank : mu;
-                const int t0 = (int)((int64_t)sp * n_tiles / splits), t1 = (int)((int64_t)(sp + 1) * n_tiles / splits);
-                for (int t = t0; t < t1; ++t) {
+                int u, u1;
+                job_range(sp, u, u1);
+                while (u < u1) {
+                    int row0, ncols;
+                    next_unit(u, u1, row0, ncols);
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
                         const uint32_t full = smem_u32(&bars->full[stage]);
                         // database operand coordinates: row-major [n_pad][d_pad] -> (k, row); tiled
                         // [n_pad/256][d_pad/64][256][64] (every box one contiguous 16/32 KB run) -> (0, ((row/256)*KB + kb)*256 + row%256)
-                        const int brow = t * tile_stride * TILE_N + (PAIR ? (int)cta_rank * S::B_ROWS : 0);
+                        const int brow = row0 + (PAIR ? (int)cta_rank * S::B_ROWS : 0);
                         const int bc0 = db_tiled ? 0 : kb * GEMM_BK;
                         const int bc1 = db_tiled ? (((brow >> 8) * k_blocks + kb) << 8) + (brow & 255) : brow;
                         if constexpr (PAIR) {
@@ -246,9 +265,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             tma_load_2d_pair(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
                             tma_load_2d_pair(smem_u32(sB + stage * B_BYTES), &tmap_db, full, bc0, bc1, HINT_EVICT_LAST);
                         } else {
-                            mbar_expect_tx(full, STAGE_BYTES);
+                            const bool lone_half = ncols != TILE_N;
+                            mbar_expect_tx(full, A_BYTES + ncols * GEMM_BK * 2);
                             tma_load_2d(smem_u32(sA + stage * A_BYTES), &tmap_q, full, kb * GEMM_BK, a_row0 + mt * GEMM_BM, HINT_EVICT_LAST);
-                            tma_load_2d(smem_u32(sB + stage * B_BYTES), &tmap_db, full, bc0, bc1, hint_db);
+                            tma_load_2d(smem_u32(sB + stage * B_BYTES), lone_half ? &tmap_db_h : &tmap_db, full, bc0, bc1, hint_db);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -262,8 +282,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             for (int job = unit; job < n_jobs; job += n_units) {
                 const int sp = job / m_units;
-                const int t0 = (int)((int64_t)sp * n_tiles / splits), t1 = (int)((int64_t)(sp + 1) * n_tiles / splits);
-                for (int t = t0; t < t1; ++t, ++it) {
+                int u, u1;
+                job_range(sp, u, u1);
+                for (; u < u1; ++it) {
+                    int row0, ncols;
+                    next_unit(u, u1, row0, ncols);
+                    const uint32_t idesc = (ncols == TILE_N) ? S::IDESC : IDESC_HALF;
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                     mbar_wait(smem_u32(&bars->tempty[acc]), acc_phase ^ 1);      // epilogue(s) drained this accumulator
                     tc_fence_after();
@@ -275,8 +299,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
 #pragma unroll
                         for (int kk = 0; kk < GEMM_BK / 16; ++kk) {               // +32 B per K=16 step inside the atom
-                            if constexpr (PAIR) tc_mma_bf16_pair(d_tmem, da + 2 * kk, db + 2 * kk, S::IDESC, (kb | kk) != 0);
-                            else                tc_mma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, S::IDESC, (kb | kk) != 0);
+                            if constexpr (PAIR) tc_mma_bf16_pair(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+                            else                tc_mma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
                         }
                         // frees the smem slot (in both CTAs) when the MMAs retire
                         if constexpr (PAIR) tc_commit_pair(smem_u32(&bars->empty[stage])); else tc_commit(smem_u32(&bars->empty[stage]));
@@ -305,7 +329,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int job = unit; job < n_jobs; job += n_units) {
             const int sp = job / m_units, mu = job - sp * m_units;
             const int mt = PAIR ? 2 * mu + (int)cta_rank : mu;
-            const int t0 = (int)((int64_t)sp * n_tiles / splits), t1 = (int)((int64_t)(sp + 1) * n_tiles / splits);
+            int u, u1;
+            job_range(sp, u, u1);
             const int64_t q = (int64_t)mt * GEMM_BM + m;
             const bool active = q < nq;
             const int64_t slot = ((int64_t)mt * splits + sp) * GEMM_BM + m;
@@ -316,7 +341,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (__ballot_sync(0xffffffffu, active) == 0u) {
                 // all 32 query rows of this warp are tile padding (e.g. rows 96..127 of a 70-query batch): nothing to
                 // read back -- only hand the accumulators over so that the MMA thread can go on
-                for (int t = t0; t < t1; ++t, ++it) {
+                for (; u < u1; ++it) {
+                    int row0, ncols;
+                    next_unit(u, u1, row0, ncols);
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                     mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
                     release_acc(acc);
@@ -329,7 +356,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 // Threshold bootstrap: per tile only 8 scores are kept -- the maxima of its 8 column groups (branch-free:
                 // one max per score).  They are real scores, so the k-th best of the union over all sampled tiles is a
                 // valid lower bound of the database's k-th best.  No lists, no trims.  (One tile per job.)
-                for (int t = t0; t < t1; ++t, ++it) {
+                for (; u < u1; ++it) {
+                    int row0, ncols;
+                    next_unit(u, u1, row0, ncols);
                     const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                     mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
                     tc_fence_after();
@@ -339,7 +368,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         uint32_t v[32];
                         tc_ld32(taddr + c * 32, v);
                         tc_ld_wait();
-                        const int64_t lim = n_valid - ((int64_t)t * tile_stride * TILE_N + c * 32);
+                        const int64_t lim = n_valid - ((int64_t)row0 + c * 32);
                         constexpr int G = TILE_N / 8;                          // columns per group: 32 (256-row tiles) or 16
                         float gmax[32 / G];
 #pragma unroll
@@ -356,14 +385,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 continue;
             }
             // one accumulator -> this thread's list: keep what beats the running threshold, trim a list that could overflow
-            auto filter_tile = [&](uint32_t acc, int t) {
+            auto filter_tile = [&](uint32_t acc, int row0, int ncols) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * GEMM_BN;
 #pragma unroll 1
-                for (int c = 0; c < TILE_N / 32; ++c) {
+                for (int c = 0; c < ncols / 32; ++c) {
                     uint32_t v[32];
                     tc_ld32(taddr + c * 32, v);
                     tc_ld_wait();
-                    const int64_t row_base = (int64_t)t * tile_stride * TILE_N + c * 32;
+                    const int64_t row_base = (int64_t)row0 + c * 32;
                     const int64_t lim = n_valid - row_base;                 // rows >= n_valid are zero padding
                     if (lim >= 32) {
 #pragma unroll
@@ -391,8 +420,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     }
                 }
             };
-            int t_first = t0;
             if (boot.on) {
+                int row_first, ncols_first;
+                next_unit(u, u1, row_first, ncols_first);          // the job's first unit (a whole tile or a lone half) is the sample
                 // ---- in-kernel threshold bootstrap (one job per CTA, every CTA resident) ------------------------------
                 // The FIRST tile of every CTA doubles as the sample: (A) its 8 best scores per query go to global memory,
                 // (B) once all CTAs have arrived, CTA c takes the k-th best of query c's sample (a valid lower bound of the
@@ -408,14 +438,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
                     float* dst = boot.samp + ((size_t)q * gridDim.x + blockIdx.x) * 8;
 #pragma unroll 1
-                    for (int c = 0; c < TILE_N / 32; ++c) {                  // the maximum of every 32-column group: one max per score
-                        uint32_t v[32];
-                        tc_ld32(taddr + c * 32, v);
-                        tc_ld_wait();
-                        const int64_t lim = n_valid - ((int64_t)t0 * tile_stride * TILE_N + c * 32);
+                    for (int c = 0; c < 8; ++c) {                            // the maximum of every 32-column group: one max per score
                         float gmax = -INFINITY;
+                        if (c < ncols_first / 32) {                          // (uniform)
+                            uint32_t v[32];
+                            tc_ld32(taddr + c * 32, v);
+                            tc_ld_wait();
+                            const int64_t lim = n_valid - ((int64_t)row_first + c * 32);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) gmax = fmaxf(gmax, (i < lim) ? __uint_as_float(v[i]) : -INFINITY);
+                            for (int i = 0; i < 32; ++i) gmax = fmaxf(gmax, (i < lim) ? __uint_as_float(v[i]) : -INFINITY);
+                        }
                         if (active) dst[c] = gmax;
                     }
                 }
@@ -506,17 +538,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     thr = __uint_as_float((uint32_t)w);
                 }
                 __syncwarp();
-                filter_tile(0u, t0);
+                filter_tile(0u, row_first, ncols_first);
                 release_acc(0u);
                 BOOT_STAMP(5);                                   // first accumulator handed back
-                t_first = t0 + 1;
                 it = 1;
             }
-            for (int t = t_first; t < t1; ++t, ++it) {
+            for (; u < u1; ++it) {
+                int row0, ncols;
+                next_unit(u, u1, row0, ncols);
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 mbar_wait(smem_u32(&bars->tfull[acc]), acc_phase);
                 tc_fence_after();
-                filter_tile(acc, t);
+                filter_tile(acc, row0, ncols);
                 release_acc(acc);
             }
             // end of job: keep only what can still matter -- everything within 2*eps below this
@@ -588,6 +621,7 @@ GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_spl
     // in-kernel threshold bootstrap: one query tile, exactly one job per CTA (so every CTA is resident and its first tile
     // can serve as the sample), and a sample that holds well over k scores
     p.inline_boot = 0;
+    p.half_units = p.pair ? 0 : 1;                    // single-CTA shapes deal the database in half tiles (balance)
     if (!p.pair && p.m_tiles == 1 && forced_splits <= 0 && p.n_tiles >= 16) {
         const int s = p.n_tiles < num_sms ? p.n_tiles : num_sms;
         if (s <= BOOT_MAX_GRID && 8 * s >= (5 * k + 3) / 4 + 8) { p.splits = s; p.grid = s; p.inline_boot = 1; }
@@ -617,12 +651,13 @@ GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k) {
     p.sample_mode = 1;                              // 8 group maxima per (query, tile)
     p.inline_boot = 0;
     p.stages3 = 0;
+    p.half_units = 0;
     const int64_t jobs = (int64_t)p.m_tiles * p.splits;
     p.grid = (int)(jobs < num_sms ? jobs : num_sms);
     return p;
 }
 
-cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
+cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const CUtensorMap* tmap_db_half, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
                              const float* thr0, const InlineBoot* boot, cudaStream_t st) {
@@ -656,7 +691,8 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
         if (!boot || !boot->samp || !boot->arrive || !boot->thr_pub || plan.grid != plan.splits || plan.pair || plan.half) return cudaErrorInvalidValue;
         ib = *boot; ib.on = 1;
     }
-    return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, k_blocks,
+    const int half_units = (plan.half_units && tmap_db_half && !plan.pair && !plan.half && !plan.sample_mode && plan.tile_stride == 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, tmap_q, tmap_db, half_units ? *tmap_db_half : tmap_db, plan.m_tiles, plan.n_tiles, plan.tile_stride, plan.splits, half_units, k_blocks,
                               a_row0, nq, n_valid, k, plan.k_keep, plan.cap, plan.sample_mode, plan.db_tiled, hint_db, eps, thr0,
                               pool_items, pool_count, pool_thr, ib);
 }

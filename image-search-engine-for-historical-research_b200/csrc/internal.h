@@ -80,6 +80,7 @@ struct GemmPlan {
     int sample_mode;  // 1: threshold bootstrap pass (8 best scores per query and tile, no ids)
     int tile_stride;  // database tile t of the plan is tile t * tile_stride of the matrix (sample pass > 1)
     int inline_boot;  // 1: one job per CTA; the first tile of every CTA is the threshold sample (no separate bootstrap launch)
+    int half_units;   // 1: single-CTA shapes deal the database in half tiles of 128 rows (jobs differ by at most half a tile)
     int stages3;      // 1: single-CTA shape with a 3-stage operand ring (leaves shared memory for a co-resident finalise CTA)
 };
 // In-kernel threshold bootstrap of gemm_topk_kernel (plan.inline_boot): the CTAs meet once through these words.
@@ -98,7 +99,8 @@ struct InlineBoot {
 GemmPlan plan_gemm(int64_t nq, int64_t n_pad, int k, int num_sms, int forced_splits, bool allow_pair);
 GemmPlan plan_gemm_sample(const GemmPlan& main_plan, int num_sms, int k);
 // tmap_q: [nq_pad128][d_pad] bf16, box {64,128};  tmap_db: [n_pad][d_pad] bf16, box {64,256} (box {64,128} when plan.pair)
-cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const GemmPlan& plan,
+//   tmap_db_half: the 128-row-box map of the same database (for plan.half_units; may be null)
+cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_db, const CUtensorMap* tmap_db_half, const GemmPlan& plan,
                              int64_t nq, int64_t n_valid, int d_pad, int k, const float* eps,
                              uint64_t* pool_items, int* pool_count, uint32_t* pool_thr, int a_row0,
                              const float* thr0, const InlineBoot* boot, cudaStream_t st);
