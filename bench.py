@@ -455,11 +455,18 @@ def run_ours(args):
         ids_pin = torch.empty((N_QUERIES, TOPK), dtype=torch.int64).pin_memory()
         sims_pin = torch.empty((N_QUERIES, TOPK), dtype=torch.float32).pin_memory()
 
+    # the blocking (latency) form at N > 1: one step at a time through a one-lane native pipeline with its own mailboxes --
+    # the index's latency shapes (4-stage scan ring, six finalise CTAs per query), certificates checked before the copy back
+    e2e_searcher, e2e_exchange = searcher, None
+    if native and world > 1 and not replicas:
+        e2e_exchange = sharded.PeerExchange(local, N_QUERIES, TOPK)
+        _, e2e_searcher = sharded.make_searcher(index, local, lanes=1, exchange=e2e_exchange, pipeline=(N_QUERIES, TOPK))
+
     def e2e_step():
         if world == 1 or replicas:
             return index.search(q_np, TOPK)                       # pinned host queries in, ids + scores back on the host
         qd.copy_(q_host, non_blocking=True)
-        i_d, s_d = searcher.search(qd, TOPK)
+        i_d, s_d = e2e_searcher.search(qd, TOPK)
         ids_pin.copy_(i_d, non_blocking=True)
         sims_pin.copy_(s_d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -475,6 +482,10 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     reruns = int(searcher.n_rerun) + (int(index.stats()["n_exact_rerun"]) if (world == 1 or replicas) else 0)
+    if e2e_exchange is not None:
+        reruns += int(e2e_searcher.n_rerun)
+        e2e_searcher.close()
+        e2e_exchange.close()
 
     # ---- dominant kernel, timed on its own stream by the library's CUDA events --------------------------
     coarse = []
