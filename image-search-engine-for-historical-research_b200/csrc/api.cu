@@ -81,6 +81,7 @@ struct xs_index {
     __nv_bfloat16* db16t = nullptr;              // tiled twin of db16 for the GEMM's database operand (optional)
     CUtensorMap tmap_db_b, tmap_db_a;            // db16 as GEMM operand B (box 256 rows) / A (box 128 rows, self-kNN)
     CUtensorMap tmap_dbt_b, tmap_dbt_h;          // tiled twin: boxes of 256 / 128 rows, each one contiguous run
+    CUtensorMap tmap_q_cached; const void* tmap_q_base = nullptr; int64_t tmap_q_rows = 0;   // query operand map of the last GEMM call
     // tunables
     float eps_sigmas = 8.f; int scan_max_q = 1; int force_path = 0; int gemm_splits = 0; int sample_pass = 1; int pair_mode = 1; int timing = 0;
     int eps_mode = 0;                             // certificate: 0 = statistical band (8 sigma, random rotation, model check), 1 = worst-case band
@@ -823,7 +824,14 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
             const CUtensorMap* ta = a.tmap_a;
             int64_t row0 = a.a_row0 + q0;
             if (!ta) {
-                XS_TRY(make_tmap(&tmap_q, ix->q16.as<__nv_bfloat16>() + q0 * ix->d_pad, round_up(c, GEMM_BM), ix->d_pad, GEMM_BM));
+                // the query operand's tensor map only depends on (address, rows): encoded once per shape, not per step
+                const void* qbase = ix->q16.as<__nv_bfloat16>() + q0 * ix->d_pad;
+                const int64_t qrows = round_up(c, GEMM_BM);
+                if (ix->tmap_q_base != qbase || ix->tmap_q_rows != qrows) {
+                    XS_TRY(make_tmap(&ix->tmap_q_cached, qbase, qrows, ix->d_pad, GEMM_BM));
+                    ix->tmap_q_base = qbase; ix->tmap_q_rows = qrows;
+                }
+                tmap_q = ix->tmap_q_cached;
                 ta = &tmap_q; row0 = 0;
             }
             // threshold bootstrap on a strided sample of database tiles (skipped when the sample would be the whole database)

@@ -879,8 +879,15 @@ bool launch_finalise(const FinaliseArgs& a_in, int64_t nq, cudaStream_t st) {
             if (S == 0 || cand <= want) S = cand;
         }                                                         // S == 0: more lists than a cluster can take -> the two-kernel form below
         if (S) {
-            cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 96 * 1024 ? smem : 96 * 1024));
-            cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+            static size_t attr_smem[64] = {};                     // largest size the attribute has been raised to, per device
+            int dev = 0;
+            cudaGetDevice(&dev);
+            const size_t want_attr = smem > 96 * 1024 ? smem : 96 * 1024;
+            if (dev < 0 || dev >= 64 || attr_smem[dev] < want_attr) {
+                cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want_attr);
+                cudaFuncSetAttribute(finalise_cluster_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+                if (dev >= 0 && dev < 64) attr_smem[dev] = want_attr;
+            }
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)S, (unsigned)nq); cfg.blockDim = dim3(FF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
             cudaLaunchAttribute attr[2];

@@ -664,11 +664,20 @@ cudaError_t launch_gemm_topk(const CUtensorMap& tmap_q, const CUtensorMap& tmap_
     const bool three = plan.stages3 && !plan.pair && !plan.half;
     auto kern = plan.pair ? gemm_topk_kernel<MODE_PAIR> : (plan.half ? gemm_topk_kernel<MODE_HALF> : (three ? gemm_topk_kernel<MODE_FULL3> : gemm_topk_kernel<MODE_FULL>));
     const size_t smem_bytes = three ? GEMM_SMEM3 : GEMM_SMEM;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    // the SM's whole 228 KB as shared memory whatever this kernel needs: with the 3-stage ring the 70 KB it leaves are for a
-    // finalise CTA of the other lane (the driver would otherwise carve out just enough for this kernel and nothing else fits)
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    // function attributes are set once per kernel shape and device (each call is a driver round trip on the per-step host path)
+    const int shape = plan.pair ? 1 : (plan.half ? 2 : (three ? 3 : 0));
+    static unsigned char attr_done[4][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaSuccess;
+    if (dev < 0 || dev >= 64 || !attr_done[shape][dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        // the SM's whole 228 KB as shared memory whatever this kernel needs: with the 3-stage ring the 70 KB it leaves are for a
+        // finalise CTA of the other lane (the driver would otherwise carve out just enough for this kernel and nothing else fits)
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (dev >= 0 && dev < 64) attr_done[shape][dev] = 1;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)plan.grid);
     cfg.blockDim = dim3(GEMM_THREADS);

@@ -416,6 +416,8 @@ class PipelinedSearcher:
                                               int(lanes), C.byref(self._h)), "xs_pipeline_create")
         self._pending = [None, None]
         self._next = 0
+        self._views = {}
+        self._flag_buf = (C.c_int32 * self.nq_max)()
 
     def close(self):
         if self._h:
@@ -452,12 +454,16 @@ class _PipelineHandle:
         torch = o.torch
         stream = torch.cuda.current_stream(o.device).cuda_stream
         pi, ps, nf = C.c_void_p(), C.c_void_p(), C.c_int64(0)
-        flagged = (C.c_int32 * self.nq)()
+        flagged = o._flag_buf
         nat.check(o.lib.xs_pipeline_collect(o._h, self.slot, C.c_void_p(stream) if stream else None, C.byref(pi), C.byref(ps), C.byref(nf), flagged),
                   "xs_pipeline_collect")
         self.collected = True
-        ids = _wrap_device(torch, pi.value, (self.nq, self.k), torch.int64, o.device)
-        sims = _wrap_device(torch, ps.value, (self.nq, self.k), torch.float32, o.device)
+        key = (pi.value, ps.value, self.nq, self.k)
+        views = o._views.get(key)
+        if views is None:                           # the slot's result buffers do not move: wrap them once
+            views = o._views[key] = (_wrap_device(torch, pi.value, (self.nq, self.k), torch.int64, o.device),
+                                     _wrap_device(torch, ps.value, (self.nq, self.k), torch.float32, o.device))
+        ids, sims = views
         if nf.value:
             if o.fallback is None:
                 raise RuntimeError(f"{nf.value} queries could not be certified and no exact fallback was configured")
