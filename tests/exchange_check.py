@@ -97,6 +97,13 @@ def main():
         assert np.array_equal(h.result()[0].cpu().numpy(), want_i)
     pipe.close()
     ex_p.close()
+    # the one-call form with the merge riding in the search's last kernel (xs_search_dev_exchange), both slots, twice round
+    ex_f = sharded.PeerExchange(local, 70, 100)
+    for step in range(4):
+        fi, fs, fst = shard.local_exchange(q, 100, ex_f, step & 1)
+        torch.cuda.synchronize()
+        assert np.array_equal(fi.cpu().numpy(), want_i) and int(fst.sum().item()) == 0, f"rank {rank}: fused exchange step {step}"
+    ex_f.close()
     index.close()
 
     # families where shards cannot certify every query: the certificate words travel with the lists and the flagged
