@@ -1382,7 +1382,7 @@ static int search_exchange(xs_index* ix, const float* q_dev, int64_t nq, int ren
     XS_TRY(search_core(ix, a));
     ++ex->push_epoch[slot];
     if (want_merge) {
-        if (merged) { ++ex->merge_epoch[slot]; ix->stats.gpu_launches += 0; }
+        if (merged) ++ex->merge_epoch[slot];
         else {
             lk2.unlock();
             XS_TRY(xs_exchange_merge(ex, slot, nq, k, out_idx, out_score, out_status, stream));

@@ -30,6 +30,5 @@ for rep in range(2):
     t0 = time.time()
     oi, _, osc = pkg.diffusion.offline_device(d.knn.index, T, kd)
     t1 = time.time()
-    print(f"device-resident pipeline (xs_diffusion_offline), all {n} rows: {t1-t0:.2f}s  (stagewise above: self-kNN + Laplacian + CG = {(t2 - t0_all) if False else 0:.0f})" if False else
-          f"device-resident pipeline (xs_diffusion_offline), all {n} rows: {t1-t0:.2f}s", flush=True)
+    print(f"device-resident pipeline (xs_diffusion_offline), all {n} rows: {t1-t0:.2f}s", flush=True)
 print("device pipeline vs stagewise: ids equal", bool((oi == ids).all()), " max |score diff| =", float(np.abs(osc - out).max()))
