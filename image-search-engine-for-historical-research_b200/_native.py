@@ -100,7 +100,8 @@ def load() -> C.CDLL:
 
 
 def config_set(name: str, value: float) -> None:
-    """Process-wide defaults picked up by later index builds (xs_config_set): ``rotation`` 0/1, ``rotation_seed``."""
+    """Process-wide defaults picked up by later index builds (xs_config_set): ``rotation`` 0/1, ``rotation_seed``,
+    ``compact`` 1/0 (one tiled bf16 copy of the database, or the row-major copy next to it as well)."""
     check(load().xs_config_set(name.encode(), float(value)), "xs_config_set")
 
 

@@ -1,7 +1,8 @@
 // C ABI (include/xs_b200.h) and host-side orchestration of the exhaustive matcher.
 //
-// Data in HBM per index:  db32 [n][d_pad] fp32 (exact operand), db16 [n_pad][d_pad] bf16 (coarse
-// operand, n_pad = multiple of 256 so TMA boxes never straddle the end), a grow-only workspace
+// Data in HBM per index:  db32 [n][d_pad] fp32 (exact operand), db16t = the rotated rows in bf16, tiled
+// [n_pad/256][d_pad/64][256][64] (coarse operand of the GEMM and of the batch-1 scan; n_pad = multiple of 256 so TMA
+// boxes never straddle the end; the row-major form db16 only with "compact" 0), a grow-only workspace
 // (query copies, score rows, candidate pools, results).  One search = prep_queries -> coarse
 // kernel (batch-1 scan | tcgen05 GEMM with fused top-K) -> finalise (exact rescoring + sort),
 // all on one stream; uncertified queries are re-run on the exact fp32 path.
@@ -88,6 +89,7 @@ struct xs_index {
     int inline_boot = 1;                          // small batches: threshold bootstrap inside the GEMM launch (0: separate sample pass)
     int half_units = 1;                           // single-CTA GEMM shapes: deal the database in half tiles (0: whole tiles)
     int gemm_stages = 4;                          // operand ring of the single-CTA GEMM shape: 4 stages, or 3 to leave room for a co-resident finalise CTA
+    int scan_tiled = 1;                           // batch-1 scan reads the tiled twin when there is one (0: the row-major copy, while it is kept)
     int fin_per_sm = 0;                           // cluster finalise: 0 = latency mode (three CTAs per SM), 1 = one slim CTA per SM, resident next to a GEMM CTA
     bool rotate = true; uint32_t rot_seed = 0;    // random rotation applied before bf16 rounding (fixed at build time)
     uint32_t boot_arrived = 0, boot_published = 0, boot_epoch = 0;    // host mirrors of the in-kernel bootstrap's counters / epoch
@@ -98,7 +100,7 @@ struct xs_index {
     Buf boot_samp, boot_sync, boot_trace, q32r, sbound;
     int boot_trace_on = 0, boot_trace_grid = 0;
     Buf fin_trace; int fin_trace_rows = 0;
-    Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage;
+    Buf fin_work, fin_ticket, aqe_ids, q_raw, q32, q16, eps, thr0, ghist, sort_work, rank_out, rank_scores, scores, pool_items, pool_count, pool_thr, status, ncand, out_idx, out_score, stage, stage16;
     PinnedBuf h_idx, h_score, h_status;           // pinned landing zone of the host API (one sync per call)
     PinnedBuf h_aqe;                              // pinned staging of xs_aqe_search's id lists
     cudaStream_t stream = nullptr;                // the index's own stream (host API, build)
@@ -147,6 +149,12 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 static std::mutex g_cfg_mu;
 static int g_rotate = -1;                         // -1: not set -> on unless XS_NO_ROTATE=1
 static uint32_t g_rot_seed = 0x5EEDB200u;
+static int g_compact = -1;                        // -1: not set -> on unless XS_KEEP_ROWMAJOR=1
+static bool default_compact() {
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    if (g_compact < 0) { const char* e = getenv("XS_KEEP_ROWMAJOR"); g_compact = (e && atoi(e)) ? 0 : 1; }
+    return g_compact != 0;
+}
 static void default_rotation(bool* on, uint32_t* seed) {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
     if (g_rotate < 0) { const char* e = getenv("XS_NO_ROTATE"); g_rotate = (e && atoi(e)) ? 0 : 1; }
@@ -157,6 +165,7 @@ extern "C" int xs_config_set(const char* name, double value) {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
     if (!strcmp(name, "rotation")) g_rotate = value != 0.0 ? 1 : 0;
     else if (!strcmp(name, "rotation_seed")) g_rot_seed = (uint32_t)(uint64_t)value;
+    else if (!strcmp(name, "compact")) g_compact = value != 0.0 ? 1 : 0;
     else return fail(XS_ERR_ARG, "unknown configuration key '%s'", name);
     return XS_OK;
 }
@@ -173,7 +182,7 @@ extern "C" int xs_device_count(int* count) {
 }
 
 // ---- index lifecycle -------------------------------------------------------------------------------------
-static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_offset) {
+static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_offset, bool rowmajor16 = true) {
     if (n <= 0 || d <= 0) return fail(XS_ERR_ARG, "empty database (n=%lld, d=%d)", (long long)n, d);
     if (n >= (int64_t)0xFFFFFF00u) return fail(XS_ERR_UNSUPPORTED, "more than 2^32-256 rows per index; shard the database");
     // the rescoring kernels stage eight fp32 rows per CTA in shared memory and the row kernels one: 4096 columns is what fits
@@ -189,15 +198,16 @@ static int index_alloc(xs_index* ix, int64_t n, int d, int device, int64_t id_of
     default_rotation(&ix->rotate, &ix->rot_seed);
     const size_t b32 = (size_t)n * ix->d_pad * sizeof(float), b16 = (size_t)ix->n_pad * ix->d_pad * 2;
     CU_TRY(cudaMalloc(&ix->db32, b32));
-    CU_TRY(cudaMalloc(&ix->db16, b16));
+    if (rowmajor16) CU_TRY(cudaMalloc(&ix->db16, b16));
     CU_TRY(cudaMalloc(&ix->dstats, sizeof(DevStats)));
     ix->share = new DbShare();
     ix->share->db16 = ix->db16; ix->share->db32 = ix->db32; ix->share->dstats = ix->dstats;
-    ix->bytes = (int64_t)(b32 + b16);
+    ix->bytes = (int64_t)(b32 + (rowmajor16 ? b16 : 0));
     CU_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     for (auto& e : ix->ev) CU_TRY(cudaEventCreate(&e));
     CU_TRY(cudaMemsetAsync(ix->dstats, 0, sizeof(DevStats), ix->stream));
     // zero the padding rows of the bf16 copy (they are read by TMA boxes and by the scan's row groups)
+    if (!rowmajor16) return XS_OK;
     if (ix->n_pad > n) CU_TRY(cudaMemsetAsync(ix->db16 + (size_t)n * ix->d_pad, 0, (size_t)(ix->n_pad - n) * ix->d_pad * 2, ix->stream));
     XS_TRY(make_tmap(&ix->tmap_db_b, ix->db16, ix->n_pad, ix->d_pad, GEMM_BN));
     XS_TRY(make_tmap(&ix->tmap_db_a, ix->db16, ix->n_pad, ix->d_pad, GEMM_BM));
@@ -210,7 +220,7 @@ static void index_free(xs_index* ix) {
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     for (Buf* b : {&ix->boot_samp, &ix->boot_sync, &ix->boot_trace, &ix->fin_trace, &ix->q32r, &ix->sbound, &ix->fin_work, &ix->fin_ticket, &ix->aqe_ids, &ix->q_raw, &ix->q32, &ix->q16, &ix->eps, &ix->thr0, &ix->ghist, &ix->sort_work, &ix->rank_out, &ix->rank_scores, &ix->scores, &ix->pool_items, &ix->pool_count, &ix->pool_thr,
-                   &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage}) b->release();
+                   &ix->status, &ix->ncand, &ix->out_idx, &ix->out_score, &ix->stage, &ix->stage16}) b->release();
     ix->h_idx.release(); ix->h_score.release(); ix->h_status.release(); ix->h_aqe.release();
     if (ix->share) {
         bool last;
@@ -253,11 +263,49 @@ static int build_tiled_twin(xs_index* ix) {
     const size_t b16 = (size_t)ix->n_pad * ix->d_pad * 2;
     if (cudaMalloc(&ix->db16t, b16) != cudaSuccess) { cudaGetLastError(); ix->db16t = nullptr; return XS_OK; }   // optional: fall back to the row-major maps
     ix->share->db16t = ix->db16t;
-    launch_tile_db16(ix->db16, ix->db16t, ix->n_pad, ix->d_pad, ix->stream);
+    launch_tile_db16(ix->db16, ix->db16t, 0, ix->n_pad, ix->d_pad, ix->stream);
     CU_TRY(cudaStreamSynchronize(ix->stream));
     XS_TRY(make_tmap_tiled(&ix->tmap_dbt_b, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BN));
     XS_TRY(make_tmap_tiled(&ix->tmap_dbt_h, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BM));
     ix->bytes += (int64_t)b16;
+    // Compact index (the default): every reader of the bf16 copy -- the GEMM's TMA boxes and the batch-1 scan -- now has the
+    // tiled form, so the row-major one goes back to the allocator: 2 * d_pad bytes per row, 4.1 GB per million 2048-d rows.
+    if (default_compact()) {
+        CU_TRY(cudaFree(ix->db16));
+        ix->db16 = nullptr; ix->share->db16 = nullptr;
+        ix->bytes -= (int64_t)b16;
+    }
+    return XS_OK;
+}
+
+// Compact build: no row-major bf16 copy is ever allocated.  The tiled array is allocated up front (padding rows of the last
+// 256-row block zeroed); each staged chunk's bf16 rows land in a chunk-sized scratch and are tiled from there.
+static bool want_compact_build() {
+    const char* e = getenv("XS_NO_TILED");
+    return !(e && atoi(e)) && default_compact();
+}
+static int alloc_tiled(xs_index* ix) {
+    const size_t b16 = (size_t)ix->n_pad * ix->d_pad * 2;
+    if (cudaMalloc(&ix->db16t, b16) != cudaSuccess) { cudaGetLastError(); ix->db16t = nullptr; return fail(XS_ERR_NOMEM, "no memory for the bf16 database (%zu bytes)", b16); }
+    ix->share->db16t = ix->db16t;
+    ix->bytes += (int64_t)b16;
+    if (ix->n_pad > ix->n) {
+        const size_t block = (size_t)ROW_ALIGN * ix->d_pad * 2;          // one 256-row block, all its k-blocks: contiguous
+        CU_TRY(cudaMemsetAsync(reinterpret_cast<char*>(ix->db16t) + b16 - block, 0, block, ix->stream));
+    }
+    XS_TRY(make_tmap_tiled(&ix->tmap_dbt_b, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BN));
+    XS_TRY(make_tmap_tiled(&ix->tmap_dbt_h, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BM));
+    return XS_OK;
+}
+// fp32 rows r0 .. r0 + rows are in place in db32: finish them (normalise / rotate / statistics / bf16) into the layout(s) kept.
+static int finish_chunk(xs_index* ix, int64_t r0, int64_t rows, bool renormalise) {
+    if (ix->db16) {
+        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise, ix->rotate, ix->rot_seed, ix->dstats, ix->stream);
+        return XS_OK;
+    }
+    XS_TRY(ix->stage16.ensure((size_t)rows * ix->d_pad * 2));
+    launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->stage16.as<__nv_bfloat16>(), rows, ix->d_pad, renormalise, ix->rotate, ix->rot_seed, ix->dstats, ix->stream);
+    launch_tile_db16(ix->stage16.as<__nv_bfloat16>(), ix->db16t, r0, rows, ix->d_pad, ix->stream);
     return XS_OK;
 }
 
@@ -382,7 +430,9 @@ extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int6
     bool colmajor = false;
     XS_TRY(check_layout(dtype, n, d, stride_row, stride_col, &colmajor));
     xs_index* ix = new xs_index();
-    int rc = index_alloc(ix, n, d, device, id_offset);
+    const bool compact = want_compact_build();
+    int rc = index_alloc(ix, n, d, device, id_offset, !compact);
+    if (rc == XS_OK && compact) rc = alloc_tiled(ix);
     if (rc != XS_OK) { index_free(ix); return rc; }
     const size_t es = dtype == XS_F64 ? 8 : 4;
     // The caller's matrix is pageable.  Worker threads copy a chunk of rows into a ring of pinned buffers (contiguous runs
@@ -416,11 +466,11 @@ extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int6
         if (e == cudaSuccess) e = cudaEventRecord(g_ring.ev[slot], ix->stream);
         if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); break; }
         launch_layout_rows(ix->stage.p, dtype, colmajor, colmajor ? rows : d, rows, d, ix->d_pad, ix->db32 + (size_t)r0 * ix->d_pad, ix->stream);
-        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->rotate, ix->rot_seed, ix->dstats, ix->stream);
+        rc = finish_chunk(ix, r0, rows, renormalise != 0);
     }
     if (rc == XS_OK) { cudaError_t e = cudaStreamSynchronize(ix->stream); if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); }
-    ix->stage.release();
-    if (rc == XS_OK) rc = build_tiled_twin(ix);
+    ix->stage.release(); ix->stage16.release();
+    if (rc == XS_OK && !compact) rc = build_tiled_twin(ix);
     if (rc != XS_OK) { index_free(ix); return rc; }
     *out = ix;
     return XS_OK;
@@ -429,17 +479,21 @@ extern "C" int xs_index_create(const void* db, int dtype, int64_t n, int d, int6
 extern "C" int xs_index_create_dev(const float* db_dev, int64_t n, int d, int device, int renormalise, int64_t id_offset, xs_index** out) {
     if (!db_dev || !out) return fail(XS_ERR_ARG, "null pointer");
     xs_index* ix = new xs_index();
-    int rc = index_alloc(ix, n, d, device, id_offset);
+    const bool compact = want_compact_build();
+    int rc = index_alloc(ix, n, d, device, id_offset, !compact);
+    if (rc == XS_OK && compact) rc = alloc_tiled(ix);
     if (rc != XS_OK) { index_free(ix); return rc; }
-    const int64_t chunk = 1 << 20;
-    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t chunk = compact ? (1 << 16) : (1 << 20);                // compact: the chunk's bf16 rows pass through a scratch of this many rows
+    for (int64_t r0 = 0; r0 < n && rc == XS_OK; r0 += chunk) {
         const int64_t rows = (n - r0 < chunk) ? n - r0 : chunk;
         launch_layout_rows(db_dev + (size_t)r0 * d, XS_F32, false, d, rows, d, ix->d_pad, ix->db32 + (size_t)r0 * ix->d_pad, ix->stream);
-        launch_finish_rows(ix->db32 + (size_t)r0 * ix->d_pad, ix->db16 + (size_t)r0 * ix->d_pad, rows, ix->d_pad, renormalise != 0, ix->rotate, ix->rot_seed, ix->dstats, ix->stream);
+        rc = finish_chunk(ix, r0, rows, renormalise != 0);
     }
+    if (rc != XS_OK) { index_free(ix); return rc; }
     cudaError_t e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, "index build failed: %s", cudaGetErrorString(e)); index_free(ix); return rc; }
-    rc = build_tiled_twin(ix);
+    ix->stage16.release();
+    if (!compact) rc = build_tiled_twin(ix);
     if (rc != XS_OK) { index_free(ix); return rc; }
     *out = ix;
     return XS_OK;
@@ -453,20 +507,20 @@ extern "C" int xs_index_save(xs_index* ix, const char* path) {
     XS_TRY(g_ring.ensure());
     IndexFileHeader h{};
     memcpy(h.magic, "XSB200\0\1", 8);
-    h.version = 1; h.flags = (ix->rotate ? 1u : 0u) | (ix->db16t ? 2u : 0u);
+    h.version = 1; h.flags = (ix->rotate ? 1u : 0u) | (ix->db16t ? 2u : 0u) | (ix->db16 ? 0u : 4u);      // 4: no row-major bf16 section (compact index)
     h.n = ix->n; h.n_pad = ix->n_pad; h.d = ix->d; h.d_pad = ix->d_pad; h.rot_seed = ix->rot_seed;
     CU_TRY(cudaMemcpy(&h.stats, ix->dstats, sizeof(DevStats), cudaMemcpyDeviceToHost));
     h.bytes32 = (uint64_t)ix->n * ix->d_pad * 4; h.bytes16 = (uint64_t)ix->n_pad * ix->d_pad * 2;
     h.off32 = FILE_ALIGN;
     h.off16 = (h.off32 + h.bytes32 + FILE_ALIGN - 1) / FILE_ALIGN * FILE_ALIGN;
-    h.off16t = (h.off16 + h.bytes16 + FILE_ALIGN - 1) / FILE_ALIGN * FILE_ALIGN;
+    h.off16t = ix->db16 ? (h.off16 + h.bytes16 + FILE_ALIGN - 1) / FILE_ALIGN * FILE_ALIGN : h.off16;
     const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) return fail(XS_ERR_ARG, "cannot create %s", path);
     char page[FILE_ALIGN] = {};
     memcpy(page, &h, sizeof h);
     int rc = pwrite_all(fd, page, FILE_ALIGN, 0) ? XS_OK : fail(XS_ERR_ARG, "cannot write %s", path);
     if (rc == XS_OK) rc = download_section(fd, h.off32, ix->db32, h.bytes32, ix->stream);
-    if (rc == XS_OK) rc = download_section(fd, h.off16, ix->db16, h.bytes16, ix->stream);
+    if (rc == XS_OK && ix->db16) rc = download_section(fd, h.off16, ix->db16, h.bytes16, ix->stream);
     if (rc == XS_OK && ix->db16t) rc = download_section(fd, h.off16t, ix->db16t, h.bytes16, ix->stream);
     close(fd);
     return rc;
@@ -479,8 +533,13 @@ extern "C" int xs_index_load(const char* path, int device, int64_t id_offset, xs
     IndexFileHeader h{};
     if (!pread_all(fd, &h, sizeof h, 0) || memcmp(h.magic, "XSB200\0\1", 8) != 0 || h.version != 1) { close(fd); return fail(XS_ERR_ARG, "%s is not an index file of this library", path); }
     std::lock_guard<std::mutex> lk2(g_ring.mu);
+    const char* no_tiled_env = getenv("XS_NO_TILED");
+    const bool no_tiled = no_tiled_env && atoi(no_tiled_env);
+    if ((h.flags & 4u) && !(h.flags & 2u)) { close(fd); return fail(XS_ERR_ARG, "%s holds no bf16 section at all", path); }
+    // compact: only the tiled twin is uploaded (a file written by a compact index holds nothing else)
+    const bool compact = (h.flags & 4u) || ((h.flags & 2u) && !no_tiled && default_compact());
     xs_index* ix = new xs_index();
-    int rc = index_alloc(ix, h.n, h.d, device, id_offset);
+    int rc = index_alloc(ix, h.n, h.d, device, id_offset, !compact);
     if (rc == XS_OK && (ix->d_pad != h.d_pad || ix->n_pad != h.n_pad)) rc = fail(XS_ERR_ARG, "%s was written with another padding", path);
     if (rc == XS_OK) rc = g_ring.ensure();
     if (rc == XS_OK) {
@@ -489,16 +548,18 @@ extern "C" int xs_index_load(const char* path, int device, int64_t id_offset, xs
         if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "xs_index_load: %s", cudaGetErrorString(e));
     }
     if (rc == XS_OK) rc = upload_section(fd, h.off32, ix->db32, h.bytes32, ix->stream);
-    if (rc == XS_OK) rc = upload_section(fd, h.off16, ix->db16, h.bytes16, ix->stream);
+    if (rc == XS_OK && !compact) rc = upload_section(fd, h.off16, ix->db16, h.bytes16, ix->stream);
     if (rc == XS_OK && (h.flags & 2u)) {
-        const char* e = getenv("XS_NO_TILED");
-        if (!(e && atoi(e)) && cudaMalloc(&ix->db16t, h.bytes16) == cudaSuccess) {
+        if ((compact || !no_tiled) && cudaMalloc(&ix->db16t, h.bytes16) == cudaSuccess) {
             ix->share->db16t = ix->db16t;
             rc = upload_section(fd, h.off16t, ix->db16t, h.bytes16, ix->stream);
             if (rc == XS_OK) rc = make_tmap_tiled(&ix->tmap_dbt_b, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BN);
             if (rc == XS_OK) rc = make_tmap_tiled(&ix->tmap_dbt_h, ix->db16t, ix->n_pad, ix->d_pad, GEMM_BM);
             if (rc == XS_OK) ix->bytes += (int64_t)h.bytes16;
-        } else { cudaGetLastError(); ix->db16t = nullptr; }
+        } else {
+            cudaGetLastError(); ix->db16t = nullptr;
+            if (compact && rc == XS_OK) rc = fail(XS_ERR_NOMEM, "xs_index_load: no memory for the bf16 database");
+        }
     }
     close(fd);
     if (rc == XS_OK) { cudaError_t e = cudaStreamSynchronize(ix->stream); if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, "xs_index_load: %s", cudaGetErrorString(e)); }
@@ -519,7 +580,7 @@ extern "C" int xs_index_destroy(xs_index* ix) {
 static void copy_tunables(xs_index* dst, const xs_index* src) {
     dst->eps_sigmas = src->eps_sigmas; dst->scan_max_q = src->scan_max_q; dst->force_path = src->force_path;
     dst->gemm_splits = src->gemm_splits; dst->sample_pass = src->sample_pass; dst->pair_mode = src->pair_mode;
-    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot; dst->gemm_stages = src->gemm_stages; dst->half_units = src->half_units; dst->fin_per_sm = src->fin_per_sm;
+    dst->eps_mode = src->eps_mode; dst->inline_boot = src->inline_boot; dst->gemm_stages = src->gemm_stages; dst->half_units = src->half_units; dst->fin_per_sm = src->fin_per_sm; dst->scan_tiled = src->scan_tiled;
 }
 
 // caller holds src->mu
@@ -573,6 +634,7 @@ extern "C" int xs_set_param(xs_index* ix, const char* name, double value) {
     else if (!strcmp(name, "gemm_stages")) ix->gemm_stages = ((int)value == 3) ? 3 : 4;
     else if (!strcmp(name, "half_units")) ix->half_units = (int)value != 0;
     else if (!strcmp(name, "fin_per_sm")) ix->fin_per_sm = (int)value == 1 ? 1 : 0;
+    else if (!strcmp(name, "scan_tiled")) ix->scan_tiled = (int)value != 0;
     else if (!strcmp(name, "self_lanes")) ix->self_lanes = ((int)value >= 2) ? 2 : 1;
     else return fail(XS_ERR_ARG, "unknown parameter '%s'", name);
     return XS_OK;
@@ -759,11 +821,12 @@ static int search_core(xs_index* ix, const CoreArgs& a) {
         XS_TRY(ix->pool_items.ensure((size_t)slots * cap * 8));
         XS_TRY(ix->pool_count.ensure((size_t)slots * 4));
         XS_TRY(ix->pool_thr.ensure((size_t)slots * 4));
+        const bool scan_tiled = ix->db16t && (ix->scan_tiled || !ix->db16);
         for (int64_t q0 = 0; q0 < nq; q0 += chunk_max) {
             const int c = (int)((nq - q0 < chunk_max) ? nq - q0 : chunk_max);
             CU_TRY(cudaMemsetAsync(ix->ghist.p, 0, (size_t)c * HIST_BINS * sizeof(uint32_t), ix->cur));
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[1], ix->cur));
-            launch_scan_scores(ix->db16, ix->q32r.as<float>() + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->dstats, ix->sbound.as<float>(), ix->num_sms, ix->cur);
+            launch_scan_scores(scan_tiled ? ix->db16t : ix->db16, scan_tiled, ix->q32r.as<float>() + q0 * ix->d_pad, c, ix->n, ix->d_pad, ix->scores.as<float>(), ix->n, ix->ghist.as<uint32_t>(), ix->dstats, ix->sbound.as<float>(), ix->num_sms, ix->cur);
             launches += (c + 1) / 2;
             if (timing && q0 == 0) CU_TRY(cudaEventRecord(ix->ev[2], ix->cur));
             launch_scores_to_pools(ix->scores.as<float>(), ix->n, c, ix->n, k, ix->eps.as<float>() + q0, ix->ghist.as<uint32_t>(), ix->sbound.as<float>(), false, ix->pool_items.as<uint64_t>(),
@@ -1144,7 +1207,8 @@ extern "C" int xs_self_knn(xs_index* ix, int64_t q_begin, int64_t q_end, int k, 
         CoreArgs a{};
         a.q32 = L->db32 + (size_t)r0 * L->d_pad; a.nq = c; a.k = k; a.prep = true; a.prep_renorm = false;   // rows are used as stored
         a.path = choose_path(L, c, k);
-        a.tmap_a = (a.path == PATH_GEMM) ? &L->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
+        a.tmap_a = (a.path == PATH_GEMM && L->db16) ? &L->tmap_db_a : nullptr;     // compact index: the rows go through prep like any query
+        a.a_row0 = r0; a.self_base = r0;
         a.out_idx = L->out_idx.as<int64_t>(); a.out_score = L->out_score.as<float>(); a.status = L->status.as<int>();
         rc = search_core(L, a);
         if (rc != XS_OK) break;
@@ -1735,7 +1799,7 @@ extern "C" int xs_diffusion_offline(xs_index* ix, int n_trunc, int kd, double al
         CoreArgs a{};
         a.q32 = ix->db32 + (size_t)r0 * ix->d_pad; a.nq = c; a.k = T; a.prep = true; a.prep_renorm = false;
         a.path = choose_path(ix, c, T);
-        a.tmap_a = (a.path == PATH_GEMM) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
+        a.tmap_a = (a.path == PATH_GEMM && ix->db16) ? &ix->tmap_db_a : nullptr; a.a_row0 = r0; a.self_base = r0;
         a.out_idx = ix->out_idx.as<int64_t>(); a.out_score = ix->out_score.as<float>(); a.status = ix->status.as<int>();
         XS_TRY(search_core(ix, a));
         total.n_queries += c; total.gpu_launches += ix->stats.gpu_launches; total.path = ix->stats.path;

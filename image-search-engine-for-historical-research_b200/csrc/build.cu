@@ -438,22 +438,25 @@ void launch_finish_rows(float* rows32, __nv_bfloat16* rows16, int64_t rows, int 
 }
 
 // ---- tiled bf16 copy ---------------------------------------------------------------------------------
-__global__ void tile_db16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n_pad, int d_pad) {
-    // one thread per 16-byte chunk: row r, k-block kb, chunk c (8 chunks of 8 bf16 per 128-byte k-block row)
+__global__ void tile_db16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t r0, int64_t rows, int d_pad) {
+    // one thread per 16-byte chunk: row r0 + rl of the database = row rl of `src`, k-block kb, chunk c (8 chunks of 8 bf16
+    // per 128-byte k-block row)
     const int chunks_per_row = d_pad >> 3;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pad * chunks_per_row) return;
-    const int64_t r = i / chunks_per_row;
-    const int cc = (int)(i - r * chunks_per_row);
+    if (i >= rows * chunks_per_row) return;
+    const int64_t rl = i / chunks_per_row;
+    const int cc = (int)(i - rl * chunks_per_row);
+    const int64_t r = r0 + rl;
     const int kb = cc >> 3, c = cc & 7;
     const int KB = d_pad >> 6;
     const int64_t out = ((((r >> 8) * KB + kb) << 8) + (r & 255)) * 8 + c;
     dst[out] = src[i];
 }
 
-void launch_tile_db16(const __nv_bfloat16* db16, __nv_bfloat16* db16t, int64_t n_pad, int d_pad, cudaStream_t st) {
-    const int64_t total = n_pad * (d_pad >> 3);
-    tile_db16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(db16), reinterpret_cast<uint4*>(db16t), n_pad, d_pad);
+void launch_tile_db16(const __nv_bfloat16* rows16, __nv_bfloat16* db16t, int64_t r0, int64_t rows, int d_pad, cudaStream_t st) {
+    const int64_t total = rows * (d_pad >> 3);
+    if (total <= 0) return;
+    tile_db16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(rows16), reinterpret_cast<uint4*>(db16t), r0, rows, d_pad);
 }
 
 // ---- AQE query construction ------------------------------------------------------------------------

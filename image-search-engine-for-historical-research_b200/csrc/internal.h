@@ -48,13 +48,14 @@ void launch_aqe_queries(const float* db32, const int64_t* top_ids, int64_t nq, i
 
 // Tiled copy of the bf16 database for the GEMM's B operand: [n_pad/256][d_pad/64][256][64], so that every TMA box
 // (128 or 256 rows x 64 columns) is one contiguous 16/32 KB run in HBM instead of 128-byte pieces 4 KB apart.
-void launch_tile_db16(const __nv_bfloat16* db16, __nv_bfloat16* db16t, int64_t n_pad, int d_pad, cudaStream_t st);
+// `rows16`: `rows` row-major bf16 rows that are rows r0 .. r0 + rows of the database.
+void launch_tile_db16(const __nv_bfloat16* rows16, __nv_bfloat16* db16t, int64_t r0, int64_t rows, int d_pad, cudaStream_t st);
 
 // ---- scan.cu ------------------------------------------------------------------------------------
 // Batch-1 HBM scan: scores[q][row] = <db16[row], q32[q]>, fp32 accumulate.  Both scoring kernels also
 // add every score to the linear histogram ghist[q][.] (zeroed by the caller).
 //   The histogram is linear over [-B, B], B = ||q|| max||v||; the kernels publish B per query in bounds[q] for scores_to_pools.
-void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
+void launch_scan_scores(const __nv_bfloat16* db16, bool tiled, const float* q32, int nq, int64_t n, int d_pad,
                         float* scores, int64_t score_pitch, uint32_t* ghist, const DevStats* stats, float* bounds, int num_sms, cudaStream_t st);
 // Exact scoring: scores[q][row] = fp32( sum_fp64 db32[row][i] * q32[q][i] ).  Any nq (looped in 4s).
 void launch_exact_scores(const float* db32, const float* q32, int nq, int64_t n, int d_pad,

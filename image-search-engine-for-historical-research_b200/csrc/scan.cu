@@ -132,23 +132,118 @@ scan_scores_kernel(const uint4* __restrict__ db16, const float* __restrict__ q32
         if (sh[i]) atomicAdd(&ghist[i], sh[i]);
 }
 
-void launch_scan_scores(const __nv_bfloat16* db16, const float* q32, int nq, int64_t n, int d_pad,
+// The same pass over the TILED twin (tile_db16_kernel: [row >> 8][k-block][row & 255][64 bf16], what the GEMM's TMA boxes
+// read), so an index that keeps only the twin still serves the batch-1 path.  Per k-block, 16 consecutive rows are 2 KB
+// contiguous: a warp owns groups of 16 rows and issues four 512-byte loads per k-block (load j: rows 4j .. 4j+3, lane l
+// holds row 4j + (l >> 3), 16-byte chunk l & 7), two k-blocks in flight -- the same 8 x 16 B outstanding per lane as above.
+// A row's sum is spread over the 8 lanes that share l >> 3.
+template <int QB>
+__global__ void __launch_bounds__(256, 2)
+scan_scores_tiled_kernel(const uint4* __restrict__ db16t, const float* __restrict__ q32, int64_t n, int d_pad,
+                         float* __restrict__ scores, int64_t pitch, uint32_t* __restrict__ ghist, const DevStats* __restrict__ stats,
+                         float* __restrict__ bounds) {
+    extern __shared__ float qs[];                       // [QB][d_pad] query rows | [QB][HIST_BINS] score histogram
+    __shared__ double red[QB * 8];
+    pdl_wait();
+    uint32_t* sh = reinterpret_cast<uint32_t*>(qs + QB * d_pad);
+    for (int i = threadIdx.x; i < QB * d_pad; i += blockDim.x) qs[i] = q32[i];
+    for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    float inv[QB];
+    query_bounds<QB>(qs, d_pad, stats, red, bounds, inv);
+    constexpr int G = 16;                               // rows per warp group
+    const int kbs = d_pad >> 6;                         // 64-column k-blocks
+    const int lane = lane_id();
+    const int sub = lane >> 3;                          // row within a 4-row load
+    const float* qlane = qs + (lane & 7) * 8;           // this lane's 8 columns of every k-block
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t groups = (n + G - 1) / G;
+    for (int64_t g = gw; g < groups; g += nw) {
+        const int64_t row0 = g * G;                     // rows >= n are zero padding (n_pad is a multiple of 256)
+        const uint4* base = db16t + (((row0 >> 8) * kbs) << 11) + ((row0 & 255) << 3) + lane;    // k-block 0; next k-block: + 2048 chunks
+        float acc[4][QB];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < QB; ++b) acc[j][b] = 0.f;
+        for (int kb = 0; kb < kbs; kb += 2) {
+            uint4 w0[4], w1[4];
+            const bool two = (kb + 1) < kbs;
+            const uint4* p = base + ((int64_t)kb << 11);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w0[j] = ld_stream_u4(p + j * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w1[j] = two ? ld_stream_u4(p + 2048 + j * 32) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                const float4 qa = *reinterpret_cast<const float4*>(qlane + b * d_pad + kb * 64);
+                const float4 qb = *reinterpret_cast<const float4*>(qlane + b * d_pad + kb * 64 + 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = acc[j][b];
+                    a = fmaf(bf16lo(w0[j].x), qa.x, a); a = fmaf(bf16hi(w0[j].x), qa.y, a);
+                    a = fmaf(bf16lo(w0[j].y), qa.z, a); a = fmaf(bf16hi(w0[j].y), qa.w, a);
+                    a = fmaf(bf16lo(w0[j].z), qb.x, a); a = fmaf(bf16hi(w0[j].z), qb.y, a);
+                    a = fmaf(bf16lo(w0[j].w), qb.z, a); a = fmaf(bf16hi(w0[j].w), qb.w, a);
+                    acc[j][b] = a;
+                }
+                if (two) {
+                    const float4 qc = *reinterpret_cast<const float4*>(qlane + b * d_pad + kb * 64 + 64);
+                    const float4 qd = *reinterpret_cast<const float4*>(qlane + b * d_pad + kb * 64 + 68);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a = acc[j][b];
+                        a = fmaf(bf16lo(w1[j].x), qc.x, a); a = fmaf(bf16hi(w1[j].x), qc.y, a);
+                        a = fmaf(bf16lo(w1[j].y), qc.z, a); a = fmaf(bf16hi(w1[j].y), qc.w, a);
+                        a = fmaf(bf16lo(w1[j].z), qd.x, a); a = fmaf(bf16hi(w1[j].z), qd.y, a);
+                        a = fmaf(bf16lo(w1[j].w), qd.z, a); a = fmaf(bf16hi(w1[j].w), qd.w, a);
+                        acc[j][b] = a;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                float s = acc[j][b];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                const int64_t row = row0 + 4 * j + sub;
+                if ((lane & 7) == 0 && row < n) {
+                    scores[(int64_t)b * pitch + row] = s;
+                    atomicAdd(&sh[b * HIST_BINS + score_bin(s, inv[b])], 1u);
+                }
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QB * HIST_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+void launch_scan_scores(const __nv_bfloat16* db16, bool tiled, const float* q32, int nq, int64_t n, int d_pad,
                         float* scores, int64_t score_pitch, uint32_t* ghist, const DevStats* stats, float* bounds, int num_sms, cudaStream_t st) {
     const int grid = num_sms * 2;
     const uint4* db = reinterpret_cast<const uint4*>(db16);
     const size_t per_q = (size_t)d_pad * sizeof(float) + HIST_BINS * sizeof(uint32_t);
     cudaFuncSetAttribute(scan_scores_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per_q));
     cudaFuncSetAttribute(scan_scores_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_q);
+    cudaFuncSetAttribute(scan_scores_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per_q));
+    cudaFuncSetAttribute(scan_scores_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_q);
     for (int q0 = 0; q0 < nq;) {
         const int left = nq - q0;
         const float* q = q32 + (int64_t)q0 * d_pad;
         float* s = scores + (int64_t)q0 * score_pitch;
         uint32_t* h = ghist + (size_t)q0 * HIST_BINS;
         if (left >= 2) {
-            launch_pdl(scan_scores_kernel<2, 4>, dim3(grid), dim3(256), 2 * per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
+            if (tiled) launch_pdl(scan_scores_tiled_kernel<2>, dim3(grid), dim3(256), 2 * per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
+            else launch_pdl(scan_scores_kernel<2, 4>, dim3(grid), dim3(256), 2 * per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 2;
         } else {
-            launch_pdl(scan_scores_kernel<1, 4>, dim3(grid), dim3(256), per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
+            if (tiled) launch_pdl(scan_scores_tiled_kernel<1>, dim3(grid), dim3(256), per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
+            else launch_pdl(scan_scores_kernel<1, 4>, dim3(grid), dim3(256), per_q, st, db, q, n, d_pad, s, score_pitch, h, stats, bounds + q0);
             q0 += 1;
         }
     }

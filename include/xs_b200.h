@@ -66,6 +66,11 @@ XS_API int xs_device_count(int* count);
  *                    structure in the data (the exact stage always uses the unrotated fp32 values)
  *   "rotation_seed"  the 32-bit seed of that rotation; results never depend on it, only which inputs could defeat
  *                    the statistical certificate does
+ *   "compact"        1 (default; XS_KEEP_ROWMAJOR=1 in the environment = 0): keep ONE bf16 copy of the database, in
+ *                    the tiled layout the GEMM's TMA boxes read; the batch-1 scan reads it too and xs_self_knn sends
+ *                    its rows through the ordinary query preparation.  0: also keep the row-major copy (2 * d_pad
+ *                    bytes per row more).  Applies to xs_index_create* and to xs_index_load of a two-copy image; an
+ *                    image written by a compact index always loads compact.  Results do not depend on it.
  */
 XS_API int xs_config_set(const char* name, double value);
 
@@ -95,8 +100,9 @@ XS_API int xs_index_create_dev(const float* db_dev, int64_t n, int d,
 XS_API int xs_index_destroy(xs_index* index);
 
 /*
- * On-disk image of an index: the arrays exactly as they live in HBM (fp32 rows, bf16 rows of the rotated vectors and their
- * tiled twin, the statistics behind the error band, the rotation seed).
+ * On-disk image of an index: the arrays exactly as they live in HBM (fp32 rows, the bf16 rotated vectors in the tiled
+ * layout -- plus their row-major form when the index keeps it, see "compact" --, the statistics behind the error band,
+ * the rotation seed): 6 * d_pad bytes per row for a compact index.
  *   replaces: save_path_feature / load_path_features pickles and the .pt distractor file      src/utils/general.py:67-92
  *             + the unpickle / concatenate / transpose of every start-up                       src/online.py:93-102
  * xs_index_load is a straight upload -- reader threads fill a ring of pinned buffers, one cudaMemcpyAsync per 32 MB slice,
@@ -308,6 +314,7 @@ XS_API int xs_diffusion_cg(int device, const int64_t* indptr, const int32_t* ind
  *   "timing"       int    1 = record CUDA events so xs_index_stats reports ms_coarse/ms_total (0)
  *   "pair_mode"    int    1 = CTA-pair (cta_group::2) GEMM shape for batches > 128 queries   (1)
  *   "sample_pass"  int    1 = threshold bootstrap pass before the GEMM                    (1)
+ *   "scan_tiled"   int    1 = the batch-1 scan reads the tiled bf16 array (always, on a compact index)   (1)
  *   "self_lanes"   int    2 = xs_self_knn alternates its batches between the index and an internal clone (1)
  */
 XS_API int xs_set_param(xs_index* index, const char* name, double value);
