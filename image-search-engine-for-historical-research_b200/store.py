@@ -19,7 +19,7 @@ import numpy as np
 
 ROWS_FILE = "rows.npy"
 PATHS_FILE = "paths.json"
-INDEX_FILE = "index.xsb"          # device image: fp32 rows + bf16 rows + tiled twin, as they live in HBM (xs_index_save)
+INDEX_FILE = "index.xsb"          # device image: fp32 rows + tiled bf16 rows, as they live in HBM (xs_index_save)
 
 
 def save_store(directory: str, vecs, paths=None, chunk: int = 65536) -> str:
