@@ -228,10 +228,19 @@ void launch_scan_scores(const __nv_bfloat16* db16, bool tiled, const float* q32,
     const int grid = num_sms * 2;
     const uint4* db = reinterpret_cast<const uint4*>(db16);
     const size_t per_q = (size_t)d_pad * sizeof(float) + HIST_BINS * sizeof(uint32_t);
-    cudaFuncSetAttribute(scan_scores_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per_q));
-    cudaFuncSetAttribute(scan_scores_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_q);
-    cudaFuncSetAttribute(scan_scores_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * per_q));
-    cudaFuncSetAttribute(scan_scores_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_q);
+    {   // dynamic shared memory limit: raised once per device (and again only if a wider index shows up), not on every query
+        static int attr_bytes[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int need = (int)(2 * per_q);
+        if (dev < 0 || dev >= 64 || attr_bytes[dev] < need) {
+            cudaFuncSetAttribute(scan_scores_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+            cudaFuncSetAttribute(scan_scores_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+            cudaFuncSetAttribute(scan_scores_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+            cudaFuncSetAttribute(scan_scores_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+            if (dev >= 0 && dev < 64) attr_bytes[dev] = need;
+        }
+    }
     for (int q0 = 0; q0 < nq;) {
         const int left = nq - q0;
         const float* q = q32 + (int64_t)q0 * d_pad;
