@@ -15,7 +15,8 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("XS_NO_TILED", "0") not in ("", "0"), reason="XS_NO_TILED=1: no tiled array, nothing to compact")]
 
 
 @pytest.fixture()
